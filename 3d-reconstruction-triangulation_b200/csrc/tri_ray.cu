@@ -1,0 +1,156 @@
+// tri_ray.cu -- kernel 2: fused pixel-ray generation + quaternion rotation + nearest-point-to-rays
+// solve (RayTriangulator::triangulatePoints, src/RayTriangulator.cpp:51-107) for sm_100a.
+//
+// Reference: ray_i = (camera position, q (0, normalise(v_i)) q*) with v_i the pixel ray of
+// Triangulator.cpp:27-44; the point minimises S(p) = sum_i r_i(p)^2, r_i = |dir_i x (p - o_i)|
+// (Triangulator.cpp:3-9, RayTriangulator.cpp:16-26), found by cv::LMSolver on the n scalar residuals
+// r_i with a central-difference Jacobian.  S is QUADRATIC in p:
+//     S(p) = p^T M p - 2 c^T p + k,  M = sum_i (|d_i|^2 I - d_i d_i^T),  c = sum_i M_i o_i.
+// The fused kernel therefore runs Levenberg-Marquardt on the 3n residual components
+// e_i = dir_i x (p - o_i), whose Jacobian [dir_i]_x is analytic and exact: J^T J = M, J^T e = M p - c.
+// Same objective, same minimiser, same cv::LMSolver damping schedule -- but M, c, k are accumulated
+// once per frame in registers (~40 FMA per view, rig constants from the constant bank) and each LM
+// iteration is O(1).  (The scalar-residual form the reference uses has a rank-2 J^T J for two views,
+// which is why its LM crawls there)  opt bit 0: 1 = LM loop, 0 = closed form
+// p = M^-1 c (one exact Newton step).  The trajectory-exact emulation of the reference's LM lives in
+// tri_ray_ref.cu.
+#include <float.h>
+
+#include "tri_batch.cuh"
+
+namespace tri {
+
+template <typename T_>
+struct RayPolicy {
+  using T = T_;
+  using Rig = RayFold<T>;
+  struct Acc {
+    T uu[6] = {0, 0, 0, 0, 0, 0};  // sum u u^T / |v|^2        (M = tr I - uu)
+    T cu[3] = {0, 0, 0};           // sum u (s . ob)           (c = cn - cu)
+    T cn[3] = {0, 0, 0};           // sum n4 ob
+    T so[3] = {0, 0, 0};           // sum ob                   (LM start = mean of origins, :90-98)
+    T tr = 0, ku = 0, kn = 0;      // k = kn - ku
+  };
+  // u (unnormalised rotated ray) and 1/|v|^2 of one view
+  static __device__ __forceinline__ void ray(const Rig& r, int c, T x, T y, T (&u)[3], T& inv) {
+    u[0] = r.U0[c][0] * x + (r.U1[c][0] * y + r.U2[c][0]);
+    u[1] = r.U0[c][1] * x + (r.U1[c][1] * y + r.U2[c][1]);
+    u[2] = r.U0[c][2] * x + (r.U1[c][2] * y + r.U2[c][2]);
+    T vx = r.ax[c] * x + r.bx[c], vy = r.ay[c] * y + r.by[c];
+    inv = T(1) / (vx * vx + (vy * vy + r.dd[c]));
+  }
+  static __device__ __forceinline__ void add(const Rig& r, int c, T x, T y, Acc& a) {
+    T u[3], inv;
+    ray(r, c, x, y, u, inv);
+    T s0 = u[0] * inv, s1 = u[1] * inv, s2 = u[2] * inv;
+    a.uu[0] += s0 * u[0]; a.uu[1] += s0 * u[1]; a.uu[2] += s0 * u[2];
+    a.uu[3] += s1 * u[1]; a.uu[4] += s1 * u[2]; a.uu[5] += s2 * u[2];
+    T t = s0 * r.ob[c][0] + s1 * r.ob[c][1] + s2 * r.ob[c][2];
+    T w = u[0] * r.ob[c][0] + u[1] * r.ob[c][1] + u[2] * r.ob[c][2];
+    a.cu[0] += u[0] * t; a.cu[1] += u[1] * t; a.cu[2] += u[2] * t;
+    a.ku += t * w;
+    a.cn[0] += r.n4ob[c][0]; a.cn[1] += r.n4ob[c][1]; a.cn[2] += r.n4ob[c][2];
+    a.so[0] += r.ob[c][0]; a.so[1] += r.ob[c][1]; a.so[2] += r.ob[c][2];
+    a.tr += r.n4[c];
+    a.kn += r.n4ob2[c];
+  }
+  static __device__ __forceinline__ T quad(const T (&M)[6], const T (&c)[3], T k, const T (&p)[3]) {
+    T Mp0 = M[0] * p[0] + M[1] * p[1] + M[2] * p[2];
+    T Mp1 = M[1] * p[0] + M[3] * p[1] + M[4] * p[2];
+    T Mp2 = M[2] * p[0] + M[4] * p[1] + M[5] * p[2];
+    return p[0] * (Mp0 - 2 * c[0]) + p[1] * (Mp1 - 2 * c[1]) + p[2] * (Mp2 - 2 * c[2]) + k;
+  }
+  static __device__ __forceinline__ void solve(const Rig&, const Acc& a, int n, T (&X)[3], int opt, int& iters) {
+    const T M[6] = {a.tr - a.uu[0], -a.uu[1], -a.uu[2], a.tr - a.uu[3], -a.uu[4], a.tr - a.uu[5]};
+    const T c[3] = {a.cn[0] - a.cu[0], a.cn[1] - a.cu[1], a.cn[2] - a.cu[2]};
+    if (!(opt & 1)) {
+      solve_sym3<T>(M, c, X);
+      iters = 1;
+      return;
+    }
+    // cv::LMSolver's loop (calib3d levmarq.cpp: lambda = 1, lc = 0.75, Rlo/Rhi = 0.25/0.75, diagonal
+    // scaling fixed at the start point, eps = FLT_EPSILON, 1000 iterations: RayTriangulator.h:9-11,
+    // RayTriangulator.cpp:100-104) on the analytic normal equations A = M, v = M p - c.
+    const T k = a.kn - a.ku;
+    const T rn = T(1) / (T)n;
+    T p[3] = {a.so[0] * rn, a.so[1] * rn, a.so[2] * rn};
+    const T D[3] = {M[0], M[3], M[5]};
+    T lambda = 1, lc = T(0.75);
+    T S = quad(M, c, k, p);
+    T g[3] = {M[0] * p[0] + M[1] * p[1] + M[2] * p[2] - c[0], M[1] * p[0] + M[3] * p[1] + M[4] * p[2] - c[1],
+              M[2] * p[0] + M[4] * p[1] + M[5] * p[2] - c[2]};
+    int it = 0;
+    for (;;) {
+      const T Ap[6] = {M[0] + lambda * D[0], M[1], M[2], M[3] + lambda * D[1], M[4], M[5] + lambda * D[2]};
+      T d[3];
+      solve_sym3<T>(Ap, g, d);
+      const T pd[3] = {p[0] - d[0], p[1] - d[1], p[2] - d[2]};
+      const T Sd = quad(M, c, k, pd);
+      const T Md0 = M[0] * d[0] + M[1] * d[1] + M[2] * d[2], Md1 = M[1] * d[0] + M[3] * d[1] + M[4] * d[2],
+              Md2 = M[2] * d[0] + M[4] * d[1] + M[5] * d[2];
+      const T dS = d[0] * (2 * g[0] - Md0) + d[1] * (2 * g[1] - Md1) + d[2] * (2 * g[2] - Md2);
+      const T R = (S - Sd) / (fabs(dS) > (T)DBL_EPSILON ? dS : T(1));
+      if (R > T(0.75)) {
+        lambda *= T(0.5);
+        if (lambda < lc) lambda = 0;
+      } else if (R < T(0.25)) {
+        const T t = d[0] * g[0] + d[1] * g[1] + d[2] * g[2];
+        T nu = (Sd - S) / (fabs(t) > (T)DBL_EPSILON ? t : T(1)) + 2;
+        nu = fmin(fmax(nu, T(2)), T(10));
+        if (lambda == 0) {  // re-inflate from diag(M^-1)
+          const T c00 = M[3] * M[5] - M[4] * M[4], c11 = M[0] * M[5] - M[2] * M[2], c22 = M[0] * M[3] - M[1] * M[1];
+          const T det = M[0] * c00 + M[1] * (M[2] * M[4] - M[1] * M[5]) + M[2] * (M[1] * M[4] - M[2] * M[3]);
+          const T mx = fmax(fmax(fabs(c00 / det), fabs(c11 / det)), fmax(fabs(c22 / det), (T)DBL_EPSILON));
+          lambda = lc = T(1) / mx;
+          nu *= T(0.5);
+        }
+        lambda *= nu;
+      }
+      if (Sd < S) {
+        S = Sd;
+        p[0] = pd[0]; p[1] = pd[1]; p[2] = pd[2];
+        g[0] -= Md0; g[1] -= Md1; g[2] -= Md2;  // M (p - d) - c
+      }
+      it++;
+      const T dmax = fmax(fabs(d[0]), fmax(fabs(d[1]), fabs(d[2])));
+      if (!(it < 1000 && dmax >= (T)FLT_EPSILON)) break;
+    }
+    X[0] = p[0]; X[1] = p[1]; X[2] = p[2];
+    iters = it;
+  }
+  // r_i = |dir_i x (p - o_i)| (Triangulator.cpp:3-9); the reported error is the mean (RayTriangulator.cpp:26)
+  static __device__ __forceinline__ T residual(const Rig& r, int c, T x, T y, const T (&X)[3]) {
+    T u[3], inv;
+    ray(r, c, x, y, u, inv);
+    const T w0 = X[0] - r.ob[c][0], w1 = X[1] - r.ob[c][1], w2 = X[2] - r.ob[c][2];
+    const T c0 = u[1] * w2 - u[2] * w1, c1 = u[2] * w0 - u[0] * w2, c2 = u[0] * w1 - u[1] * w0;
+    return sqrt((c0 * c0 + c1 * c1 + c2 * c2) * inv);
+  }
+  static __device__ __forceinline__ double error(T sum, int n) { return (double)sum / (double)n; }
+  static __device__ __forceinline__ void to_world(const Rig& r, T (&X)[3]) {
+    X[0] += r.origin[0]; X[1] += r.origin[1]; X[2] += r.origin[2];
+  }
+};
+
+cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt, const RayFold<double>& r64,
+                            const RayFold<float>& r32, const void* d_xy, int n_use, int64_t n_frames,
+                            int64_t cam_stride, const BatchOut& out) {
+  if (n_frames <= 0) return cudaSuccess;
+  using P32 = RayPolicy<float>;
+  using P64 = RayPolicy<double>;
+  const int opt = lm ? 1 : 0;
+  if (f32) {  // FP32: closed form only (the gain ratio of the LM loop needs S to ~1e-9 relative)
+    switch (pixfmt) {
+      case PIX_F32: return launch_batch_policy<P32, PIX_F32>(ctx, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case PIX_F64: return launch_batch_policy<P32, PIX_F64>(ctx, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      default: return launch_batch_policy<P32, PIX_U16>(ctx, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+    }
+  }
+  switch (pixfmt) {
+    case PIX_F32: return launch_batch_policy<P64, PIX_F32>(ctx, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+    case PIX_F64: return launch_batch_policy<P64, PIX_F64>(ctx, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+    default: return launch_batch_policy<P64, PIX_U16>(ctx, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+  }
+}
+
+}  // namespace tri
