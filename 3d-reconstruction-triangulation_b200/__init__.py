@@ -247,9 +247,9 @@ class Engine:
         self.device = int(device)
 
     def close(self):
-        if getattr(self, "_h", None):
-            lib().tri_destroy(self._h)
-            self._h = None
+        if getattr(self, "_h", None) and _lib is not None:
+            _lib.tri_destroy(self._h)
+        self._h = None
 
     __del__ = close
 

@@ -154,8 +154,8 @@ static int check_batch_args(tri_engine* e, int mode, unsigned flags, const void*
                             int64_t cam_stride, const tri_batch_out* out, int* n_use) {
   if (!e) return fail(TRI_ERR_ARG, "null engine");
   if (mode != TRI_MATRIX && mode != TRI_RAY) return fail(TRI_ERR_ARG, "mode must be TRI_MATRIX or TRI_RAY");
-  if (!out || (!out->xyz_f32 && !out->xyz_f64)) return fail(TRI_ERR_ARG, "no xyz output buffer");
   if (n_frames < 0 || n_point_cams < 0) return fail(TRI_ERR_ARG, "negative size");
+  if (!out || (n_frames > 0 && !out->xyz_f32 && !out->xyz_f64)) return fail(TRI_ERR_ARG, "no xyz output buffer");
   if (n_frames > 0 && !xy) return fail(TRI_ERR_ARG, "null pixel buffer");
   if (cam_stride < n_frames) return fail(TRI_ERR_DIM, "Every camera should have the same number of points");
   if (mode == TRI_MATRIX) {
@@ -272,6 +272,7 @@ int tri_triangulate_points_device(tri_engine* e, int mode, unsigned flags, const
   int st = check_batch_args(e, mode, flags, d_xy, n_point_cams, n_frames, cam_stride, d_out, &n_use);
   if (st != TRI_OK) return st;
   if ((st = pix_format(flags, &fmt)) != TRI_OK) return st;
+  if (n_frames == 0) return TRI_OK;
   DeviceGuard g(e->device);
   BatchOut out{d_out->xyz_f32, d_out->xyz_f64, d_out->mask, d_out->err, d_out->iters};
   if (n_use == 0 && n_frames > 0) {  // no rows at all: every frame has too few views

@@ -73,93 +73,116 @@ __device__ __forceinline__ void fetch1(const char* row, int64_t f, T& x, T& y, b
   }
 }
 
-// ---- two frames per thread; NC > 0 unrolls the camera loop and keeps every pixel in registers ----
-template <class S, int NC, int PIX>
-__global__ void __launch_bounds__(BATCH_THREADS)
-batch_pairs_kernel(const __grid_constant__ typename S::Rig rig, const char* __restrict__ xy, int64_t row_bytes,
-                   int64_t n_pairs, int n_use, BatchOut out, int opt, unsigned long long* first_bad, int64_t frame_base) {
-  using T = typename S::T;
-  __shared__ __align__(16) float tile[BATCH_THREADS * 6];
-  const int64_t block_pair0 = (int64_t)blockIdx.x * BATCH_THREADS;
-  const int64_t pair = block_pair0 + threadIdx.x;
-  const int nc = NC > 0 ? NC : n_use;
-  T X0[3] = {0, 0, 0}, X1[3] = {0, 0, 0};
+// ---- FPT (1 or 2) consecutive frames per thread; NC > 0 unrolls the camera loop and keeps every
+// pixel in registers.  FPT = 2 needs 16-byte aligned camera rows (8 for ushort2). ----
+template <typename T, int PIX, int FPT>
+struct Views {
+  T x[FPT], y[FPT];
+  bool v[FPT];
+};
 
-  if (pair < n_pairs) {
-    typename S::Acc a0, a1;
-    uint32_t mask0 = 0, mask1 = 0;
-    T e0 = 0, e1 = 0;
-    int it0 = 0, it1 = 0;
+template <typename T, int PIX, int FPT>
+__device__ __forceinline__ Views<T, PIX, FPT> fetch(const char* row, int64_t group) {
+  Views<T, PIX, FPT> r;
+  if constexpr (FPT == 2) {
+    View2<T> w = fetch2<T, PIX>(row, group);
+    r.x[0] = w.x0; r.y[0] = w.y0; r.v[0] = w.v0; r.x[1] = w.x1; r.y[1] = w.y1; r.v[1] = w.v1;
+  } else {
+    fetch1<T, PIX>(row, group, r.x[0], r.y[0], r.v[0]);
+  }
+  return r;
+}
+
+template <class S, int NC, int PIX, int FPT, int MINB>
+__global__ void __launch_bounds__(BATCH_THREADS, MINB)
+batch_kernel(const __grid_constant__ typename S::Rig rig, const char* __restrict__ xy, int64_t row_bytes,
+             int64_t n_groups, int n_use, BatchOut out, int opt, unsigned long long* first_bad, int64_t frame_base) {
+  using T = typename S::T;
+  __shared__ __align__(16) float tile[BATCH_THREADS * 3 * FPT];
+  const int64_t block_group0 = (int64_t)blockIdx.x * BATCH_THREADS;
+  const int64_t group = block_group0 + threadIdx.x;
+  const int nc = NC > 0 ? NC : n_use;
+  T X[FPT][3];
+#pragma unroll
+  for (int j = 0; j < FPT; j++) X[j][0] = X[j][1] = X[j][2] = 0;
+
+  if (group < n_groups) {
+    typename S::Acc acc[FPT];
+    uint32_t mask[FPT];
+    T e[FPT];
+    int it[FPT], n[FPT];
+#pragma unroll
+    for (int j = 0; j < FPT; j++) { mask[j] = 0; e[j] = 0; it[j] = 0; }
     if constexpr (NC > 0) {
-      View2<T> w[NC];
+      Views<T, PIX, FPT> w[NC];
 #pragma unroll
-      for (int c = 0; c < NC; c++) w[c] = fetch2<T, PIX>(xy + c * row_bytes, pair);
+      for (int c = 0; c < NC; c++) w[c] = fetch<T, PIX, FPT>(xy + c * row_bytes, group);  // all loads in flight
 #pragma unroll
-      for (int c = 0; c < NC; c++) {
-        if (w[c].v0) { S::add(rig, c, w[c].x0, w[c].y0, a0); mask0 |= 1u << c; }
-        if (w[c].v1) { S::add(rig, c, w[c].x1, w[c].y1, a1); mask1 |= 1u << c; }
+      for (int c = 0; c < NC; c++)
+#pragma unroll
+        for (int j = 0; j < FPT; j++)
+          if (w[c].v[j]) { S::add(rig, c, w[c].x[j], w[c].y[j], acc[j]); mask[j] |= 1u << c; }
+#pragma unroll
+      for (int j = 0; j < FPT; j++) {
+        n[j] = __popc(mask[j]);
+        if (n[j] >= 2) S::solve(rig, acc[j], n[j], X[j], opt, it[j]);
       }
-      const int n0 = __popc(mask0), n1 = __popc(mask1);
-      if (n0 >= 2) S::solve(rig, a0, n0, X0, opt, it0);
-      if (n1 >= 2) S::solve(rig, a1, n1, X1, opt, it1);
       if (out.err) {
 #pragma unroll
-        for (int c = 0; c < NC; c++) {
-          if (w[c].v0) e0 += S::residual(rig, c, w[c].x0, w[c].y0, X0);
-          if (w[c].v1) e1 += S::residual(rig, c, w[c].x1, w[c].y1, X1);
-        }
+        for (int c = 0; c < NC; c++)
+#pragma unroll
+          for (int j = 0; j < FPT; j++)
+            if (w[c].v[j]) e[j] += S::residual(rig, c, w[c].x[j], w[c].y[j], X[j]);
       }
     } else {
 #pragma unroll 4
       for (int c = 0; c < nc; c++) {
-        View2<T> w = fetch2<T, PIX>(xy + c * row_bytes, pair);
-        if (w.v0) { S::add(rig, c, w.x0, w.y0, a0); mask0 |= 1u << c; }
-        if (w.v1) { S::add(rig, c, w.x1, w.y1, a1); mask1 |= 1u << c; }
+        Views<T, PIX, FPT> w = fetch<T, PIX, FPT>(xy + c * row_bytes, group);
+#pragma unroll
+        for (int j = 0; j < FPT; j++)
+          if (w.v[j]) { S::add(rig, c, w.x[j], w.y[j], acc[j]); mask[j] |= 1u << c; }
       }
-      const int n0 = __popc(mask0), n1 = __popc(mask1);
-      if (n0 >= 2) S::solve(rig, a0, n0, X0, opt, it0);
-      if (n1 >= 2) S::solve(rig, a1, n1, X1, opt, it1);
+#pragma unroll
+      for (int j = 0; j < FPT; j++) {
+        n[j] = __popc(mask[j]);
+        if (n[j] >= 2) S::solve(rig, acc[j], n[j], X[j], opt, it[j]);
+      }
       if (out.err) {
         for (int c = 0; c < nc; c++) {
-          View2<T> w = fetch2<T, PIX>(xy + c * row_bytes, pair);
-          if (w.v0) e0 += S::residual(rig, c, w.x0, w.y0, X0);
-          if (w.v1) e1 += S::residual(rig, c, w.x1, w.y1, X1);
+          Views<T, PIX, FPT> w = fetch<T, PIX, FPT>(xy + c * row_bytes, group);
+#pragma unroll
+          for (int j = 0; j < FPT; j++)
+            if (w.v[j]) e[j] += S::residual(rig, c, w.x[j], w.y[j], X[j]);
         }
       }
     }
-    const int n0 = __popc(mask0), n1 = __popc(mask1);
-    if (n0 >= 2) S::to_world(rig, X0);
-    else atomicMin(first_bad, (unsigned long long)(frame_base + 2 * pair));
-    if (n1 >= 2) S::to_world(rig, X1);
-    else atomicMin(first_bad, (unsigned long long)(frame_base + 2 * pair + 1));
-
-    if (out.xyz_f64) {
-      double* o = out.xyz_f64 + 6 * pair;
-      o[0] = X0[0]; o[1] = X0[1]; o[2] = X0[2]; o[3] = X1[0]; o[4] = X1[1]; o[5] = X1[2];
+#pragma unroll
+    for (int j = 0; j < FPT; j++) {
+      const int64_t f = FPT * group + j;
+      if (n[j] >= 2) S::to_world(rig, X[j]);
+      else atomicMin(first_bad, (unsigned long long)(frame_base + f));
+      if (out.xyz_f64) { double* o = out.xyz_f64 + 3 * f; o[0] = X[j][0]; o[1] = X[j][1]; o[2] = X[j][2]; }
+      if (out.mask) out.mask[f] = mask[j];
+      if (out.err) out.err[f] = n[j] >= 2 ? S::error(e[j], n[j]) : 0.0;
+      if (out.iters) out.iters[f] = it[j];
     }
-    if (out.mask) reinterpret_cast<uint2*>(out.mask)[pair] = make_uint2(mask0, mask1);
-    if (out.err)
-      reinterpret_cast<double2*>(out.err)[pair] =
-          make_double2(n0 >= 2 ? S::error(e0, n0) : 0.0, n1 >= 2 ? S::error(e1, n1) : 0.0);
-    if (out.iters) reinterpret_cast<int2*>(out.iters)[pair] = make_int2(it0, it1);
   }
 
-  if (out.xyz_f32) {  // uniform branch: 24 B per thread into the tile, the tile out as 16 B vectors
-    float2* t2 = reinterpret_cast<float2*>(tile) + 3 * threadIdx.x;
-    t2[0] = make_float2((float)X0[0], (float)X0[1]);
-    t2[1] = make_float2((float)X0[2], (float)X1[0]);
-    t2[2] = make_float2((float)X1[1], (float)X1[2]);
+  if (out.xyz_f32) {  // uniform branch: 12 B per frame into the tile, the tile out as 16 B vectors
+    float* t = tile + 3 * FPT * threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < FPT; j++) { t[3 * j] = (float)X[j][0]; t[3 * j + 1] = (float)X[j][1]; t[3 * j + 2] = (float)X[j][2]; }
     __syncthreads();
-    const int64_t remaining = n_pairs - block_pair0;
-    float* dst = out.xyz_f32 + 6 * block_pair0;
-    if (remaining >= BATCH_THREADS) {
+    const int64_t remaining = n_groups - block_group0;
+    float* dst = out.xyz_f32 + 3 * FPT * block_group0;
+    if (remaining >= BATCH_THREADS && ((uintptr_t)dst & 15) == 0) {
       float4* d4 = reinterpret_cast<float4*>(dst);
       const float4* s4 = reinterpret_cast<const float4*>(tile);
 #pragma unroll
-      for (int i = threadIdx.x; i < BATCH_THREADS * 6 / 4; i += BATCH_THREADS) __stcs(d4 + i, s4[i]);
+      for (int i = threadIdx.x; i < BATCH_THREADS * 3 * FPT / 4; i += BATCH_THREADS) __stcs(d4 + i, s4[i]);
     } else {
-      const int n = (int)remaining * 6;
-      for (int i = threadIdx.x; i < n; i += BATCH_THREADS) dst[i] = tile[i];
+      const int cnt = (int)(remaining < BATCH_THREADS ? remaining : BATCH_THREADS) * 3 * FPT;
+      for (int i = threadIdx.x; i < cnt; i += BATCH_THREADS) dst[i] = tile[i];
     }
   }
 }
@@ -202,36 +225,33 @@ batch_single_kernel(const __grid_constant__ typename S::Rig rig, const char* __r
   if (out.iters) out.iters[f] = it;
 }
 
-template <class S, int PIX>
+// FPT = frames per thread of the main kernel, MINB = resident blocks per SM asked of ptxas.
+template <class S, int PIX, int FPT, int MINB>
 static cudaError_t launch_batch_policy(const LaunchCtx& ctx, const typename S::Rig& rig, const void* d_xy, int n_use,
                                        int64_t n_frames, int64_t cam_stride, const BatchOut& out, int opt) {
   const char* xy = static_cast<const char*>(d_xy);
   const int64_t row_bytes = cam_stride * pix_bytes(PIX);
-  const int64_t need = PIX == PIX_U16 ? 8 : 16;  // every camera row must start vector-aligned
-  const bool vec = ((uintptr_t)xy % need == 0) && (row_bytes % need == 0) &&
-                   (out.xyz_f32 == nullptr || (uintptr_t)out.xyz_f32 % 16 == 0) &&
-                   (out.mask == nullptr || (uintptr_t)out.mask % 8 == 0) &&
-                   (out.err == nullptr || (uintptr_t)out.err % 16 == 0) &&
-                   (out.iters == nullptr || (uintptr_t)out.iters % 8 == 0);
-  const int64_t n_pairs = vec ? n_frames / 2 : 0;
-  if (n_pairs > 0) {
-    const unsigned grid = (unsigned)((n_pairs + BATCH_THREADS - 1) / BATCH_THREADS);
-#define TRI_CASE(N)                                                                                            \
-  case N:                                                                                                      \
-    batch_pairs_kernel<S, N, PIX><<<grid, BATCH_THREADS, 0, ctx.stream>>>(rig, xy, row_bytes, n_pairs, n_use, \
-                                                                          out, opt, ctx.d_first_bad,           \
-                                                                          ctx.frame_base);                     \
+  const int64_t need = FPT * pix_bytes(PIX);  // every camera row must start vector-aligned
+  const bool vec = FPT == 1 || (((uintptr_t)xy % need == 0) && (row_bytes % need == 0));
+  const int64_t n_groups = vec ? n_frames / FPT : 0;
+  if (n_groups > 0) {
+    const unsigned grid = (unsigned)((n_groups + BATCH_THREADS - 1) / BATCH_THREADS);
+#define TRI_CASE(N)                                                                                              \
+  case N:                                                                                                        \
+    batch_kernel<S, N, PIX, FPT, MINB><<<grid, BATCH_THREADS, 0, ctx.stream>>>(rig, xy, row_bytes, n_groups, n_use, \
+                                                                               out, opt, ctx.d_first_bad,        \
+                                                                               ctx.frame_base);                  \
     break;
     switch (n_use) {
       TRI_CASE(2) TRI_CASE(3) TRI_CASE(4) TRI_CASE(5) TRI_CASE(6) TRI_CASE(7) TRI_CASE(8)
       default:
-        batch_pairs_kernel<S, 0, PIX><<<grid, BATCH_THREADS, 0, ctx.stream>>>(rig, xy, row_bytes, n_pairs, n_use, out,
-                                                                              opt, ctx.d_first_bad, ctx.frame_base);
+        batch_kernel<S, 0, PIX, FPT, MINB><<<grid, BATCH_THREADS, 0, ctx.stream>>>(rig, xy, row_bytes, n_groups, n_use, out,
+                                                                                   opt, ctx.d_first_bad, ctx.frame_base);
     }
 #undef TRI_CASE
     ++*ctx.launches;
   }
-  const int64_t done = 2 * n_pairs;
+  const int64_t done = FPT * n_groups;
   if (done < n_frames) {
     const unsigned grid = (unsigned)((n_frames - done + BATCH_THREADS - 1) / BATCH_THREADS);
     batch_single_kernel<S, PIX><<<grid, BATCH_THREADS, 0, ctx.stream>>>(rig, xy, row_bytes, done, n_frames, n_use, out,

@@ -72,7 +72,7 @@ __device__ __forceinline__ double widen(float f) {
 
 template <typename T> __device__ __forceinline__ T to_real(float v);
 template <> __device__ __forceinline__ float to_real<float>(float v) { return v; }
-template <> __device__ __forceinline__ double to_real<double>(float v) { return widen(v); }
+template <> __device__ __forceinline__ double to_real<double>(float v) { return (double)v; }
 
 // streaming (read-once) vector loads
 __device__ __forceinline__ float4 ld_stream(const float4* p) { return __ldcs(p); }
@@ -84,19 +84,27 @@ __device__ __forceinline__ unsigned ld_stream(const unsigned* p) { return __ldcs
 // Solve the 3x3 symmetric positive definite system M X = v by the adjugate (one reciprocal).
 // M = (m00 m01 m02 m11 m12 m22).  cond(A^T A) <= ~25 on real rigs, so this matches
 // cv::invert(DECOMP_SVD) X = pinv(A) b (MatrixTriangulator.cpp:53-54) to ~1e-15 relative in FP64.
+// Explicit fused multiply-adds everywhere below (and in the policies): the rounding sequence is then
+// fixed by the source, so every kernel variant (vector / scalar path, any camera-count template)
+// returns bit-identical points for the same frame.
+__device__ __forceinline__ double fma_(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
+
 template <typename T>
 __device__ __forceinline__ void solve_sym3(const T M[6], const T v[3], T X[3]) {
-  T c00 = M[3] * M[5] - M[4] * M[4];
-  T c01 = M[2] * M[4] - M[1] * M[5];
-  T c02 = M[1] * M[4] - M[2] * M[3];
-  T c11 = M[0] * M[5] - M[2] * M[2];
-  T c12 = M[1] * M[2] - M[0] * M[4];
-  T c22 = M[0] * M[3] - M[1] * M[1];
-  T det = M[0] * c00 + M[1] * c01 + M[2] * c02;
-  T inv = T(1) / det;
-  X[0] = (c00 * v[0] + c01 * v[1] + c02 * v[2]) * inv;
-  X[1] = (c01 * v[0] + c11 * v[1] + c12 * v[2]) * inv;
-  X[2] = (c02 * v[0] + c12 * v[1] + c22 * v[2]) * inv;
+  const T c00 = fma_(M[3], M[5], -mul_(M[4], M[4]));
+  const T c01 = fma_(M[2], M[4], -mul_(M[1], M[5]));
+  const T c02 = fma_(M[1], M[4], -mul_(M[2], M[3]));
+  const T c11 = fma_(M[0], M[5], -mul_(M[2], M[2]));
+  const T c12 = fma_(M[1], M[2], -mul_(M[0], M[4]));
+  const T c22 = fma_(M[0], M[3], -mul_(M[1], M[1]));
+  const T det = fma_(M[0], c00, fma_(M[1], c01, mul_(M[2], c02)));
+  const T inv = T(1) / det;
+  X[0] = mul_(fma_(c00, v[0], fma_(c01, v[1], mul_(c02, v[2]))), inv);
+  X[1] = mul_(fma_(c01, v[0], fma_(c11, v[1], mul_(c12, v[2]))), inv);
+  X[2] = mul_(fma_(c02, v[0], fma_(c12, v[1], mul_(c22, v[2]))), inv);
 }
 
 }  // namespace tri

@@ -33,32 +33,32 @@ struct RayPolicy {
   };
   // u (unnormalised rotated ray) and 1/|v|^2 of one view
   static __device__ __forceinline__ void ray(const Rig& r, int c, T x, T y, T (&u)[3], T& inv) {
-    u[0] = r.U0[c][0] * x + (r.U1[c][0] * y + r.U2[c][0]);
-    u[1] = r.U0[c][1] * x + (r.U1[c][1] * y + r.U2[c][1]);
-    u[2] = r.U0[c][2] * x + (r.U1[c][2] * y + r.U2[c][2]);
-    T vx = r.ax[c] * x + r.bx[c], vy = r.ay[c] * y + r.by[c];
-    inv = T(1) / (vx * vx + (vy * vy + r.dd[c]));
+    u[0] = fma_(r.U0[c][0], x, fma_(r.U1[c][0], y, r.U2[c][0]));
+    u[1] = fma_(r.U0[c][1], x, fma_(r.U1[c][1], y, r.U2[c][1]));
+    u[2] = fma_(r.U0[c][2], x, fma_(r.U1[c][2], y, r.U2[c][2]));
+    const T vx = fma_(r.ax[c], x, r.bx[c]), vy = fma_(r.ay[c], y, r.by[c]);
+    inv = T(1) / fma_(vx, vx, fma_(vy, vy, r.dd[c]));
   }
   static __device__ __forceinline__ void add(const Rig& r, int c, T x, T y, Acc& a) {
     T u[3], inv;
     ray(r, c, x, y, u, inv);
-    T s0 = u[0] * inv, s1 = u[1] * inv, s2 = u[2] * inv;
-    a.uu[0] += s0 * u[0]; a.uu[1] += s0 * u[1]; a.uu[2] += s0 * u[2];
-    a.uu[3] += s1 * u[1]; a.uu[4] += s1 * u[2]; a.uu[5] += s2 * u[2];
-    T t = s0 * r.ob[c][0] + s1 * r.ob[c][1] + s2 * r.ob[c][2];
-    T w = u[0] * r.ob[c][0] + u[1] * r.ob[c][1] + u[2] * r.ob[c][2];
-    a.cu[0] += u[0] * t; a.cu[1] += u[1] * t; a.cu[2] += u[2] * t;
-    a.ku += t * w;
+    const T s0 = mul_(u[0], inv), s1 = mul_(u[1], inv), s2 = mul_(u[2], inv);
+    a.uu[0] = fma_(s0, u[0], a.uu[0]); a.uu[1] = fma_(s0, u[1], a.uu[1]); a.uu[2] = fma_(s0, u[2], a.uu[2]);
+    a.uu[3] = fma_(s1, u[1], a.uu[3]); a.uu[4] = fma_(s1, u[2], a.uu[4]); a.uu[5] = fma_(s2, u[2], a.uu[5]);
+    const T t = fma_(s0, r.ob[c][0], fma_(s1, r.ob[c][1], mul_(s2, r.ob[c][2])));
+    const T w = fma_(u[0], r.ob[c][0], fma_(u[1], r.ob[c][1], mul_(u[2], r.ob[c][2])));
+    a.cu[0] = fma_(u[0], t, a.cu[0]); a.cu[1] = fma_(u[1], t, a.cu[1]); a.cu[2] = fma_(u[2], t, a.cu[2]);
+    a.ku = fma_(t, w, a.ku);
     a.cn[0] += r.n4ob[c][0]; a.cn[1] += r.n4ob[c][1]; a.cn[2] += r.n4ob[c][2];
     a.so[0] += r.ob[c][0]; a.so[1] += r.ob[c][1]; a.so[2] += r.ob[c][2];
     a.tr += r.n4[c];
     a.kn += r.n4ob2[c];
   }
   static __device__ __forceinline__ T quad(const T (&M)[6], const T (&c)[3], T k, const T (&p)[3]) {
-    T Mp0 = M[0] * p[0] + M[1] * p[1] + M[2] * p[2];
-    T Mp1 = M[1] * p[0] + M[3] * p[1] + M[4] * p[2];
-    T Mp2 = M[2] * p[0] + M[4] * p[1] + M[5] * p[2];
-    return p[0] * (Mp0 - 2 * c[0]) + p[1] * (Mp1 - 2 * c[1]) + p[2] * (Mp2 - 2 * c[2]) + k;
+    const T Mp0 = fma_(M[0], p[0], fma_(M[1], p[1], mul_(M[2], p[2])));
+    const T Mp1 = fma_(M[1], p[0], fma_(M[3], p[1], mul_(M[4], p[2])));
+    const T Mp2 = fma_(M[2], p[0], fma_(M[4], p[1], mul_(M[5], p[2])));
+    return fma_(p[0], fma_(T(-2), c[0], Mp0), fma_(p[1], fma_(T(-2), c[1], Mp1), fma_(p[2], fma_(T(-2), c[2], Mp2), k)));
   }
   static __device__ __forceinline__ void solve(const Rig&, const Acc& a, int n, T (&X)[3], int opt, int& iters) {
     const T M[6] = {a.tr - a.uu[0], -a.uu[1], -a.uu[2], a.tr - a.uu[3], -a.uu[4], a.tr - a.uu[5]};
@@ -123,8 +123,8 @@ struct RayPolicy {
     T u[3], inv;
     ray(r, c, x, y, u, inv);
     const T w0 = X[0] - r.ob[c][0], w1 = X[1] - r.ob[c][1], w2 = X[2] - r.ob[c][2];
-    const T c0 = u[1] * w2 - u[2] * w1, c1 = u[2] * w0 - u[0] * w2, c2 = u[0] * w1 - u[1] * w0;
-    return sqrt((c0 * c0 + c1 * c1 + c2 * c2) * inv);
+    const T c0 = fma_(u[1], w2, -mul_(u[2], w1)), c1 = fma_(u[2], w0, -mul_(u[0], w2)), c2 = fma_(u[0], w1, -mul_(u[1], w0));
+    return sqrt(mul_(fma_(c0, c0, fma_(c1, c1, mul_(c2, c2))), inv));
   }
   static __device__ __forceinline__ double error(T sum, int n) { return (double)sum / (double)n; }
   static __device__ __forceinline__ void to_world(const Rig& r, T (&X)[3]) {
@@ -141,15 +141,15 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
   const int opt = lm ? 1 : 0;
   if (f32) {  // FP32: closed form only (the gain ratio of the LM loop needs S to ~1e-9 relative)
     switch (pixfmt) {
-      case PIX_F32: return launch_batch_policy<P32, PIX_F32>(ctx, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case PIX_F64: return launch_batch_policy<P32, PIX_F64>(ctx, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-      default: return launch_batch_policy<P32, PIX_U16>(ctx, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case PIX_F32: return launch_batch_policy<P32, PIX_F32, 2, 2>(ctx, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case PIX_F64: return launch_batch_policy<P32, PIX_F64, 2, 2>(ctx, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      default: return launch_batch_policy<P32, PIX_U16, 2, 2>(ctx, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
     }
   }
   switch (pixfmt) {
-    case PIX_F32: return launch_batch_policy<P64, PIX_F32>(ctx, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
-    case PIX_F64: return launch_batch_policy<P64, PIX_F64>(ctx, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
-    default: return launch_batch_policy<P64, PIX_U16>(ctx, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+    case PIX_F32: return launch_batch_policy<P64, PIX_F32, 1, 2>(ctx, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+    case PIX_F64: return launch_batch_policy<P64, PIX_F64, 1, 2>(ctx, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+    default: return launch_batch_policy<P64, PIX_U16, 1, 2>(ctx, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
   }
 }
 

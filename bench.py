@@ -302,7 +302,9 @@ def main():
                       "d2h_bytes_per_step": 12 * F, "ms_per_step": e_s * 1e3, "steps": esteps,
                       "api": "tri_triangulate_points (host buffers, pinned), per rank",
                       "pcie_gbs": (8 * N_CAMS * F + 12 * F) / e_s / 1e9, "kernel_launches": eng.kernel_launches - l0}
-        same = bool(torch.equal(h_out[:1000000].to(dev), out["xyz_f32"][:1000000]))
+        step()
+        torch.cuda.synchronize()
+        same = bool(torch.equal(h_out[:4000000].to(dev), out["xyz_f32"][:4000000]))
         res["e2e"]["matches_device_path"] = same
         del h_xy, h_out
 
