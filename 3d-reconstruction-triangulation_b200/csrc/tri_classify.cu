@@ -1,6 +1,555 @@
-// tri_classify.cu -- kernel 3 (placeholder until the batched classifier lands in this round)
+// tri_classify.cu -- kernel 3: DroneClassifier::classifyDrones (src/DroneClassifier.cpp:96-332) as two
+// kernels.  Compiled with -fmad=false: every compare that decides an index (error_ pruning, the
+// MAX_STEP gates, the priority order) is evaluated in the reference's operation order.
+//
+// (A) enumerate_kernel -- frame-parallel.  fillCombinationQueue (:156-198) walks a tree whose level c
+//     picks, for camera c, "none" (0) or detection k (1..n_c); every node with >= 2 detections is
+//     triangulated and its subtree cut when error > error_ (:185-187); complete nodes with
+//     >= MIN_CAMERAS detections are the candidate combinations (:190-196).  Whether a node survives
+//     depends only on its own prefix, so the tree is expanded level-synchronously: one CTA owns a
+//     frame, a level's children are evaluated one per thread and compacted IN ORDER (ballot + scan),
+//     which reproduces the reference's DFS order of the leaves (lexicographic in the per-camera
+//     choices).  A combination is one 64-bit word, 4 bits per camera.  The gated enumerations of
+//     triangulateWithLastPos (:219-250) are subsets of this full-frame leaf list (same prefixes, same
+//     pixels => same errors), so the tree is expanded ONCE per frame instead of once per path.
+// (B) link_kernel -- frame-sequential (the reference's tracking state: last position + 3-point tail
+//     per path, :119-135, :269-297).  One CTA walks the frames in order; per path it evaluates the
+//     MAX_STEP ray gate of every detection in parallel, then takes the arg-min over the admissible
+//     leaves of the key (fewest unused cameras, smallest error, DFS order) -- the first element the
+//     reference's priority_queue would pop that passes :241-246.  Phase 2 (pickBestCombinations +
+//     classifyPaths, :200-217, :262-332) is the same arg-min repeated greedily, then the tiny
+//     path-assignment logic on one thread.  Ties on (unused cameras, error) are broken by DFS order
+//     (the reference's heap order is an artefact of libstdc++); they are counted in stats.ties.
+#include <float.h>
+
+#include <algorithm>
+#include <vector>
+
 #include "tri_engine.cuh"
-extern "C" int tri_classify(tri_engine*, int, unsigned, int, const int32_t*, const double*, int, double*, int8_t*, uint8_t*,
-                            tri_classify_stats*) {
-  return tri::fail(TRI_ERR_ARG, "tri_classify: not built yet");
+#include "tri_ref.cuh"
+
+namespace tri {
+
+constexpr int CLS_MAX_CAMS = 16;   // 4 bits per camera in a 64-bit combination
+constexpr int CLS_THREADS = 128;
+constexpr int LINK_THREADS = 256;
+constexpr int LINK_MAX_FINAL = 128;
+typedef unsigned long long u64;
+
+// DroneClassifier.h:11-17
+constexpr double MAX_ERROR_MATRIX = 1e+5, MAX_ERROR_RAY = 120, MAX_STEP = 200;
+constexpr int MIN_CAMERAS = 2, PATH_TAIL = 3;
+
+struct ClsParams {
+  int n_cams, n_drones, solver;  // solver: 0 matrix, 1 ray reference LM, 2 ray closed form
+  int n_frames;                  // whole sequence (row length of the CSR offsets is n_frames + 1)
+  int f0, f1;                    // frame batch [f0, f1)
+  int cap;                       // frontier capacity per CTA
+  long long leaf_cap;
+  double error_;
+};
+
+struct ClsCounters {
+  u64 leaf_total, nodes, solves, leaves, lm_iters, phase1, phase2, ties;
+  int max_frontier, overflow_frontier, overflow_leaves, bad_input;
+};
+
+struct LinkState {
+  double tail[TRI_MAX_DRONES][PATH_TAIL][3];  // oldest .. newest of the last min(n,3) points
+  int n[TRI_MAX_DRONES];                      // points pushed so far (saturating)
+};
+
+__device__ __forceinline__ u64 nonzero_nibbles(u64 v) { return (v | (v >> 1) | (v >> 2) | (v >> 3)) & 0x1111111111111111ull; }
+
+// isCombinationUnique (DroneClassifier.cpp:32-41): no camera where both use the same detection
+__device__ __forceinline__ bool conflicts(u64 a, u64 b) { return (nonzero_nibbles(a) & ~nonzero_nibbles(a ^ b)) != 0; }
+
+__device__ inline double solve_combination(const DltRig<double>& dlt, const RayRig& ray, int solver, u64 comb, int n_cams,
+                                           const double (*px)[TRI_MAX_DETS], const double (*py)[TRI_MAX_DETS], double X[3],
+                                           int& iters) {
+  iters = 0;
+  if (solver == 0) {
+    int cam[CLS_MAX_CAMS], n = 0;
+    double x[CLS_MAX_CAMS], y[CLS_MAX_CAMS];
+    for (int i = 0; i < n_cams; i++) {
+      const int k = (int)((comb >> (4 * i)) & 15);
+      if (k) { cam[n] = i; x[n] = px[i][k - 1]; y[n] = py[i][k - 1]; n++; }
+    }
+    return ref::dlt_point(dlt, n, cam, x, y, X);
+  }
+  ref::RaySet rs;
+  rs.n = 0;
+  for (int i = 0; i < n_cams; i++) {
+    const int k = (int)((comb >> (4 * i)) & 15);
+    if (k) { rs.cam[rs.n] = i; ref::make_dir(ray, i, px[i][k - 1], py[i][k - 1], rs.d[rs.n]); rs.n++; }
+  }
+  if (solver == 1) return ref::lm_point(ray, rs, X, iters);
+  // closed form about the mean origin (the minimiser the reference's LM converges to)
+  const int n = rs.n;
+  double m[3] = {0, 0, 0};
+  for (int k = 0; k < n; k++) for (int j = 0; j < 3; j++) m[j] += ray.pos[rs.cam[k]][j] / n;
+  double M[6] = {0, 0, 0, 0, 0, 0}, c[3] = {0, 0, 0};
+  for (int k = 0; k < n; k++) {
+    const double* d = rs.d[k];
+    const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
+    const double o[3] = {ray.pos[rs.cam[k]][0] - m[0], ray.pos[rs.cam[k]][1] - m[1], ray.pos[rs.cam[k]][2] - m[2]};
+    const double dot = d[0] * o[0] + d[1] * o[1] + d[2] * o[2];
+    M[0] += dd - d[0] * d[0]; M[1] -= d[0] * d[1]; M[2] -= d[0] * d[2];
+    M[3] += dd - d[1] * d[1]; M[4] -= d[1] * d[2]; M[5] += dd - d[2] * d[2];
+    for (int j = 0; j < 3; j++) c[j] += dd * o[j] - d[j] * dot;
+  }
+  solve_sym3<double>(M, c, X);
+  for (int j = 0; j < 3; j++) X[j] += m[j];
+  double S, rmax, e;
+  ref::residual_pass(ray, rs, X, S, rmax, e);
+  iters = 1;
+  return e;
+}
+
+// ---- (A) candidate generation ------------------------------------------------------------------
+__global__ void __launch_bounds__(CLS_THREADS)
+enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_constant__ RayRig ray, ClsParams p,
+                 const int32_t* __restrict__ offs, const double* __restrict__ dets, u64* __restrict__ front,
+                 double* __restrict__ tmp_xyz, double* __restrict__ tmp_err, u64* __restrict__ leaf_comb,
+                 double* __restrict__ leaf_err, double* __restrict__ leaf_xyz, long long* __restrict__ leaf_off,
+                 int* __restrict__ leaf_cnt, ClsCounters* ctr) {
+  __shared__ int s_n[CLS_MAX_CAMS];
+  __shared__ double s_px[CLS_MAX_CAMS][TRI_MAX_DETS], s_py[CLS_MAX_CAMS][TRI_MAX_DETS];
+  __shared__ int s_warp[CLS_THREADS / 32];
+  __shared__ long long s_off;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int C = p.n_cams;
+  u64* buf0 = front + (size_t)blockIdx.x * 2 * p.cap;
+  u64* buf1 = buf0 + p.cap;
+  double* t_xyz = tmp_xyz + (size_t)blockIdx.x * 3 * p.cap;
+  double* t_err = tmp_err + (size_t)blockIdx.x * p.cap;
+  u64 st_nodes = 0, st_solves = 0, st_iters = 0;
+
+  for (int f = p.f0 + blockIdx.x; f < p.f1; f += gridDim.x) {
+    __syncthreads();
+    for (int i = tid; i < C * TRI_MAX_DETS; i += CLS_THREADS) {
+      const int c = i / TRI_MAX_DETS, d = i % TRI_MAX_DETS;
+      const int a = offs[(size_t)c * (p.n_frames + 1) + f], b = offs[(size_t)c * (p.n_frames + 1) + f + 1];
+      if (d == 0) {
+        s_n[c] = min(b - a, TRI_MAX_DETS);
+        if (b - a > TRI_MAX_DETS || b < a) atomicExch(&ctr->bad_input, 1);
+      }
+      if (d < b - a) { s_px[c][d] = dets[2 * (size_t)(a + d)]; s_py[c][d] = dets[2 * (size_t)(a + d) + 1]; }
+    }
+    if (tid == 0) buf0[0] = 0;
+    __syncthreads();
+    u64 *fin = buf0, *fout = buf1;
+    int m = 1;
+    for (int c = 0; c < C && m > 0; c++) {
+      const int nch = s_n[c] + 1;
+      const int total = m * nch;
+      const bool last = c == C - 1;
+      int out_base = 0;
+      for (int j0 = 0; j0 < total; j0 += CLS_THREADS) {
+        const int j = j0 + tid;
+        bool keep = false;
+        u64 comb = 0;
+        double X[3] = {0, 0, 0}, err = 0;
+        if (j < total) {
+          const int parent = j / nch, k = j - parent * nch;
+          comb = fin[parent] | ((u64)k << (4 * c));
+          const int cnt = __popcll(nonzero_nibbles(comb));
+          keep = true;
+          st_nodes++;
+          if (cnt >= 2) st_solves++;  // the reference re-solves the "none" children too (:166-181)
+          if (cnt >= 2 && (k > 0 || last)) {  // a "none" child repeats its parent's subset: same error
+            int it;
+            err = solve_combination(dlt, ray, p.solver, comb, c + 1, s_px, s_py, X, it);
+            st_iters += it;
+            if (err > p.error_) keep = false;  // :185-187
+          }
+          if (last && cnt < MIN_CAMERAS) keep = false;  // complete but too few detections: no candidate
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) s_warp[warp] = __popc(ballot);
+        __syncthreads();
+        int before = 0, chunk = 0;
+#pragma unroll
+        for (int w = 0; w < CLS_THREADS / 32; w++) {
+          if (w < warp) before += s_warp[w];
+          chunk += s_warp[w];
+        }
+        const int pos = out_base + before + __popc(ballot & ((1u << lane) - 1));
+        if (keep) {
+          if (pos < p.cap) {
+            fout[pos] = comb;
+            if (last) { t_xyz[3 * pos] = X[0]; t_xyz[3 * pos + 1] = X[1]; t_xyz[3 * pos + 2] = X[2]; t_err[pos] = err; }
+          } else {
+            atomicExch(&ctr->overflow_frontier, 1);
+          }
+        }
+        out_base += chunk;
+        __syncthreads();
+      }
+      m = min(out_base, p.cap);
+      if (tid == 0) atomicMax(&ctr->max_frontier, out_base);
+      u64* t = fin; fin = fout; fout = t;
+      if (m == 0) break;
+      if (last) {
+        // publish this frame's leaves (in order) into a contiguous range of the global leaf arrays
+        if (tid == 0) {
+          long long off = (long long)atomicAdd(&ctr->leaf_total, (u64)m);
+          if (off + m > p.leaf_cap) { atomicExch(&ctr->overflow_leaves, 1); off = -1; }
+          s_off = off;
+        }
+        __syncthreads();
+        const long long off = s_off;
+        if (off >= 0) {
+          for (int i = tid; i < m; i += CLS_THREADS) {
+            leaf_comb[off + i] = fin[i];
+            leaf_err[off + i] = t_err[i];
+            leaf_xyz[3 * (off + i)] = t_xyz[3 * i]; leaf_xyz[3 * (off + i) + 1] = t_xyz[3 * i + 1]; leaf_xyz[3 * (off + i) + 2] = t_xyz[3 * i + 2];
+          }
+          if (tid == 0) { leaf_off[f - p.f0] = off; leaf_cnt[f - p.f0] = m; atomicAdd(&ctr->leaves, (u64)m); }
+        } else if (tid == 0) {
+          leaf_off[f - p.f0] = 0; leaf_cnt[f - p.f0] = 0;
+        }
+        m = -1;  // done
+      }
+    }
+    if (m >= 0 && tid == 0) { leaf_off[f - p.f0] = 0; leaf_cnt[f - p.f0] = 0; }  // the tree died out (or no cameras)
+  }
+  // block totals of the per-thread statistics
+  for (int o = 16; o > 0; o >>= 1) {
+    st_nodes += __shfl_down_sync(0xffffffffu, st_nodes, o);
+    st_solves += __shfl_down_sync(0xffffffffu, st_solves, o);
+    st_iters += __shfl_down_sync(0xffffffffu, st_iters, o);
+  }
+  if (lane == 0) { atomicAdd(&ctr->nodes, st_nodes); atomicAdd(&ctr->solves, st_solves); atomicAdd(&ctr->lm_iters, st_iters); }
+}
+
+// ---- (B) linking -------------------------------------------------------------------------------
+struct Best {
+  int zeros;   // INT_MAX = none
+  double err;
+  int idx, same;  // same = admissible leaves seen with this (zeros, err)
+};
+__device__ __forceinline__ Best better(const Best& a, const Best& b) {
+  if (a.zeros == 0x7fffffff) return b;
+  if (b.zeros == 0x7fffffff) return a;
+  if (a.zeros == b.zeros && a.err == b.err) { Best r = a.idx < b.idx ? a : b; r.same = a.same + b.same; return r; }
+  if (a.zeros != b.zeros) return a.zeros < b.zeros ? a : b;  // Combination::operator< (:12-20)
+  return a.err < b.err ? a : b;
+}
+__device__ inline Best block_best(Best v, Best* s_best) {
+  for (int o = 16; o > 0; o >>= 1) {
+    Best u;
+    u.zeros = __shfl_down_sync(0xffffffffu, v.zeros, o);
+    u.err = __shfl_down_sync(0xffffffffu, v.err, o);
+    u.idx = __shfl_down_sync(0xffffffffu, v.idx, o);
+    u.same = __shfl_down_sync(0xffffffffu, v.same, o);
+    v = better(v, u);
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = v;
+  __syncthreads();
+  Best r = s_best[0];
+  for (int w = 1; w < LINK_THREADS / 32; w++) r = better(r, s_best[w]);
+  return r;
+}
+
+__device__ __forceinline__ double dist3(const double* a, const double* b) {  // cv::norm(a - b)
+  const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
+  return sqrt(x * x + y * y + z * z);
+}
+
+__global__ void __launch_bounds__(LINK_THREADS)
+link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __restrict__ offs, const double* __restrict__ dets,
+            const u64* __restrict__ leaf_comb, const double* __restrict__ leaf_err, const double* __restrict__ leaf_xyz,
+            const long long* __restrict__ leaf_off, const int* __restrict__ leaf_cnt, LinkState* state,
+            double* __restrict__ out_paths, int8_t* __restrict__ out_assign, uint8_t* __restrict__ out_phase, ClsCounters* ctr) {
+  __shared__ LinkState S;
+  __shared__ unsigned s_gate[CLS_MAX_CAMS];
+  __shared__ u64 s_used[TRI_MAX_DRONES];
+  __shared__ u64 s_fin[LINK_MAX_FINAL];
+  __shared__ int s_fin_idx[LINK_MAX_FINAL];
+  __shared__ Best s_best[LINK_THREADS / 32];
+  __shared__ int s_n_used, s_n_fin;
+  __shared__ unsigned s_processed;
+  const int tid = threadIdx.x, C = p.n_cams, D = p.n_drones;
+  const u64 cam_bits = C == 16 ? ~0ull : ((1ull << (4 * C)) - 1);
+  for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += LINK_THREADS) ((int*)&S)[i] = ((const int*)state)[i];
+  u64 n_phase1 = 0, n_phase2 = 0, n_ties = 0;  // thread 0 only
+  __syncthreads();
+
+  auto emit = [&](int path, int f, u64 comb, const double* pt, int phase) {  // thread 0: push a point to a path
+    const int n = S.n[path];
+    if (n >= PATH_TAIL) {
+      for (int k = 0; k < PATH_TAIL - 1; k++) for (int j = 0; j < 3; j++) S.tail[path][k][j] = S.tail[path][k + 1][j];
+      for (int j = 0; j < 3; j++) S.tail[path][PATH_TAIL - 1][j] = pt[j];
+    } else {
+      for (int j = 0; j < 3; j++) S.tail[path][n][j] = pt[j];
+    }
+    if (n < 0x3fffffff) S.n[path] = n + 1;
+    double* o = out_paths + ((size_t)path * p.n_frames + f) * 3;
+    o[0] = pt[0]; o[1] = pt[1]; o[2] = pt[2];
+    if (out_assign) for (int c = 0; c < C; c++) out_assign[((size_t)path * p.n_frames + f) * C + c] = (int8_t)((comb >> (4 * c)) & 15);
+    if (out_phase) out_phase[(size_t)path * p.n_frames + f] = (uint8_t)phase;
+  };
+
+  for (int f = p.f0; f < p.f1; f++) {
+    const int L = leaf_cnt[f - p.f0];
+    const long long off = leaf_off[f - p.f0];
+    const u64* lc = leaf_comb + off;
+    const double* le = leaf_err + off;
+    const double* lx = leaf_xyz + 3 * off;
+    if (tid == 0) { s_n_used = 0; s_processed = 0; }
+    __syncthreads();
+
+    // ---- phase 1: tracking (:119-135) ----
+    for (int np = 0; np < D; np++) {
+      const int n = S.n[np];
+      if (n == 0) continue;
+      const double* lastp = S.tail[np][min(n, PATH_TAIL) - 1];
+      const double last[3] = {lastp[0], lastp[1], lastp[2]};
+      if (last[0] == 0 && last[1] == 0 && last[2] == 0) continue;  // :123
+      if (tid < C) s_gate[tid] = 1u;  // choice 0 ("none") is always available
+      __syncthreads();
+      for (int i = tid; i < C * TRI_MAX_DETS; i += LINK_THREADS) {  // MAX_STEP ray gate, :228-236
+        const int c = i / TRI_MAX_DETS, d = i % TRI_MAX_DETS;
+        const int a = offs[(size_t)c * (p.n_frames + 1) + f], b = offs[(size_t)c * (p.n_frames + 1) + f + 1];
+        if (d < b - a && ref::dist_from_ray(ray, c, dets[2 * (size_t)(a + d)], dets[2 * (size_t)(a + d) + 1], last) < MAX_STEP)
+          atomicOr(&s_gate[c], 1u << (d + 1));
+      }
+      __syncthreads();
+      const int n_used = s_n_used;
+      Best mine{0x7fffffff, 0.0, 0, 0};
+      for (int i = tid; i < L; i += LINK_THREADS) {
+        const u64 comb = lc[i];
+        bool ok = true;
+        for (int c = 0; c < C; c++) ok = ok && ((s_gate[c] >> ((comb >> (4 * c)) & 15)) & 1u);
+        for (int u = 0; u < n_used && ok; u++) ok = !conflicts(comb, s_used[u]);
+        if (!ok) continue;
+        const double err = le[i];
+        if (!(err < p.error_)) continue;
+        if (!(dist3(lx + 3 * i, last) < MAX_STEP)) continue;  // cv::norm(c.point - pos) < MAX_STEP, :244
+        const Best cand{C - __popcll(nonzero_nibbles(comb & cam_bits)), err, i, 1};
+        mine = better(mine, cand);
+      }
+      const Best best = block_best(mine, s_best);
+      if (tid == 0 && best.zeros != 0x7fffffff) {
+        s_used[s_n_used++] = lc[best.idx];
+        s_processed |= 1u << np;
+        emit(np, f, lc[best.idx], lx + 3 * best.idx, 1);
+        n_phase1++;
+        if (best.same > 1) n_ties++;
+      }
+      __syncthreads();
+    }
+    if (__popc(s_processed) == D) continue;  // :137
+
+    // ---- phase 2: pickBestCombinations (:200-217) ----
+    if (tid == 0) s_n_fin = 0;
+    __syncthreads();
+    for (;;) {
+      const int n_used = s_n_used, n_fin = s_n_fin;
+      Best mine{0x7fffffff, 0.0, 0, 0};
+      for (int i = tid; i < L; i += LINK_THREADS) {
+        const u64 comb = lc[i];
+        bool ok = true;
+        for (int u = 0; u < n_fin && ok; u++) ok = !conflicts(comb, s_fin[u]);
+        for (int u = 0; u < n_used && ok; u++) ok = !conflicts(comb, s_used[u]);
+        if (!ok) continue;
+        const double err = le[i];
+        if (!(err < p.error_)) continue;
+        const Best cand{C - __popcll(nonzero_nibbles(comb & cam_bits)), err, i, 1};
+        mine = better(mine, cand);
+      }
+      const Best best = block_best(mine, s_best);
+      if (best.zeros == 0x7fffffff || n_fin >= LINK_MAX_FINAL) break;
+      if (tid == 0) {
+        s_fin[n_fin] = lc[best.idx];
+        s_fin_idx[n_fin] = best.idx;
+        s_n_fin = n_fin + 1;
+        if (best.same > 1) n_ties++;
+      }
+      __syncthreads();
+    }
+    // ---- classifyPaths (:262-332), one thread ----
+    if (tid == 0) {
+      const int nf = s_n_fin;
+      int cp_comb[LINK_MAX_FINAL], cp_path[LINK_MAX_FINAL];
+      double cp_err[LINK_MAX_FINAL];
+      unsigned processed = s_processed;
+      for (int i = 0; i < nf; i++) {
+        const double* pt = lx + 3 * s_fin_idx[i];
+        int bestPath = 0;
+        double bestDist = -1;
+        for (int j = 0; j < D; j++) {
+          if (processed >> j & 1u) continue;
+          const int npc = min(S.n[j], PATH_TAIL);
+          if (npc == 0) continue;
+          double dist = 0;
+          for (int t = 0; t < npc; t++) dist += dist3(S.tail[j][t], pt);
+          dist /= (double)npc;
+          if (dist < bestDist || bestDist == -1) { bestDist = dist; bestPath = j; }
+        }
+        // std::sort(greater<>) of <= 16 elements is an insertion sort in libstdc++: stable, ascending error
+        int k = i - 1;
+        while (k >= 0 && bestDist < cp_err[k]) { cp_comb[k + 1] = cp_comb[k]; cp_path[k + 1] = cp_path[k]; cp_err[k + 1] = cp_err[k]; k--; }
+        cp_comb[k + 1] = i; cp_path[k + 1] = bestPath; cp_err[k + 1] = bestDist;
+      }
+      for (int k = 0; k < nf; k++) {
+        int target = -1;
+        if (processed >> cp_path[k] & 1u) {
+          for (int i = 0; i < D; i++) if (S.n[i] == 0) { target = i; break; }
+        } else {
+          target = cp_path[k];
+        }
+        if (target != -1) {
+          emit(target, f, s_fin[cp_comb[k]], lx + 3 * s_fin_idx[cp_comb[k]], 2);
+          processed |= 1u << target;
+          n_phase2++;
+        }
+      }
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += LINK_THREADS) ((int*)state)[i] = ((const int*)&S)[i];
+  if (tid == 0) { atomicAdd(&ctr->phase1, n_phase1); atomicAdd(&ctr->phase2, n_phase2); atomicAdd(&ctr->ties, n_ties); }
+}
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { if (p) cudaFree(p); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  template <typename T> T* as() { return static_cast<T*>(p); }
+};
+
+}  // namespace tri
+
+using namespace tri;
+
+#define TRI_CUDA(call)                                         \
+  do {                                                         \
+    cudaError_t err__ = (call);                                \
+    if (err__ != cudaSuccess) return cuda_fail(err__, #call);  \
+  } while (0)
+
+extern "C" int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t* det_offsets,
+                            const double* dets_xy, int n_frames, double* out_paths, int8_t* out_assign, uint8_t* out_phase,
+                            tri_classify_stats* stats) {
+  if (!e) return fail(TRI_ERR_ARG, "null engine");
+  if (mode != TRI_MATRIX && mode != TRI_RAY) return fail(TRI_ERR_ARG, "mode must be TRI_MATRIX or TRI_RAY");
+  const int C = e->n_cams;
+  if (C > CLS_MAX_CAMS) return fail(TRI_ERR_ARG, "the classifier handles at most 16 cameras (the search is exponential in the camera count)");
+  if (n_drones < 1 || n_drones > TRI_MAX_DRONES) return fail(TRI_ERR_ARG, "n_drones must be in [1, TRI_MAX_DRONES]");
+  if (n_frames < 0 || !out_paths) return fail(TRI_ERR_ARG, "bad output arguments");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n_frames == 0) return TRI_OK;
+  if (!det_offsets) return fail(TRI_ERR_ARG, "null detection offsets");
+  const size_t n_offs = (size_t)C * (n_frames + 1);
+  int64_t n_det = 0;
+  for (int c = 0; c < C; c++) {
+    const int32_t* o = det_offsets + (size_t)c * (n_frames + 1);
+    for (int f = 0; f < n_frames; f++) {
+      if (o[f + 1] < o[f]) return fail(TRI_ERR_ARG, "detection offsets must be non-decreasing");
+      if (o[f + 1] - o[f] > TRI_MAX_DETS) return fail(TRI_ERR_CAPACITY, "more than TRI_MAX_DETS detections on one camera in one frame");
+    }
+    n_det = std::max<int64_t>(n_det, o[n_frames]);
+  }
+  if (n_det > 0 && !dets_xy) return fail(TRI_ERR_ARG, "null detections");
+  DeviceGuard g(e->device);
+  cudaStream_t s = e->stream;
+
+  ClsParams p;
+  p.n_cams = C; p.n_drones = n_drones; p.n_frames = n_frames;
+  p.solver = mode == TRI_MATRIX ? 0 : (flags & TRI_RAY_REFERENCE_LM) ? 1 : 2;
+  p.error_ = mode == TRI_MATRIX ? MAX_ERROR_MATRIX : MAX_ERROR_RAY;  // DroneClassifier.cpp:3-10
+
+  DevBuf d_offs, d_dets, d_paths, d_assign, d_phase, d_state, d_ctr, d_front, d_txyz, d_terr, d_lcomb, d_lerr, d_lxyz, d_loff, d_lcnt;
+  const size_t sz_paths = sizeof(double) * 3 * n_drones * (size_t)n_frames, sz_assign = (size_t)n_drones * n_frames * C,
+               sz_phase = (size_t)n_drones * n_frames;
+  TRI_CUDA(d_offs.alloc(sizeof(int32_t) * n_offs));
+  TRI_CUDA(d_dets.alloc(sizeof(double) * 2 * n_det));
+  TRI_CUDA(d_paths.alloc(sz_paths));
+  TRI_CUDA(d_assign.alloc(sz_assign));
+  TRI_CUDA(d_phase.alloc(sz_phase));
+  TRI_CUDA(d_state.alloc(sizeof(LinkState)));
+  TRI_CUDA(d_ctr.alloc(sizeof(ClsCounters)));
+  TRI_CUDA(cudaMemcpyAsync(d_offs.p, det_offsets, sizeof(int32_t) * n_offs, cudaMemcpyHostToDevice, s));
+  if (n_det) TRI_CUDA(cudaMemcpyAsync(d_dets.p, dets_xy, sizeof(double) * 2 * n_det, cudaMemcpyHostToDevice, s));
+  TRI_CUDA(cudaMemsetAsync(d_paths.p, 0, sz_paths, s));
+  TRI_CUDA(cudaMemsetAsync(d_assign.p, 0xff, sz_assign, s));
+  TRI_CUDA(cudaMemsetAsync(d_phase.p, 0, sz_phase, s));
+  TRI_CUDA(cudaMemsetAsync(d_state.p, 0, sizeof(LinkState), s));
+  TRI_CUDA(cudaMemsetAsync(d_ctr.p, 0, sizeof(ClsCounters), s));
+
+  int batch = std::min(n_frames, 8192);
+  int cap = 1 << 14;
+  long long leaf_cap = 4ll << 20;
+  int grid = 0;
+  auto alloc_work = [&]() -> int {
+    grid = std::max(1, std::min(batch, 2 * e->sm_count));
+    for (DevBuf* b : {&d_front, &d_txyz, &d_terr, &d_lcomb, &d_lerr, &d_lxyz, &d_loff, &d_lcnt}) {
+      if (b->p) cudaFree(b->p);
+      b->p = nullptr;
+    }
+    TRI_CUDA(d_front.alloc(sizeof(u64) * 2 * (size_t)cap * grid));
+    TRI_CUDA(d_txyz.alloc(sizeof(double) * 3 * (size_t)cap * grid));
+    TRI_CUDA(d_terr.alloc(sizeof(double) * (size_t)cap * grid));
+    TRI_CUDA(d_lcomb.alloc(sizeof(u64) * leaf_cap));
+    TRI_CUDA(d_lerr.alloc(sizeof(double) * leaf_cap));
+    TRI_CUDA(d_lxyz.alloc(sizeof(double) * 3 * leaf_cap));
+    TRI_CUDA(d_loff.alloc(sizeof(long long) * batch));
+    TRI_CUDA(d_lcnt.alloc(sizeof(int) * batch));
+    return TRI_OK;
+  };
+  int st = alloc_work();
+  if (st != TRI_OK) return st;
+
+  ClsCounters h{};
+  int max_frontier = 0;
+  for (int f0 = 0; f0 < n_frames;) {
+    const int f1 = std::min(n_frames, f0 + batch);
+    p.f0 = f0; p.f1 = f1; p.cap = cap; p.leaf_cap = leaf_cap;
+    ClsCounters before;
+    TRI_CUDA(cudaMemcpyAsync(&before, d_ctr.p, sizeof(before), cudaMemcpyDeviceToHost, s));
+    TRI_CUDA(cudaStreamSynchronize(s));
+    TRI_CUDA(cudaMemsetAsync(&d_ctr.as<ClsCounters>()->leaf_total, 0, sizeof(u64), s));
+    enumerate_kernel<<<grid, CLS_THREADS, 0, s>>>(e->rig64, e->ray, p, d_offs.as<int32_t>(), d_dets.as<double>(), d_front.as<u64>(),
+                                                   d_txyz.as<double>(), d_terr.as<double>(), d_lcomb.as<u64>(), d_lerr.as<double>(),
+                                                   d_lxyz.as<double>(), d_loff.as<long long>(), d_lcnt.as<int>(), d_ctr.as<ClsCounters>());
+    e->launches++;
+    TRI_CUDA(cudaGetLastError());
+    TRI_CUDA(cudaMemcpyAsync(&h, d_ctr.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    TRI_CUDA(cudaStreamSynchronize(s));
+    if (h.bad_input) return fail(TRI_ERR_ARG, "malformed detection offsets");
+    if (h.overflow_frontier || h.overflow_leaves) {
+      // grow the work buffers (or shrink the batch) and redo this batch; the statistics of the
+      // aborted attempt are rolled back
+      if (h.overflow_frontier) { if (cap >= (1 << 22)) return fail(TRI_ERR_CAPACITY, "combination frontier exceeds 4M nodes in one frame"); cap *= 4; batch = std::max(1, batch / 4); }
+      if (h.overflow_leaves) { if (batch > 64) batch /= 4; else if (leaf_cap < (256ll << 20)) leaf_cap *= 4; else return fail(TRI_ERR_CAPACITY, "candidate list exceeds device buffer"); }
+      before.overflow_frontier = before.overflow_leaves = 0;
+      TRI_CUDA(cudaMemcpyAsync(d_ctr.p, &before, sizeof(before), cudaMemcpyHostToDevice, s));
+      TRI_CUDA(cudaStreamSynchronize(s));
+      if ((st = alloc_work()) != TRI_OK) return st;
+      continue;
+    }
+    max_frontier = std::max(max_frontier, h.max_frontier);
+    link_kernel<<<1, LINK_THREADS, 0, s>>>(e->ray, p, d_offs.as<int32_t>(), d_dets.as<double>(), d_lcomb.as<u64>(), d_lerr.as<double>(),
+                                            d_lxyz.as<double>(), d_loff.as<long long>(), d_lcnt.as<int>(), d_state.as<LinkState>(),
+                                            d_paths.as<double>(), out_assign ? d_assign.as<int8_t>() : nullptr,
+                                            out_phase ? d_phase.as<uint8_t>() : nullptr, d_ctr.as<ClsCounters>());
+    e->launches++;
+    TRI_CUDA(cudaGetLastError());
+    f0 = f1;
+  }
+  TRI_CUDA(cudaMemcpyAsync(out_paths, d_paths.p, sz_paths, cudaMemcpyDeviceToHost, s));
+  if (out_assign) TRI_CUDA(cudaMemcpyAsync(out_assign, d_assign.p, sz_assign, cudaMemcpyDeviceToHost, s));
+  if (out_phase) TRI_CUDA(cudaMemcpyAsync(out_phase, d_phase.p, sz_phase, cudaMemcpyDeviceToHost, s));
+  TRI_CUDA(cudaMemcpyAsync(&h, d_ctr.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  TRI_CUDA(cudaStreamSynchronize(s));
+  if (stats) {
+    stats->nodes = (int64_t)h.nodes; stats->solves = (int64_t)h.solves; stats->leaves = (int64_t)h.leaves;
+    stats->lm_iters = (int64_t)h.lm_iters; stats->phase1 = (int64_t)h.phase1; stats->phase2 = (int64_t)h.phase2;
+    stats->ties = (int64_t)h.ties; stats->max_frontier = max_frontier;
+  }
+  return TRI_OK;
 }

@@ -1,0 +1,155 @@
+"""GPU parity of the batched DroneClassifier (tri_classify) against the oracle and the golden vectors
+(generated with the cv2 twin).  Assignment indices and phases must be bit-exact."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+import tri_b200 as T
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def ocams(cams):
+    return [O.make_camera(c.cam_id, c.width, c.height, c.focal, c.position, c.quat) for c in cams]
+
+
+@pytest.fixture(scope="module")
+def r02():
+    cams = T.load_cameras_xml(G + "/R02_D1_cameras.xml")
+    return cams, T.Engine(cams, 0), O.load_dets(G + "/R02_D1_dets.npz")
+
+
+@pytest.fixture(scope="module")
+def s09():
+    cams = T.load_cameras_xml(G + "/S09_D6_cameras.xml")
+    return cams, T.Engine(cams, 0), O.load_dets(G + "/S09_D6_dets.npz")
+
+
+def check(r, g, atol=1e-6):
+    assert np.array_equal(r["assign"], g["assign"])
+    assert np.array_equal(r["phase"], g["phase"])
+    np.testing.assert_allclose(r["paths"], g["paths"], rtol=1e-9, atol=atol)
+
+
+def test_r02_matrix_single_drone_golden(r02):
+    cams, eng, (offs, xy, nc, nf) = r02
+    g = np.load(G + "/golden_R02_D1_classify_matrix.npz")
+    r = eng.classify(T.MATRIX, 1, offs, xy, nf)
+    check(r, g)
+    assert np.all(r["assign"] == 1) and r["phase"][0, 0] == 2 and np.all(r["phase"][0, 1:] == 1)
+    # for one detection per camera the classifier output equals the batch API
+    pts = O.dets_to_points(offs, xy, nc, nf)
+    b = eng.triangulate_points(T.MATRIX, pts, want=("xyz_f64",))
+    assert np.abs(b["xyz_f64"] - r["paths"][0]).max() < 1e-9
+
+
+def test_r02_ray_reference_lm_golden(r02):
+    cams, eng, (offs, xy, nc, nf) = r02
+    g = np.load(G + "/golden_R02_D1_classify_ray.npz")
+    fr = g["paths"].shape[1]
+    o, x, _, _ = O.slice_frames(offs, xy, nc, nf, 0, fr)
+    r = eng.classify(T.RAY, 1, o, x, fr, T.RAY_REFERENCE_LM)
+    check(r, g, atol=1e-5)
+    ref = O.classify(ocams(cams), O.RAY, 1, o, x, nc, fr)
+    assert np.array_equal(r["paths"], ref["paths"])  # same LM trajectory: bit-identical points
+
+
+def test_r02_ray_reference_lm_long_vs_oracle(r02):
+    cams, eng, (offs, xy, nc, nf) = r02
+    fr = 400
+    o, x, _, _ = O.slice_frames(offs, xy, nc, nf, 0, fr)
+    ref = O.classify(ocams(cams), O.RAY, 1, o, x, nc, fr)
+    r = eng.classify(T.RAY, 1, o, x, fr, T.RAY_REFERENCE_LM)
+    assert np.array_equal(r["assign"], ref["assign"]) and np.array_equal(r["phase"], ref["phase"])
+    assert np.array_equal(r["paths"], ref["paths"])
+
+
+def test_s09_matrix_six_drones_golden_and_oracle(s09):
+    cams, eng, (offs, xy, nc, nf) = s09
+    g = np.load(G + "/golden_S09_D6_classify_matrix.npz")
+    fr = g["paths"].shape[1]
+    o, x, _, _ = O.slice_frames(offs, xy, nc, nf, 0, fr)
+    r = eng.classify(T.MATRIX, 6, o, x, fr)
+    check(r, g, atol=1e-5)
+    want = [(4, 1, 4, 1, 1, 5, 1, 1), (2, 4, 3, 2, 3, 2, 3, 2), (5, 2, 5, 6, 0, 3, 4, 5), (6, 5, 2, 5, 2, 6, 0, 3),
+            (3, 3, 1, 4, 0, 4, 0, 4), (1, 0, 6, 3, 0, 1, 2, 6)]
+    assert [tuple(int(v) for v in r["assign"][p, 0]) for p in range(6)] == want
+    assert r["stats"]["ties"] == 0
+
+
+def test_s09_matrix_full_sequence_vs_oracle(s09):
+    """All 3000 frames x 6 drones: indices, phases bit-exact; enumeration statistics identical."""
+    cams, eng, (offs, xy, nc, nf) = s09
+    ref = O.classify(ocams(cams), O.MATRIX, 6, offs, xy, nc, nf)
+    r = eng.classify(T.MATRIX, 6, offs, xy, nf)
+    assert np.array_equal(r["assign"], ref["assign"])
+    assert np.array_equal(r["phase"], ref["phase"])
+    np.testing.assert_allclose(r["paths"], ref["paths"], rtol=1e-9, atol=1e-5)
+    assert r["stats"]["phase1"] == ref["stats"]["phase1"] and r["stats"]["phase2"] == ref["stats"]["phase2"]
+    empties = [int((r["phase"][p] == 0).sum()) for p in range(6)]
+    assert empties == [int((ref["phase"][p] == 0).sum()) for p in range(6)]
+
+
+def test_full_frame_enumeration_statistics(s09):
+    cams, eng, (offs, xy, nc, nf) = s09
+    oc = ocams(cams)
+    tot = dict(nodes=0, solves=0, leaves=0)
+    frames = [0, 1, 7, 333, 1500, 2999]
+    for f in frames:
+        e = O.enumerate_frame(oc, O.MATRIX, offs, xy, nc, nf, f)
+        for k in tot:
+            tot[k] += e["stats"][k]
+    got = dict(nodes=0, solves=0, leaves=0)
+    for f in frames:
+        o, x, _, _ = O.slice_frames(offs, xy, nc, nf, f, f + 1)
+        r = eng.classify(T.MATRIX, 6, o, x, 1)
+        for k in got:
+            got[k] += r["stats"][k]
+    assert got == tot
+
+
+def test_classify_fast_ray_solver_runs(s09):
+    """Closed-form ray solves inside the classifier (the throughput variant): well-formed output, every
+    assigned point close to the matrix-mode point of the same frame/path where both assign."""
+    cams, eng, (offs, xy, nc, nf) = s09
+    fr = 60
+    o, x, _, _ = O.slice_frames(offs, xy, nc, nf, 0, fr)
+    r = eng.classify(T.RAY, 6, o, x, fr)
+    m = eng.classify(T.MATRIX, 6, o, x, fr)
+    both = (r["phase"] > 0) & (m["phase"] > 0) & np.all(r["assign"] == m["assign"], axis=2)
+    assert both.mean() > 0.5
+    assert np.abs(r["paths"][both] - m["paths"][both]).max() < 100.0
+
+
+def test_classify_argument_checks(r02):
+    cams, eng, (offs, xy, nc, nf) = r02
+    with pytest.raises(T.TriError):
+        eng.classify(T.MATRIX, 0, offs, xy, nf)
+    r = eng.classify(T.MATRIX, 2, offs, xy, 0)
+    assert r["paths"].shape == (2, 0, 3)
+    # empty frames in the middle: the path gets (0,0,0) and phase 0 there (DroneClassifier.cpp:147-153)
+    o = offs.reshape(nc, nf + 1)[:, :21].copy()
+    cut = o.copy()
+    for c in range(nc):  # drop the detections of frames 10..11 on every camera
+        n10 = o[c, 12] - o[c, 10]
+        cut[c, 11:] = o[c, 11:] - np.minimum(np.arange(1, 11), 2) * 0
+    offs2, xy2, _, _ = O.slice_frames(offs, xy, nc, nf, 0, 20)
+    o2 = offs2.reshape(nc, 21).copy()
+    keep = np.ones(len(xy2), bool)
+    for c in range(nc):
+        keep[o2[c, 10]:o2[c, 12]] = False
+    new = np.zeros_like(o2)
+    base = 0
+    for c in range(nc):
+        cnt = np.diff(o2[c])
+        cnt[10:12] = 0
+        new[c, 0] = base
+        new[c, 1:] = base + np.cumsum(cnt)
+        base = new[c, -1]
+    r = eng.classify(T.MATRIX, 1, new.reshape(-1), xy2[keep], 20)
+    ref = O.classify(ocams(cams), O.MATRIX, 1, new.reshape(-1).astype(np.int32), xy2[keep], nc, 20)
+    assert np.array_equal(r["phase"], ref["phase"]) and np.array_equal(r["assign"], ref["assign"])
+    assert np.all(r["phase"][0, 10:12] == 0) and np.all(r["paths"][0, 10:12] == 0)
