@@ -30,6 +30,7 @@ RAY_REFERENCE_LM = 1 << 2
 RAY_CLOSED_FORM = 1 << 3
 PIX_F64 = 1 << 4
 PIX_U16 = 1 << 5
+DEBUG_STREAM = 1 << 30
 MAX_CAMS = 32
 
 # the runtime_error texts of the reference, re-raised by the adapters

@@ -1,6 +1,7 @@
 // tri_api.cu -- extern "C" layer of libtri_b200.so (include/tri_b200.h): engine life cycle, the
 // batch entry points (device-resident and chunked host-buffer pipelines) and the memory helpers.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -169,9 +170,10 @@ static int check_batch_args(tri_engine* e, int mode, unsigned flags, const void*
   return TRI_OK;
 }
 
-static int launch_batch(tri_engine* e, const LaunchCtx& ctx, int mode, unsigned flags, int fmt, const void* d_xy, int n_use,
+static int launch_batch(tri_engine* e, LaunchCtx ctx, int mode, unsigned flags, int fmt, const void* d_xy, int n_use,
                         int64_t n_frames, int64_t cam_stride, const BatchOut& out) {
   cudaError_t err;
+  ctx.debug_stream = (flags & TRI_DEBUG_STREAM) != 0;
   if (mode == TRI_MATRIX) {
     err = launch_dlt(ctx, (flags & TRI_F32) != 0, fmt, e->rig64, e->rig32, d_xy, n_use, n_frames, cam_stride, out);
   } else {
@@ -232,6 +234,7 @@ int tri_create(int n_cams, const tri_camera* cams, int device, tri_engine** out)
   e->device = device;
   e->n_cams = n_cams;
   e->sm_count = prop.multiProcessorCount;
+  if (const char* v = getenv("TRI_VARIANT")) e->variant = atoi(v);
   memcpy(e->cams, cams, sizeof(tri_camera) * n_cams);
   build_rigs(e);
   cudaError_t err = cudaMalloc((void**)&e->d_first_bad, sizeof(unsigned long long));

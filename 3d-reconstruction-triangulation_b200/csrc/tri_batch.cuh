@@ -8,7 +8,7 @@
 // 16-byte load per camera (8 for ushort2), all cameras' loads issued before the first use.  The
 // per-frame solve is a policy class S:
 //     S::T, S::Rig (a __grid_constant__ parameter: operands come from the constant bank), S::Acc,
-//     S::add(rig, c, x, y, acc)            one valid view into the accumulator
+//     S::add(rig, c, x, y, valid, acc)     one view into the accumulator (a no-op when !valid)
 //     S::solve(rig, acc, n, X, opt, iters) the per-frame solve, X in rig coordinates
 //     S::residual(rig, c, x, y, X)         that view's contribution to the reported error
 //     S::error(sum, n)                     the reported error from the summed contributions
@@ -121,7 +121,7 @@ batch_kernel(const __grid_constant__ typename S::Rig rig, const char* __restrict
       for (int c = 0; c < NC; c++)
 #pragma unroll
         for (int j = 0; j < FPT; j++)
-          if (w[c].v[j]) { S::add(rig, c, w[c].x[j], w[c].y[j], acc[j]); mask[j] |= 1u << c; }
+          { S::add(rig, c, w[c].x[j], w[c].y[j], w[c].v[j], acc[j]); mask[j] |= (w[c].v[j] ? 1u : 0u) << c; }
 #pragma unroll
       for (int j = 0; j < FPT; j++) {
         n[j] = __popc(mask[j]);
@@ -140,7 +140,7 @@ batch_kernel(const __grid_constant__ typename S::Rig rig, const char* __restrict
         Views<T, PIX, FPT> w = fetch<T, PIX, FPT>(xy + c * row_bytes, group);
 #pragma unroll
         for (int j = 0; j < FPT; j++)
-          if (w.v[j]) { S::add(rig, c, w.x[j], w.y[j], acc[j]); mask[j] |= 1u << c; }
+          { S::add(rig, c, w.x[j], w.y[j], w.v[j], acc[j]); mask[j] |= (w.v[j] ? 1u : 0u) << c; }
       }
 #pragma unroll
       for (int j = 0; j < FPT; j++) {
@@ -203,7 +203,7 @@ batch_single_kernel(const __grid_constant__ typename S::Rig rig, const char* __r
   for (int c = 0; c < n_use; c++) {
     T x, y; bool ok;
     fetch1<T, PIX>(xy + c * row_bytes, f, x, y, ok);
-    if (ok) { S::add(rig, c, x, y, acc); mask |= 1u << c; }
+    { S::add(rig, c, x, y, ok, acc); mask |= (ok ? 1u : 0u) << c; }
   }
   const int n = __popc(mask);
   if (n >= 2) {

@@ -12,7 +12,7 @@ namespace tri {
 
 // MatrixTriangulator rows (MatrixTriangulator.cpp:16-49): a = P[r,0:3] - u*P[2,0:3], b = u*P[2,3] - P[r,3]
 template <typename T>
-struct DltRig {
+struct __align__(16) DltRig {
   T P[TRI_MAX_CAMS][12];  // FP64: cameraPerspectiveMatrix as is.  FP32: world origin moved to the
                           // rig centre and pixel origin to (cx,cy) (algebraically the same rows)
   T pix0[TRI_MAX_CAMS][2];  // pixel origin subtracted before use (0 for FP64)
@@ -34,7 +34,7 @@ struct RayRig {  // literal form: what the reference-LM emulation reads (same op
 // Triangulator.cpp:15-25, the rotated direction is dir = u / |v| with u = R v = U0*px + U1*py + U2.
 // |dir|^2 = n4 = |q|^4.  Positions are relative to the rig centre `origin`.
 template <typename T>
-struct RayFold {
+struct __align__(16) RayFold {
   T U0[TRI_MAX_CAMS][3], U1[TRI_MAX_CAMS][3], U2[TRI_MAX_CAMS][3];
   T ax[TRI_MAX_CAMS], bx[TRI_MAX_CAMS], ay[TRI_MAX_CAMS], by[TRI_MAX_CAMS], dd[TRI_MAX_CAMS];  // dd = depth^2
   T n4[TRI_MAX_CAMS];
@@ -118,6 +118,8 @@ struct LaunchCtx {
   unsigned long long* d_first_bad;  // latched index of the first frame with < 2 views
   int64_t frame_base;               // global index of frame 0 of this launch (chunked host path)
   int64_t* launches;
+  bool debug_stream = false;
+  int variant = 0;  // TRI_VARIANT (tuning experiments)  // TRI_DEBUG_STREAM: memory-roofline probe instead of the solve
 };
 
 enum RaySolver { RAY_ANALYTIC_LM = 0, RAY_REFERENCE_LM = 1, RAY_CLOSED_FORM = 2 };

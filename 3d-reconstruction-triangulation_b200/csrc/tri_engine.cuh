@@ -47,12 +47,13 @@ struct tri_engine {
   unsigned long long* d_first_bad = nullptr;
   tri::Slot slots[tri::N_SLOTS];
   int64_t launches = 0;
+  int variant = 0;
   // scratch for the small host-buffer entry points (subsets, dist_from_ray, classify)
   char* d_scratch = nullptr;
   size_t scratch_cap = 0;
   cudaStream_t stream = nullptr;
 
   tri::LaunchCtx ctx(cudaStream_t s, int64_t frame_base = 0) {
-    return tri::LaunchCtx{s, sm_count, d_first_bad, frame_base, &launches};
+    return tri::LaunchCtx{s, sm_count, d_first_bad, frame_base, &launches, false, variant};
   }
 };

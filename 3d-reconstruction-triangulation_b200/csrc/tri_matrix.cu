@@ -10,9 +10,87 @@
 // from the constant bank -- and solves by the adjugate.  The full-rank pseudo-inverse solution IS
 // the normal-equation solution; cond(A) <= ~5 on real rigs so nothing is lost.
 // HBM traffic per frame: 8 B x n_cams in, 12 B out.
-#include "tri_batch.cuh"
+#include "tri_pipe.cuh"
 
 namespace tri {
+
+// one camera's 3x4 matrix as 16-byte vector loads (LDS.128 from the shared-memory rig)
+__device__ __forceinline__ void load12(const double (&src)[12], double (&P)[12]) {
+  const double2* v = reinterpret_cast<const double2*>(src);
+#pragma unroll
+  for (int k = 0; k < 6; k++) { const double2 q = v[k]; P[2 * k] = q.x; P[2 * k + 1] = q.y; }
+}
+__device__ __forceinline__ void load12(const float (&src)[12], float (&P)[12]) {
+  const float4* v = reinterpret_cast<const float4*>(src);
+#pragma unroll
+  for (int k = 0; k < 3; k++) { const float4 q = v[k]; P[4 * k] = q.x; P[4 * k + 1] = q.y; P[4 * k + 2] = q.z; P[4 * k + 3] = q.w; }
+}
+
+// FP64 accumulation of one view under a predicate (no branch, no reconvergence barrier): 26 @p DFMA.
+__device__ __forceinline__ void add_view_pred(bool valid, const double (&P)[12], double x, double y, double (&M)[6], double (&v)[3]) {
+  asm("{\n"
+      ".reg .pred p;\n"
+      ".reg .f64 a0, a1, a2, b, nx, ny, n3, n7;\n"
+      "setp.ne.u32 p, %9, 0;\n"
+      "neg.f64 nx, %10;\n"
+      "neg.f64 ny, %11;\n"
+      "neg.f64 n3, %15;\n"
+      "neg.f64 n7, %19;\n"
+      "@p fma.rn.f64 a0, nx, %20, %12;\n"
+      "@p fma.rn.f64 a1, nx, %21, %13;\n"
+      "@p fma.rn.f64 a2, nx, %22, %14;\n"
+      "@p fma.rn.f64 b, %10, %23, n3;\n"
+      "@p fma.rn.f64 %0, a0, a0, %0;\n"
+      "@p fma.rn.f64 %1, a0, a1, %1;\n"
+      "@p fma.rn.f64 %2, a0, a2, %2;\n"
+      "@p fma.rn.f64 %3, a1, a1, %3;\n"
+      "@p fma.rn.f64 %4, a1, a2, %4;\n"
+      "@p fma.rn.f64 %5, a2, a2, %5;\n"
+      "@p fma.rn.f64 %6, a0, b, %6;\n"
+      "@p fma.rn.f64 %7, a1, b, %7;\n"
+      "@p fma.rn.f64 %8, a2, b, %8;\n"
+      "@p fma.rn.f64 a0, ny, %20, %16;\n"
+      "@p fma.rn.f64 a1, ny, %21, %17;\n"
+      "@p fma.rn.f64 a2, ny, %22, %18;\n"
+      "@p fma.rn.f64 b, %11, %23, n7;\n"
+      "@p fma.rn.f64 %0, a0, a0, %0;\n"
+      "@p fma.rn.f64 %1, a0, a1, %1;\n"
+      "@p fma.rn.f64 %2, a0, a2, %2;\n"
+      "@p fma.rn.f64 %3, a1, a1, %3;\n"
+      "@p fma.rn.f64 %4, a1, a2, %4;\n"
+      "@p fma.rn.f64 %5, a2, a2, %5;\n"
+      "@p fma.rn.f64 %6, a0, b, %6;\n"
+      "@p fma.rn.f64 %7, a1, b, %7;\n"
+      "@p fma.rn.f64 %8, a2, b, %8;\n"
+      "}\n"
+      : "+d"(M[0]), "+d"(M[1]), "+d"(M[2]), "+d"(M[3]), "+d"(M[4]), "+d"(M[5]), "+d"(v[0]), "+d"(v[1]), "+d"(v[2])
+      : "r"((unsigned)valid), "d"(x), "d"(y), "d"(P[0]), "d"(P[1]), "d"(P[2]), "d"(P[3]), "d"(P[4]), "d"(P[5]), "d"(P[6]), "d"(P[7]),
+        "d"(P[8]), "d"(P[9]), "d"(P[10]), "d"(P[11]));
+}
+
+// FP64 tile solver with the predicated accumulation (one frame per thread)
+struct DltF64Tile {
+  static constexpr int FPT = 1;
+  using Rig = DltRig<double>;
+  template <int NC, int PIX>
+  static __device__ __forceinline__ void run(const Rig& rig, const typename RawPix<PIX, 1>::type (&raw)[NC], int, float (&X)[1][3],
+                                             uint32_t (&mask)[1]) {
+    double M[6] = {0, 0, 0, 0, 0, 0}, v[3] = {0, 0, 0};
+    uint32_t m = 0;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const Views<double, PIX, 1> w = decode<double, PIX, 1>(raw[c]);
+      double P[12];
+      load12(rig.P[c], P);
+      add_view_pred(w.v[0], P, w.x[0], w.y[0], M, v);
+      m |= (w.v[0] ? 1u : 0u) << c;
+    }
+    double S[3] = {0, 0, 0};
+    if (__popc(m) >= 2) solve_sym3<double>(M, v, S);
+    X[0][0] = (float)S[0]; X[0][1] = (float)S[1]; X[0][2] = (float)S[2];
+    mask[0] = m;
+  }
+};
 
 template <typename T_, bool CENTRED>
 struct DltPolicy {
@@ -22,14 +100,20 @@ struct DltPolicy {
     T M[6] = {0, 0, 0, 0, 0, 0};
     T v[3] = {0, 0, 0};
   };
-  static __device__ __forceinline__ void add(const Rig& rig, int c, T x, T y, Acc& a) {
-    const T(&P)[12] = rig.P[c];
+  // Branch-free: an absent view's rows are zeroed (one predicated register clear per value) instead of
+  // skipped -- within a warp some lane almost always has the view, so the FMAs issue either way, and
+  // the divergence barriers (BSSY/BSYNC, 27 % of the stall samples in profiles/r1c) disappear.
+  static __device__ __forceinline__ void add(const Rig& rig, int c, T x, T y, bool valid, Acc& a) {
+    T P[12];
+    load12(rig.P[c], P);
     if constexpr (CENTRED) { x -= rig.pix0[c][0]; y -= rig.pix0[c][1]; }
     T a0 = fma_(-x, P[8], P[0]), a1 = fma_(-x, P[9], P[1]), a2 = fma_(-x, P[10], P[2]), b = fma_(x, P[11], -P[3]);
+    a0 = valid ? a0 : T(0); a1 = valid ? a1 : T(0); a2 = valid ? a2 : T(0);
     a.M[0] = fma_(a0, a0, a.M[0]); a.M[1] = fma_(a0, a1, a.M[1]); a.M[2] = fma_(a0, a2, a.M[2]);
     a.M[3] = fma_(a1, a1, a.M[3]); a.M[4] = fma_(a1, a2, a.M[4]); a.M[5] = fma_(a2, a2, a.M[5]);
     a.v[0] = fma_(a0, b, a.v[0]); a.v[1] = fma_(a1, b, a.v[1]); a.v[2] = fma_(a2, b, a.v[2]);
     a0 = fma_(-y, P[8], P[4]); a1 = fma_(-y, P[9], P[5]); a2 = fma_(-y, P[10], P[6]); b = fma_(y, P[11], -P[7]);
+    a0 = valid ? a0 : T(0); a1 = valid ? a1 : T(0); a2 = valid ? a2 : T(0);
     a.M[0] = fma_(a0, a0, a.M[0]); a.M[1] = fma_(a0, a1, a.M[1]); a.M[2] = fma_(a0, a2, a.M[2]);
     a.M[3] = fma_(a1, a1, a.M[3]); a.M[4] = fma_(a1, a2, a.M[4]); a.M[5] = fma_(a2, a2, a.M[5]);
     a.v[0] = fma_(a0, b, a.v[0]); a.v[1] = fma_(a1, b, a.v[1]); a.v[2] = fma_(a2, b, a.v[2]);
@@ -53,12 +137,12 @@ struct DltPolicy {
 
 // ---- FP32 main path: packed-pair SIMD (FFMA2 / FMUL2 / FADD2, new on sm_100) ----
 // One thread owns frames (2g, 2g+1) as the two halves of a float2; every multiply-add of the
-// accumulation is one FFMA2, so the kernel needs half the issue slots of the scalar form (which is
-// issue-bound: ncu r1a, 80 % issue-active at 59 % DRAM).  Branch-free: an absent view is weighted by
-// w = 0 instead of skipped (w a is exact for w in {0,1}, so the points are bit-identical to the
-// scalar DltPolicy<float> path).  Rig constants are pre-duplicated/negated float2 so the operands come
-// from the uniform datapath.
-struct DltRigX2 {
+// accumulation is one FFMA2, so the solve needs half the issue slots of the scalar form (which was
+// issue-bound: profiles/r1a, 80 % issue-active).  Branch-free: an absent view is weighted by w = 0
+// instead of skipped (w a is exact for w in {0,1}, so the points are bit-identical to the scalar
+// DltPolicy<float> path, which serves the tails and the optional outputs).  Rig constants are
+// pre-duplicated / pre-negated float2 so the operands come from the uniform datapath.
+struct __align__(16) DltRigX2 {
   float2 A[TRI_MAX_CAMS][8];   // P0 P1 P2 -P3 | P4 P5 P6 -P7   (addends of the x row, the y row)
   float2 N[TRI_MAX_CAMS][4];   // -P8 -P9 -P10 P11              (multiplicands)
   float2 npix0[TRI_MAX_CAMS][2];
@@ -69,44 +153,51 @@ __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __
 __device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
-template <int NC, int PIX>
-__global__ void __launch_bounds__(BATCH_THREADS, 3)
-dlt_f32x2_kernel(const __grid_constant__ DltRigX2 rig, const char* __restrict__ xy, int64_t row_bytes, int64_t n_pairs,
-                 int n_use, BatchOut out, unsigned long long* first_bad, int64_t frame_base) {
-  __shared__ __align__(16) float tile[BATCH_THREADS * 6];
-  const int64_t block_pair0 = (int64_t)blockIdx.x * BATCH_THREADS;
-  const int64_t pair = block_pair0 + threadIdx.x;
-  const int nc = NC > 0 ? NC : n_use;
-  float2 X[3] = {{0, 0}, {0, 0}, {0, 0}};
-  if (pair < n_pairs) {
+template <bool SEL>
+struct DltX2Tile {
+  static constexpr int FPT = 2;
+  using Rig = DltRigX2;
+  template <int NC, int PIX>
+  static __device__ __forceinline__ void run(const Rig& rig, const typename RawPix<PIX, 2>::type (&raw)[NC], int,
+                                             float (&X)[2][3], uint32_t (&mask)[2]) {
     float2 M[6] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}}, v[3] = {{0, 0}, {0, 0}, {0, 0}};
     uint32_t mask0 = 0, mask1 = 0;
-    auto view = [&](int c, const View2<float>& q) {
-      const float2 w = make_float2(q.v0 ? 1.0f : 0.0f, q.v1 ? 1.0f : 0.0f);
-      mask0 |= (q.v0 ? 1u : 0u) << c;
-      mask1 |= (q.v1 ? 1u : 0u) << c;
-      const float2 x = __fadd2_rn(make_float2(q.x0, q.x1), rig.npix0[c][0]);
-      const float2 y = __fadd2_rn(make_float2(q.y0, q.y1), rig.npix0[c][1]);
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const Views<float, PIX, 2> q = decode<float, PIX, 2>(raw[c]);
+      const float2 w = make_float2(q.v[0] ? 1.0f : 0.0f, q.v[1] ? 1.0f : 0.0f);
+      mask0 |= (q.v[0] ? 1u : 0u) << c;
+      mask1 |= (q.v[1] ? 1u : 0u) << c;
+      float2 K[14];  // this camera's constants: 7 LDS.128
+      {
+        const float4* kv = reinterpret_cast<const float4*>(rig.A[c]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const float4 t = kv[k]; K[2 * k] = make_float2(t.x, t.y); K[2 * k + 1] = make_float2(t.z, t.w); }
+        const float4* nv = reinterpret_cast<const float4*>(rig.N[c]);
+#pragma unroll
+        for (int k = 0; k < 2; k++) { const float4 t = nv[k]; K[8 + 2 * k] = make_float2(t.x, t.y); K[9 + 2 * k] = make_float2(t.z, t.w); }
+        const float4 t = *reinterpret_cast<const float4*>(rig.npix0[c]);
+        K[12] = make_float2(t.x, t.y); K[13] = make_float2(t.z, t.w);
+      }
+      const float2 x = __fadd2_rn(make_float2(q.x[0], q.x[1]), K[12]);
+      const float2 y = __fadd2_rn(make_float2(q.y[0], q.y[1]), K[13]);
 #pragma unroll
       for (int r = 0; r < 2; r++) {
         const float2 u = r == 0 ? x : y;
-        const float2 a0 = fma2(u, rig.N[c][0], rig.A[c][4 * r]), a1 = fma2(u, rig.N[c][1], rig.A[c][4 * r + 1]),
-                     a2 = fma2(u, rig.N[c][2], rig.A[c][4 * r + 2]), b = fma2(u, rig.N[c][3], rig.A[c][4 * r + 3]);
-        const float2 w0 = mul2(a0, w), w1 = mul2(a1, w), w2 = mul2(a2, w);
+        const float2 a0 = fma2(u, K[8], K[4 * r]), a1 = fma2(u, K[9], K[4 * r + 1]),
+                     a2 = fma2(u, K[10], K[4 * r + 2]), b = fma2(u, K[11], K[4 * r + 3]);
+        float2 w0, w1, w2;
+        if constexpr (SEL) {  // zero an absent view's row on the ALU pipe instead of multiplying on the FMA pipe
+          w0 = make_float2(q.v[0] ? a0.x : 0.f, q.v[1] ? a0.y : 0.f);
+          w1 = make_float2(q.v[0] ? a1.x : 0.f, q.v[1] ? a1.y : 0.f);
+          w2 = make_float2(q.v[0] ? a2.x : 0.f, q.v[1] ? a2.y : 0.f);
+        } else {
+          w0 = mul2(a0, w); w1 = mul2(a1, w); w2 = mul2(a2, w);
+        }
         M[0] = fma2(w0, a0, M[0]); M[1] = fma2(w0, a1, M[1]); M[2] = fma2(w0, a2, M[2]);
         M[3] = fma2(w1, a1, M[3]); M[4] = fma2(w1, a2, M[4]); M[5] = fma2(w2, a2, M[5]);
         v[0] = fma2(w0, b, v[0]); v[1] = fma2(w1, b, v[1]); v[2] = fma2(w2, b, v[2]);
       }
-    };
-    if constexpr (NC > 0) {
-      View2<float> q[NC];
-#pragma unroll
-      for (int c = 0; c < NC; c++) q[c] = fetch2<float, PIX>(xy + c * row_bytes, pair);
-#pragma unroll
-      for (int c = 0; c < NC; c++) view(c, q[c]);
-    } else {
-#pragma unroll 2
-      for (int c = 0; c < nc; c++) view(c, fetch2<float, PIX>(xy + c * row_bytes, pair));
     }
     // adjugate solve, both frames at once (same operation order as solve_sym3<float>)
     const float2 c00 = fma2(M[3], M[5], neg2(mul2(M[4], M[4]))), c01 = fma2(M[2], M[4], neg2(mul2(M[1], M[5]))),
@@ -114,39 +205,36 @@ dlt_f32x2_kernel(const __grid_constant__ DltRigX2 rig, const char* __restrict__ 
                  c12 = fma2(M[1], M[2], neg2(mul2(M[0], M[4]))), c22 = fma2(M[0], M[3], neg2(mul2(M[1], M[1])));
     const float2 det = fma2(M[0], c00, fma2(M[1], c01, mul2(M[2], c02)));
     const float2 inv = make_float2(1.0f / det.x, 1.0f / det.y);
-    X[0] = mul2(fma2(c00, v[0], fma2(c01, v[1], mul2(c02, v[2]))), inv);
-    X[1] = mul2(fma2(c01, v[0], fma2(c11, v[1], mul2(c12, v[2]))), inv);
-    X[2] = mul2(fma2(c02, v[0], fma2(c12, v[1], mul2(c22, v[2]))), inv);
+    const float2 X0 = mul2(fma2(c00, v[0], fma2(c01, v[1], mul2(c02, v[2]))), inv);
+    const float2 X1 = mul2(fma2(c01, v[0], fma2(c11, v[1], mul2(c12, v[2]))), inv);
+    const float2 X2 = mul2(fma2(c02, v[0], fma2(c12, v[1], mul2(c22, v[2]))), inv);
     const bool ok0 = __popc(mask0) >= 2, ok1 = __popc(mask1) >= 2;
-    X[0].x = ok0 ? X[0].x + rig.origin[0] : 0.f; X[1].x = ok0 ? X[1].x + rig.origin[1] : 0.f; X[2].x = ok0 ? X[2].x + rig.origin[2] : 0.f;
-    X[0].y = ok1 ? X[0].y + rig.origin[0] : 0.f; X[1].y = ok1 ? X[1].y + rig.origin[1] : 0.f; X[2].y = ok1 ? X[2].y + rig.origin[2] : 0.f;
-    if (!ok0) atomicMin(first_bad, (unsigned long long)(frame_base + 2 * pair));
-    if (!ok1) atomicMin(first_bad, (unsigned long long)(frame_base + 2 * pair + 1));
-    if (out.xyz_f64) {
-      double* o = out.xyz_f64 + 6 * pair;
-      o[0] = X[0].x; o[1] = X[1].x; o[2] = X[2].x; o[3] = X[0].y; o[4] = X[1].y; o[5] = X[2].y;
-    }
-    if (out.mask) reinterpret_cast<uint2*>(out.mask)[pair] = make_uint2(mask0, mask1);
+    X[0][0] = ok0 ? X0.x + rig.origin[0] : 0.f; X[0][1] = ok0 ? X1.x + rig.origin[1] : 0.f; X[0][2] = ok0 ? X2.x + rig.origin[2] : 0.f;
+    X[1][0] = ok1 ? X0.y + rig.origin[0] : 0.f; X[1][1] = ok1 ? X1.y + rig.origin[1] : 0.f; X[1][2] = ok1 ? X2.y + rig.origin[2] : 0.f;
+    mask[0] = mask0; mask[1] = mask1;
   }
-  if (out.xyz_f32) {
-    float2* t2 = reinterpret_cast<float2*>(tile) + 3 * threadIdx.x;
-    t2[0] = make_float2(X[0].x, X[1].x);
-    t2[1] = make_float2(X[2].x, X[0].y);
-    t2[2] = make_float2(X[1].y, X[2].y);
-    __syncthreads();
-    const int64_t remaining = n_pairs - block_pair0;
-    float* dst = out.xyz_f32 + 6 * block_pair0;
-    if (remaining >= BATCH_THREADS && ((uintptr_t)dst & 15) == 0) {
-      float4* d4 = reinterpret_cast<float4*>(dst);
-      const float4* s4 = reinterpret_cast<const float4*>(tile);
+};
+
+// Memory-roofline probe (TRI_DEBUG_STREAM): the same pipeline with a near-empty solve -- x = sum of the
+// valid pixel x, y = sum of y, z = number of views -- to measure what the streaming skeleton alone sustains.
+struct StreamProbeTile {
+  static constexpr int FPT = 2;
+  using Rig = DltRigX2;
+  template <int NC, int PIX>
+  static __device__ __forceinline__ void run(const Rig&, const typename RawPix<PIX, 2>::type (&raw)[NC], int, float (&X)[2][3],
+                                             uint32_t (&mask)[2]) {
+    mask[0] = mask[1] = 0;
 #pragma unroll
-      for (int i = threadIdx.x; i < BATCH_THREADS * 6 / 4; i += BATCH_THREADS) __stcs(d4 + i, s4[i]);
-    } else {
-      const int cnt = (int)(remaining < BATCH_THREADS ? remaining : BATCH_THREADS) * 6;
-      for (int i = threadIdx.x; i < cnt; i += BATCH_THREADS) dst[i] = tile[i];
+    for (int j = 0; j < 2; j++) X[j][0] = X[j][1] = X[j][2] = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const Views<float, PIX, 2> q = decode<float, PIX, 2>(raw[c]);
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+        if (q.v[j]) { X[j][0] += q.x[j]; X[j][1] += q.y[j]; X[j][2] += 1.f; mask[j] |= 1u << c; }
     }
   }
-}
+};
 
 static DltRigX2 make_x2(const DltRig<float>& r) {
   DltRigX2 x;
@@ -162,64 +250,46 @@ static DltRigX2 make_x2(const DltRig<float>& r) {
   return x;
 }
 
-// xyz / mask outputs only; vector-aligned rows only; the caller falls back to the scalar policy otherwise
-template <int PIX>
-static cudaError_t launch_dlt_x2(const LaunchCtx& ctx, const DltRig<float>& rig32, const char* xy, int64_t row_bytes,
-                                 int n_use, int64_t n_pairs, const BatchOut& out) {
-  const DltRigX2 rig = make_x2(rig32);
-  const unsigned grid = (unsigned)((n_pairs + BATCH_THREADS - 1) / BATCH_THREADS);
-#define TRI_CASE(N)                                                                                                    \
-  case N:                                                                                                              \
-    dlt_f32x2_kernel<N, PIX><<<grid, BATCH_THREADS, 0, ctx.stream>>>(rig, xy, row_bytes, n_pairs, n_use, out,          \
-                                                                     ctx.d_first_bad, ctx.frame_base);                  \
-    break;
-  switch (n_use) {
-    TRI_CASE(2) TRI_CASE(3) TRI_CASE(4) TRI_CASE(5) TRI_CASE(6) TRI_CASE(7) TRI_CASE(8)
-    default:
-      dlt_f32x2_kernel<0, PIX><<<grid, BATCH_THREADS, 0, ctx.stream>>>(rig, xy, row_bytes, n_pairs, n_use, out, ctx.d_first_bad,
-                                                                       ctx.frame_base);
-  }
-#undef TRI_CASE
-  ++*ctx.launches;
-  return cudaGetLastError();
-}
-
-template <int PIX>
-static cudaError_t launch_dlt_f32(const LaunchCtx& ctx, const DltRig<float>& rig32, const void* d_xy, int n_use,
-                                  int64_t n_frames, int64_t cam_stride, const BatchOut& out) {
-  using P32 = DltPolicy<float, true>;
-  const char* xy = static_cast<const char*>(d_xy);
-  const int64_t row_bytes = cam_stride * pix_bytes(PIX), need = 2 * pix_bytes(PIX);
-  const bool packed = !out.err && !out.iters && PIX != PIX_F64 && ((uintptr_t)xy % need == 0) && (row_bytes % need == 0) &&
-                      (out.mask == nullptr || (uintptr_t)out.mask % 8 == 0) && n_frames >= 2;
-  if (!packed) return launch_batch_policy<P32, PIX, 2, 3>(ctx, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
-  const int64_t n_pairs = n_frames / 2;
-  cudaError_t err = launch_dlt_x2<PIX>(ctx, rig32, xy, row_bytes, n_use, n_pairs, out);
-  if (err != cudaSuccess || 2 * n_pairs == n_frames) return err;
-  const int64_t done = 2 * n_pairs;  // odd tail frame: scalar kernel
-  batch_single_kernel<P32, PIX><<<1, BATCH_THREADS, 0, ctx.stream>>>(rig32, xy, row_bytes, done, n_frames, n_use, out, 0,
-                                                                     ctx.d_first_bad, ctx.frame_base);
-  ++*ctx.launches;
-  return cudaGetLastError();
-}
-
 cudaError_t launch_dlt(const LaunchCtx& ctx, bool f32, int pixfmt, const DltRig<double>& rig64,
                        const DltRig<float>& rig32, const void* d_xy, int n_use, int64_t n_frames,
                        int64_t cam_stride, const BatchOut& out) {
   if (n_frames <= 0) return cudaSuccess;
+  using P32 = DltPolicy<float, true>;
   using P64 = DltPolicy<double, false>;
+  using T64 = PolicyTile<P64, 1>;
   if (f32) {
-    switch (pixfmt) {
-      case PIX_F32: return launch_dlt_f32<PIX_F32>(ctx, rig32, d_xy, n_use, n_frames, cam_stride, out);
-      case PIX_F64: return launch_dlt_f32<PIX_F64>(ctx, rig32, d_xy, n_use, n_frames, cam_stride, out);
-      default: return launch_dlt_f32<PIX_U16>(ctx, rig32, d_xy, n_use, n_frames, cam_stride, out);
+    const DltRigX2 x2 = make_x2(rig32);
+    if (ctx.debug_stream && pixfmt == PIX_F32)
+      return launch_streamed<StreamProbeTile, P32, PIX_F32, 2, 3, 2, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+    if (pixfmt == PIX_F32) {
+      switch (ctx.variant) {  // tuning variants (TRI_VARIANT)
+        case 1: return launch_streamed<DltX2Tile<false>, P32, PIX_F32, 2, 2, 3, 1>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 2: return launch_streamed<DltX2Tile<true>, P32, PIX_F32, 2, 2, 3, 0>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 3: return launch_streamed<DltX2Tile<true>, P32, PIX_F32, 2, 3, 2, 0>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 4: return launch_streamed<DltX2Tile<true>, P32, PIX_F32, 2, 2, 3, -1>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 5: return launch_streamed<DltX2Tile<false>, P32, PIX_F32, 2, 2, 3, 0>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 6: return launch_streamed<DltX2Tile<false>, P32, PIX_F32, 2, 3, 2, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        default: return launch_streamed<DltX2Tile<true>, P32, PIX_F32, 2, 2, 3, 0>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      }
+    }
+    if (pixfmt == PIX_F64) return launch_streamed<DltX2Tile<false>, P32, PIX_F64, 2, 3, 2, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+    return launch_streamed<DltX2Tile<true>, P32, PIX_U16, 2, 2, 3, 0>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+  }
+  if (pixfmt == PIX_F32) {
+    switch (ctx.variant) {
+      case 1: return launch_streamed<T64, P64, PIX_F32, 1, 2, 4, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 2: return launch_streamed<T64, P64, PIX_F32, 1, 3, 4, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 3: return launch_streamed<T64, P64, PIX_F32, 1, 3, 3, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 4: return launch_streamed<T64, P64, PIX_F32, 1, 3, 4, -1>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 5: return launch_streamed<T64, P64, PIX_F32, 1, 4, 5, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 6: return launch_streamed<PolicyTile<P64, 2>, P64, PIX_F32, 2, 3, 2, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 7: return launch_streamed<PolicyTile<P64, 2>, P64, PIX_F32, 2, 2, 3, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 8: return launch_streamed<T64, P64, PIX_F32, 1, 4, 3, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      default: return launch_streamed<PolicyTile<P64, 2>, P64, PIX_F32, 2, 3, 2, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
     }
   }
-  switch (pixfmt) {
-    case PIX_F32: return launch_batch_policy<P64, PIX_F32, 1, 3>(ctx, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
-    case PIX_F64: return launch_batch_policy<P64, PIX_F64, 1, 3>(ctx, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
-    default: return launch_batch_policy<P64, PIX_U16, 1, 3>(ctx, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
-  }
+  if (pixfmt == PIX_F64) return launch_streamed<T64, P64, PIX_F64, 1, 4, 3, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+  return launch_streamed<PolicyTile<P64, 2>, P64, PIX_U16, 2, 3, 2, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
 }
 
 }  // namespace tri

@@ -1,0 +1,404 @@
+// tri_pipe.cuh -- persistent, TMA-fed streaming kernel for the batched triangulatePoints hot path.
+//
+// The first generation (tri_batch.cuh: load 8 rows -> compute -> store, one tile per CTA) left the
+// memory system idle while a warp computed: ncu (profiles/r1_*) showed 59-61 % DRAM throughput with
+// `long_scoreboard` the top stall and only ~5.6 warps per scheduler to cover it.  Here the loads are
+// decoupled from the math, the Blackwell way:
+//   * grid = SMs x resident CTAs, each CTA walks tiles  t = blockIdx.x, += gridDim.x;
+//   * one elected thread streams a tile's camera rows (contiguous, TILE x 8 B each) into a
+//     STAGES-deep shared-memory ring with 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP), each
+//     stage completing on an mbarrier (expect_tx = bytes of the stage);
+//   * all threads wait on the stage's mbarrier, pull their pixels into registers with conflict-free
+//     LDS.128, release the stage (the producer re-arms it for tile t + STAGES*grid at once) and only
+//     then start the solve -- so STAGES tiles are always in flight per CTA, whatever the math costs;
+//   * the 12-byte points are staged in a double-buffered shared tile and leave as ONE bulk store
+//     (cp.async.bulk.global.shared::cta) per tile.
+// Algorithmic traffic is unchanged: 8 B x cameras in, 12 B out per frame; nothing is re-read.
+#pragma once
+#include "tri_batch.cuh"
+
+namespace tri {
+
+// ---- PTX wrappers (sm_90+ bulk-async / mbarrier; sm_100a here) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+
+// raw pixels of FPT consecutive frames of one camera, as they sit in the shared-memory stage
+template <int PIX, int FPT> struct RawPix;
+template <> struct RawPix<PIX_F32, 2> { using type = float4; };
+template <> struct RawPix<PIX_F32, 1> { using type = float2; };
+template <> struct RawPix<PIX_U16, 2> { using type = uint2; };
+template <> struct RawPix<PIX_U16, 1> { using type = unsigned; };
+
+template <typename T, int PIX, int FPT>
+__device__ __forceinline__ Views<T, PIX, FPT> decode(const typename RawPix<PIX, FPT>::type& q) {
+  Views<T, PIX, FPT> r;
+  if constexpr (PIX == PIX_F32 && FPT == 2) {
+    r.v[0] = pix_valid(q.x, q.y); r.v[1] = pix_valid(q.z, q.w);
+    r.x[0] = to_real<T>(q.x); r.y[0] = to_real<T>(q.y); r.x[1] = to_real<T>(q.z); r.y[1] = to_real<T>(q.w);
+  } else if constexpr (PIX == PIX_F32 && FPT == 1) {
+    r.v[0] = pix_valid(q.x, q.y); r.x[0] = to_real<T>(q.x); r.y[0] = to_real<T>(q.y);
+  } else if constexpr (PIX == PIX_U16 && FPT == 2) {
+    r.v[0] = q.x != 0xffffffffu; r.v[1] = q.y != 0xffffffffu;
+    r.x[0] = (T)(q.x & 0xffffu); r.y[0] = (T)(q.x >> 16); r.x[1] = (T)(q.y & 0xffffu); r.y[1] = (T)(q.y >> 16);
+  } else {
+    r.v[0] = q != 0xffffffffu; r.x[0] = (T)(q & 0xffffu); r.y[0] = (T)(q >> 16);
+  }
+  return r;
+}
+
+// Tile solver built from a scalar policy (tri_batch.cuh): FPT frames per thread, one after the other.
+template <class S, int FPT_>
+struct PolicyTile {
+  static constexpr int FPT = FPT_;
+  using Rig = typename S::Rig;
+  template <int NC, int PIX>
+  static __device__ __forceinline__ void run(const Rig& rig, const typename RawPix<PIX, FPT>::type (&raw)[NC], int opt,
+                                             float (&X)[FPT][3], uint32_t (&mask)[FPT]) {
+    using T = typename S::T;
+    typename S::Acc acc[FPT];
+#pragma unroll
+    for (int j = 0; j < FPT; j++) mask[j] = 0;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const Views<T, PIX, FPT> w = decode<T, PIX, FPT>(raw[c]);
+#pragma unroll
+      for (int j = 0; j < FPT; j++)
+        { S::add(rig, c, w.x[j], w.y[j], w.v[j], acc[j]); mask[j] |= (w.v[j] ? 1u : 0u) << c; }
+    }
+#pragma unroll
+    for (int j = 0; j < FPT; j++) {
+      T P[3] = {0, 0, 0};
+      int it = 0;
+      if (__popc(mask[j]) >= 2) { S::solve(rig, acc[j], __popc(mask[j]), P, opt, it); S::to_world(rig, P); }
+      X[j][0] = (float)P[0]; X[j][1] = (float)P[1]; X[j][2] = (float)P[2];
+    }
+  }
+};
+
+template <int NC, int PIX, int FPT, int STAGES, int OUTBUFS = 2>
+struct PipeLayout {
+  static constexpr int TILE = BATCH_THREADS * FPT;
+  static constexpr int PB = PIX == PIX_F32 ? 8 : 4;
+  static constexpr int ROW = TILE * PB;
+  static constexpr int STAGE = NC * ROW;
+  static constexpr int OUT = TILE * 12;
+  static constexpr int BYTES = STAGES * STAGE + OUTBUFS * OUT + STAGES * 8;
+};
+
+template <class TS, int NC, int PIX, int STAGES, int MINB, int OUTBUFS>
+__global__ void __launch_bounds__(BATCH_THREADS, MINB)
+pipe_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restrict__ xy, int64_t row_bytes, int64_t n_tiles,
+            BatchOut out, int opt, unsigned long long* first_bad, int64_t frame_base) {
+  constexpr int FPT = TS::FPT;
+  using L = PipeLayout<NC, PIX, FPT, STAGES, OUTBUFS>;
+  using Raw = typename RawPix<PIX, FPT>::type;
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* in = smem;
+  float* outb = reinterpret_cast<float*>(smem + STAGES * L::STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE + OUTBUFS * L::OUT);
+  const int tid = threadIdx.x;
+  const int64_t stride = gridDim.x;
+  int64_t tile = blockIdx.x;
+  // Rig constants live in shared memory: operands arrive by broadcast LDS.128 on the (idle) LSU pipe.
+  // Read straight from the parameter bank every FMA row needs a second constant in a register, and
+  // those LDCs saturated the ADU pipe (ncu r1c: adu 53-68 %, the top pipe).
+  __shared__ __align__(16) typename TS::Rig srig;
+  for (int i = tid; i < (int)(sizeof(typename TS::Rig) / 4); i += BATCH_THREADS)
+    reinterpret_cast<int*>(&srig)[i] = reinterpret_cast<const int*>(&rig)[i];
+
+  auto issue = [&](int s, int64_t t) {  // producer (thread 0): one stage = NC contiguous row segments
+    mbar_expect_tx(&full[s], L::STAGE);
+    const char* src = xy + t * L::ROW;
+#pragma unroll
+    for (int c = 0; c < NC; c++) bulk_load(in + s * L::STAGE + c * L::ROW, src + c * row_bytes, L::ROW, &full[s]);
+  };
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++)
+      if (tile + s * stride < n_tiles) issue(s, tile + s * stride);
+  }
+
+  for (int k = 0; tile < n_tiles; k++, tile += stride) {
+    const int s = k % STAGES;
+    mbar_wait(&full[s], (uint32_t)((k / STAGES) & 1));
+    Raw raw[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) raw[c] = reinterpret_cast<const Raw*>(in + s * L::STAGE + c * L::ROW)[tid];
+    if (tid == 0) bulk_wait_read<OUTBUFS - 1>();  // the store that last used this tile's out buffer has drained
+    __syncthreads();                    // every thread holds its pixels: stage s is free again
+    if (tid == 0 && tile + STAGES * stride < n_tiles) issue(s, tile + STAGES * stride);
+
+    float X[FPT][3];
+    uint32_t mask[FPT];
+    TS::template run<NC, PIX>(srig, raw, opt, X, mask);
+
+    const int64_t f0 = tile * L::TILE + (int64_t)tid * FPT;
+#pragma unroll
+    for (int j = 0; j < FPT; j++)
+      if (__popc(mask[j]) < 2) atomicMin(first_bad, (unsigned long long)(frame_base + f0 + j));
+    if (out.mask) {
+      if constexpr (FPT == 2) reinterpret_cast<uint2*>(out.mask)[f0 / 2] = make_uint2(mask[0], mask[1]);
+      else out.mask[f0] = mask[0];
+    }
+    float* ob = outb + (k % OUTBUFS) * (L::OUT / 4) + 3 * FPT * tid;
+    if constexpr (FPT == 2) {
+      float2* o2 = reinterpret_cast<float2*>(ob);
+      o2[0] = make_float2(X[0][0], X[0][1]); o2[1] = make_float2(X[0][2], X[1][0]); o2[2] = make_float2(X[1][1], X[1][2]);
+    } else {
+      ob[0] = X[0][0]; ob[1] = X[0][1]; ob[2] = X[0][2];
+    }
+    fence_proxy_async();  // generic-proxy writes -> visible to the bulk (async-proxy) store
+    __syncthreads();
+    if (tid == 0) {
+      bulk_store(out.xyz_f32 + 3 * tile * L::TILE, outb + (k % OUTBUFS) * (L::OUT / 4), L::OUT);
+      bulk_commit();
+    }
+  }
+  if (tid == 0) bulk_wait_read<0>();
+}
+
+// Launch the pipelined kernel on the full tiles of [0, n_frames); returns the number of frames covered
+// (0 if the layout does not qualify: unaligned rows, optional outputs the lean kernel does not write).
+template <class TS, int PIX, int STAGES, int MINB, int OUTBUFS = 2>
+static cudaError_t launch_pipe(const LaunchCtx& ctx, const typename TS::Rig& rig, const void* d_xy, int n_use, int64_t n_frames,
+                               int64_t cam_stride, const BatchOut& out, int opt, int64_t* covered) {
+  *covered = 0;
+  constexpr int FPT = TS::FPT;
+  constexpr int TILE = BATCH_THREADS * FPT;
+  const char* xy = static_cast<const char*>(d_xy);
+  const int64_t row_bytes = cam_stride * pix_bytes(PIX);
+  const int64_t n_tiles = n_frames / TILE;
+  if (n_tiles == 0 || n_use < 2 || n_use > 8) return cudaSuccess;
+  if (!out.xyz_f32 || out.xyz_f64 || out.err || out.iters) return cudaSuccess;
+  if (((uintptr_t)xy & 15) || (row_bytes & 15) || ((uintptr_t)out.xyz_f32 & 15) || (out.mask && ((uintptr_t)out.mask & 7))) return cudaSuccess;
+  cudaError_t err = cudaSuccess;
+#define TRI_CASE(N)                                                                                                     \
+  case N: {                                                                                                             \
+    auto kern = pipe_kernel<TS, N, PIX, STAGES, MINB, OUTBUFS>;                                                                  \
+    constexpr int bytes = PipeLayout<N, PIX, FPT, STAGES, OUTBUFS>::BYTES;                                                       \
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);                               \
+    if (err != cudaSuccess) return err;                                                                                 \
+    int per_sm = 1;                                                                                                     \
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BATCH_THREADS, bytes);                           \
+    if (err != cudaSuccess) return err;                                                                                 \
+    const int64_t grid = std::min<int64_t>(n_tiles, (int64_t)ctx.sm_count * std::max(per_sm, 1));                       \
+    kern<<<(unsigned)grid, BATCH_THREADS, bytes, ctx.stream>>>(rig, xy, row_bytes, n_tiles, out, opt, ctx.d_first_bad,  \
+                                                               ctx.frame_base);                                         \
+  } break;
+  switch (n_use) { TRI_CASE(2) TRI_CASE(3) TRI_CASE(4) TRI_CASE(5) TRI_CASE(6) TRI_CASE(7) TRI_CASE(8) }
+#undef TRI_CASE
+  ++*ctx.launches;
+  *covered = n_tiles * TILE;
+  return cudaGetLastError();
+}
+
+// ---- generation 3: barrier-free per-thread async pipeline -----------------------------------------
+// ncu on pipe_kernel (profiles/r1c) showed the CTA-wide phases as the limiter: all warps of a CTA hit
+// the math pipe together (stall_math / not_selected) and then idle together at the barriers (16 % of
+// stall samples), so FMA/FP64 pipes and DRAM each sat near 58-61 %.  Here nothing synchronises across
+// warps: every thread prefetches ITS OWN pixels of the next STAGES tiles with cp.async (LDGSTS, 16 B per
+// camera row, fully coalesced per warp) into a private shared-memory slot, waits only on its own
+// cp.async group, pulls the slot into registers, re-arms it, and solves.  Warps drift apart freely, so
+// one warp's memory wait hides under another warp's FMAs.  The 12-byte points are transposed through a
+// per-warp shared tile (__syncwarp only) into coalesced 16-byte streaming stores.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <class TS, int NC, int PIX, int STAGES, int MINB, bool SMEM_RIG>
+__global__ void __launch_bounds__(BATCH_THREADS, MINB)
+stream_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restrict__ xy, int64_t row_bytes, int64_t n_tiles,
+              BatchOut out, int opt, unsigned long long* first_bad, int64_t frame_base) {
+  constexpr int FPT = TS::FPT;
+  using Raw = typename RawPix<PIX, FPT>::type;
+  constexpr int TILE = BATCH_THREADS * FPT;
+  constexpr int RB = (int)sizeof(Raw);  // bytes per thread per camera per tile
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: [STAGES][NC][BATCH_THREADS] Raw | [warps][32 * FPT * 3] float
+  Raw* slots = reinterpret_cast<Raw*>(smem);
+  float* outw = reinterpret_cast<float*>(smem + STAGES * NC * BATCH_THREADS * RB) + (threadIdx.x >> 5) * (32 * FPT * 3);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t stride = gridDim.x;
+  int64_t tile = blockIdx.x;
+
+  __shared__ __align__(16) typename TS::Rig srig_store[1];
+  if constexpr (SMEM_RIG) {
+    for (int i = tid; i < (int)(sizeof(typename TS::Rig) / 4); i += BATCH_THREADS)
+      reinterpret_cast<int*>(&srig_store[0])[i] = reinterpret_cast<const int*>(&rig)[i];
+    __syncthreads();
+  }
+  const typename TS::Rig& R = SMEM_RIG ? srig_store[0] : rig;
+
+  auto prefetch = [&](int s, int64_t t) {
+    const char* src = xy + (t * BATCH_THREADS + tid) * RB;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      Raw* dst = slots + (s * NC + c) * BATCH_THREADS + tid;
+      if constexpr (RB == 16) cp_async16(dst, src + c * row_bytes);
+      else if constexpr (RB == 8) cp_async8(dst, src + c * row_bytes);
+      else cp_async4(dst, src + c * row_bytes);
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES; s++) {
+    if (tile + s * stride < n_tiles) prefetch(s, tile + s * stride);
+    cp_async_commit();
+  }
+
+  for (int k = 0; tile < n_tiles; k++, tile += stride) {
+    const int s = k % STAGES;
+    cp_async_wait<STAGES - 1>();  // this thread's copies for tile k have landed
+    Raw raw[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) raw[c] = slots[(s * NC + c) * BATCH_THREADS + tid];
+    if (tile + STAGES * stride < n_tiles) prefetch(s, tile + STAGES * stride);
+    cp_async_commit();
+
+    float X[FPT][3];
+    uint32_t mask[FPT];
+    TS::template run<NC, PIX>(R, raw, opt, X, mask);
+
+    const int64_t f0 = tile * TILE + (int64_t)tid * FPT;
+#pragma unroll
+    for (int j = 0; j < FPT; j++)
+      if (__popc(mask[j]) < 2) atomicMin(first_bad, (unsigned long long)(frame_base + f0 + j));
+    if (out.mask) {
+      if constexpr (FPT == 2) reinterpret_cast<uint2*>(out.mask)[f0 / 2] = make_uint2(mask[0], mask[1]);
+      else out.mask[f0] = mask[0];
+    }
+    // warp-level transpose: 32 x FPT x 12 B contiguous in global memory
+    __syncwarp();  // the previous tile's reads of this warp's tile are done
+    if constexpr (FPT == 2) {
+      float2* o2 = reinterpret_cast<float2*>(outw) + 3 * lane;
+      o2[0] = make_float2(X[0][0], X[0][1]); o2[1] = make_float2(X[0][2], X[1][0]); o2[2] = make_float2(X[1][1], X[1][2]);
+    } else {
+      outw[3 * lane] = X[0][0]; outw[3 * lane + 1] = X[0][1]; outw[3 * lane + 2] = X[0][2];
+    }
+    __syncwarp();
+    float4* dst = reinterpret_cast<float4*>(out.xyz_f32 + 3 * (tile * TILE + (int64_t)(tid - lane) * FPT));
+    const float4* src4 = reinterpret_cast<const float4*>(outw);
+    constexpr int N4 = 32 * FPT * 3 / 4;  // 24 or 48 float4 per warp
+#pragma unroll
+    for (int i = lane; i < N4; i += 32) __stcs(dst + i, src4[i]);
+  }
+  cp_async_wait<0>();
+}
+
+template <class TS, int PIX, int STAGES, int MINB, bool SMEM_RIG>
+static cudaError_t launch_stream(const LaunchCtx& ctx, const typename TS::Rig& rig, const void* d_xy, int n_use, int64_t n_frames,
+                                 int64_t cam_stride, const BatchOut& out, int opt, int64_t* covered) {
+  *covered = 0;
+  constexpr int FPT = TS::FPT;
+  constexpr int TILE = BATCH_THREADS * FPT;
+  using Raw = typename RawPix<PIX, FPT>::type;
+  const char* xy = static_cast<const char*>(d_xy);
+  const int64_t row_bytes = cam_stride * pix_bytes(PIX);
+  const int64_t n_tiles = n_frames / TILE;
+  if (n_tiles == 0 || n_use < 2 || n_use > 8) return cudaSuccess;
+  if (!out.xyz_f32 || out.xyz_f64 || out.err || out.iters) return cudaSuccess;
+  const int align = (int)sizeof(Raw);
+  if (((uintptr_t)xy % align) || (row_bytes % align) || ((uintptr_t)out.xyz_f32 & 15) || (out.mask && ((uintptr_t)out.mask & 7))) return cudaSuccess;
+  cudaError_t err = cudaSuccess;
+#define TRI_CASE(N)                                                                                                     \
+  case N: {                                                                                                             \
+    auto kern = stream_kernel<TS, N, PIX, STAGES, MINB, SMEM_RIG>;                                                      \
+    constexpr int bytes = STAGES * N * BATCH_THREADS * (int)sizeof(Raw) + (BATCH_THREADS / 32) * 32 * FPT * 12;         \
+    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);                               \
+    if (err != cudaSuccess) return err;                                                                                 \
+    int per_sm = 1;                                                                                                     \
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BATCH_THREADS, bytes);                           \
+    if (err != cudaSuccess) return err;                                                                                 \
+    const int64_t grid = std::min<int64_t>(n_tiles, (int64_t)ctx.sm_count * std::max(per_sm, 1));                       \
+    kern<<<(unsigned)grid, BATCH_THREADS, bytes, ctx.stream>>>(rig, xy, row_bytes, n_tiles, out, opt, ctx.d_first_bad,  \
+                                                               ctx.frame_base);                                         \
+  } break;
+  switch (n_use) { TRI_CASE(2) TRI_CASE(3) TRI_CASE(4) TRI_CASE(5) TRI_CASE(6) TRI_CASE(7) TRI_CASE(8) }
+#undef TRI_CASE
+  ++*ctx.launches;
+  *covered = n_tiles * TILE;
+  return cudaGetLastError();
+}
+
+// Sub-range helper for the tail after the pipelined tiles.
+inline BatchOut advance(const BatchOut& o, int64_t frames) {
+  BatchOut r = o;
+  if (r.xyz_f32) r.xyz_f32 += 3 * frames;
+  if (r.xyz_f64) r.xyz_f64 += 3 * frames;
+  if (r.mask) r.mask += frames;
+  if (r.err) r.err += frames;
+  if (r.iters) r.iters += frames;
+  return r;
+}
+
+
+// pipelined kernel on the full tiles, the scalar policy kernel on whatever is left
+template <class TS, class S, int PIX, int FPT, int STAGES, int MINB, int OUTBUFS>
+static cudaError_t launch_streamed(const LaunchCtx& ctx, const typename TS::Rig& tile_rig, const typename S::Rig& rig,
+                                   const void* d_xy, int n_use, int64_t n_frames, int64_t cam_stride, const BatchOut& out, int opt) {
+  int64_t covered = 0;
+  if constexpr (PIX != PIX_F64) {
+    cudaError_t err;
+    if constexpr (OUTBUFS == 0)        // generation 3: barrier-free cp.async pipeline, rig from the parameter bank
+      err = launch_stream<TS, PIX, STAGES, MINB, false>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
+    else if constexpr (OUTBUFS == -1)  // generation 3, rig staged in shared memory
+      err = launch_stream<TS, PIX, STAGES, MINB, true>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
+    else
+      err = launch_pipe<TS, PIX, STAGES, MINB, OUTBUFS>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
+    if (err != cudaSuccess || covered == n_frames) return err;
+  }
+  LaunchCtx rest = ctx;
+  rest.frame_base += covered;
+  return launch_batch_policy<S, PIX, FPT, (MINB > 3 ? 3 : MINB)>(rest, rig, static_cast<const char*>(d_xy) + covered * pix_bytes(PIX), n_use,
+                                                n_frames - covered, cam_stride, advance(out, covered), opt);
+}
+
+}  // namespace tri

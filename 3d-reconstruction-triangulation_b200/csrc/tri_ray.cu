@@ -16,7 +16,7 @@
 // tri_ray_ref.cu.
 #include <float.h>
 
-#include "tri_batch.cuh"
+#include "tri_pipe.cuh"
 
 namespace tri {
 
@@ -39,7 +39,8 @@ struct RayPolicy {
     const T vx = fma_(r.ax[c], x, r.bx[c]), vy = fma_(r.ay[c], y, r.by[c]);
     inv = T(1) / fma_(vx, vx, fma_(vy, vy, r.dd[c]));
   }
-  static __device__ __forceinline__ void add(const Rig& r, int c, T x, T y, Acc& a) {
+  static __device__ __forceinline__ void add(const Rig& r, int c, T x, T y, bool valid, Acc& a) {
+    if (!valid) return;
     T u[3], inv;
     ray(r, c, x, y, u, inv);
     const T s0 = mul_(u[0], inv), s1 = mul_(u[1], inv), s2 = mul_(u[2], inv);
@@ -140,16 +141,21 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
   using P64 = RayPolicy<double>;
   const int opt = lm ? 1 : 0;
   if (f32) {  // FP32: closed form only (the gain ratio of the LM loop needs S to ~1e-9 relative)
+    using T32 = PolicyTile<P32, 2>;
     switch (pixfmt) {
-      case PIX_F32: return launch_batch_policy<P32, PIX_F32, 2, 2>(ctx, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case PIX_F64: return launch_batch_policy<P32, PIX_F64, 2, 2>(ctx, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-      default: return launch_batch_policy<P32, PIX_U16, 2, 2>(ctx, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case PIX_F32: return launch_streamed<T32, P32, PIX_F32, 2, 2, 2, 0>(ctx, r32, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case PIX_F64: return launch_streamed<T32, P32, PIX_F64, 2, 2, 2, 0>(ctx, r32, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      default: return launch_streamed<T32, P32, PIX_U16, 2, 2, 2, 0>(ctx, r32, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
     }
   }
+  using T64 = PolicyTile<P64, 1>;
   switch (pixfmt) {
-    case PIX_F32: return launch_batch_policy<P64, PIX_F32, 1, 2>(ctx, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
-    case PIX_F64: return launch_batch_policy<P64, PIX_F64, 1, 2>(ctx, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
-    default: return launch_batch_policy<P64, PIX_U16, 1, 2>(ctx, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+    case PIX_F32:
+      if (ctx.variant == 1) return launch_streamed<PolicyTile<P64, 2>, P64, PIX_F32, 2, 2, 1, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+      if (ctx.variant == 2) return launch_streamed<T64, P64, PIX_F32, 1, 3, 3, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+      return launch_streamed<T64, P64, PIX_F32, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+    case PIX_F64: return launch_streamed<T64, P64, PIX_F64, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+    default: return launch_streamed<T64, P64, PIX_U16, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
   }
 }
 

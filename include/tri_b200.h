@@ -46,7 +46,9 @@ enum tri_flags {
                                      RayTriangulator.cpp:28-44,100-104); bit-comparable          */
   TRI_RAY_CLOSED_FORM = 1u << 3,  /* ray: one exact Newton step (the objective is quadratic)     */
   TRI_PIX_F64 = 1u << 4,          /* pixels are double2 (cv::Point2d) instead of float2          */
-  TRI_PIX_U16 = 1u << 5           /* pixels are ushort2; (0xFFFF,0xFFFF) is the missing marker   */
+  TRI_PIX_U16 = 1u << 5,          /* pixels are ushort2; (0xFFFF,0xFFFF) is the missing marker   */
+  TRI_DEBUG_STREAM = 1u << 30     /* measurement aid (matrix + TRI_F32 + float2 only): the streaming
+                                     pipeline with a near-empty solve, xyz = (sum x, sum y, views)  */
 };
 /* default ray solver (no TRI_RAY_* flag): Levenberg-Marquardt with the analytic Jacobian and
  * cv::LMSolver's damping schedule, register resident.                                          */
