@@ -1,0 +1,110 @@
+#include "DetectionsContainer.h"
+
+#include <algorithm>
+#include <filesystem>
+#include <fstream>
+#include <sstream>
+#include <stdexcept>
+
+DetectionsContainer::DetectionsContainer(const char* path, int offset, int recordSize, int startFrame, int endFrame) {
+  readFiles(getFiles(path), offset, recordSize, startFrame, endFrame);
+}
+
+DetectionsContainer::DetectionsContainer(int camCount) : n_cameras(camCount), data((size_t)camCount) {}
+
+std::vector<std::string> DetectionsContainer::getFiles(const char* path) {
+  // every *.csv below `path`, camera order = sorted path order (DetectionsContainer.cpp:78-92)
+  std::vector<std::string> files;
+  for (const auto& entry : std::filesystem::recursive_directory_iterator(path)) {
+    const std::string name = entry.path().u8string();
+    if (name.find(".csv") != std::string::npos && name.find(".avi") == std::string::npos) files.push_back(name);
+  }
+  std::sort(files.begin(), files.end());
+  return files;
+}
+
+void DetectionsContainer::readFiles(const std::vector<std::string>& files, int offset, int recordSize, int startFrame,
+                                    int endFrame) {
+  // Row = frame,(x,y,w,h,cx,cy,conf) x k.  Every token goes through std::stoi (so 0.97 -> 0); the
+  // detection is the box centre, fields 5 and 6 of the record; missing frame numbers become empty
+  // frames (DetectionsContainer.cpp:19-76).
+  for (const std::string& name : files) {
+    std::ifstream file(name);
+    data.emplace_back();
+    Cameras& cam = data.back();
+    std::string line, token;
+    int n_line = 0, frame = -1;
+    while (std::getline(file, line)) {
+      if (offset > n_line++) continue;
+      std::vector<int> fields;
+      std::istringstream iss(line);
+      while (std::getline(iss, token, ','))
+        if (!token.empty()) fields.push_back(std::stoi(token));
+      if (fields.empty()) throw std::runtime_error("Invalid CSV file!");
+      if ((fields[0] <= startFrame || fields[0] > endFrame) && startFrame != endFrame) {
+        frame = fields[0];
+        continue;
+      }
+      for (int i = 0; i < fields[0] - frame - 1; i++) cam.emplace_back();
+      frame = fields[0];
+      if ((fields.size() - 1) % (size_t)recordSize != 0) throw std::runtime_error("Invalid CSV file!");
+      cam.emplace_back();
+      for (size_t j = 0; j < fields.size() / (size_t)recordSize; j++)
+        cam.back().emplace_back((double)fields[j * recordSize + 5], (double)fields[j * recordSize + 6]);
+    }
+  }
+  if (data.size() < 2) throw std::runtime_error("There must be at least 2 cameras");
+  for (size_t i = 1; i < data.size(); i++)
+    if (data[i - 1].size() != data[i].size()) throw std::runtime_error("Number of frames on all cameras must be the same");
+  n_frames = (int)data[0].size();
+  n_cameras = (int)data.size();
+}
+
+std::vector<Detections> DetectionsContainer::getFrame(int i) const {
+  std::vector<Detections> frame;
+  for (const Cameras& cam : data) frame.push_back(cam[i]);
+  return frame;
+}
+
+std::vector<int> DetectionsContainer::getDetectionsCount(int frame) const {
+  std::vector<int> n((size_t)n_cameras);
+  for (int i = 0; i < n_cameras; i++) n[i] = (int)data[i][frame].size() + 1;  // + "no detection"
+  return n;
+}
+
+void DetectionsContainer::addEmptyFrame() {
+  for (Cameras& cam : data) cam.emplace_back();
+  n_frames = (int)data[0].size();
+}
+
+void DetectionsContainer::addDetectionToCamera(cv::Point2d det, int cam) { data[cam].back().push_back(det); }
+
+std::vector<std::vector<cv::Point2d>> DetectionsContainer::getDataForTriangulation() {
+  std::vector<std::vector<cv::Point2d>> result((size_t)n_cameras);
+  for (int frame = 0; frame < n_frames; frame++)
+    for (int cam = 0; cam < n_cameras; cam++) {
+      const size_t size = data[cam][frame].size();
+      if (size > 1)
+        throw std::runtime_error(
+            "Function 'getDataForTriangulation' can be used only for one drone. Each frame can have max one detection");
+      result[cam].push_back(size == 1 ? data[cam][frame][0] : cv::Point2d(-1, -1));
+    }
+  return result;
+}
+
+void DetectionsContainer::toCSR(std::vector<int32_t>& offsets, std::vector<double>& xy) const {
+  offsets.assign((size_t)n_cameras * (n_frames + 1), 0);
+  xy.clear();
+  int32_t at = 0;
+  for (int cam = 0; cam < n_cameras; cam++) {
+    for (int frame = 0; frame < n_frames; frame++) {
+      offsets[(size_t)cam * (n_frames + 1) + frame] = at;
+      for (const cv::Point2d& p : data[cam][frame]) {
+        xy.push_back(p.x);
+        xy.push_back(p.y);
+        at++;
+      }
+    }
+    offsets[(size_t)cam * (n_frames + 1) + n_frames] = at;
+  }
+}

@@ -1,0 +1,135 @@
+"""The C++ host mirror of the reference interface (3d-reconstruction-triangulation_b200/host):
+CPU checks of the loaders (no engine calls) and, on the GPU, the CLI clone end to end."""
+import glob
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+import py_twin
+import tri_b200 as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "3d-reconstruction-triangulation_b200", "host")
+G = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def host_bins():
+    subprocess.check_call(["make", "-s", "-C", HOST])
+    return os.path.join(HOST, "host_selftest"), os.path.join(HOST, "tri_main")
+
+
+def test_cpp_loaders_match_python_host_and_twin(host_bins):
+    out = subprocess.check_output([host_bins[0], G + "/S09_D6_cameras.xml", G + "/csv_sample"], text=True).splitlines()
+    cams = T.load_cameras_xml(G + "/S09_D6_cameras.xml")
+    rows = [l.split() for l in out if l.startswith("cam ")]
+    assert out[0] == "cameras %d" % len(cams) and len(rows) == len(cams)
+    for r, c in zip(rows, cams):
+        assert (int(r[1]), int(r[2]), int(r[3])) == (c.cam_id, c.width, c.height)
+        assert float(r[4]) == c.fovy and float(r[5]) == c.fx
+        assert np.array_equal(np.array([float(v) for v in r[6:18]]), c.P.reshape(-1))  # bit-identical constants
+    files = sorted(glob.glob(G + "/csv_sample/*.csv"))
+    want = py_twin.read_csv_files(files)  # the twin's restatement of DetectionsContainer::readFiles
+    n_cam, n_frames = (int(v) for v in [l for l in out if l.startswith("container")][0].split()[1:])
+    assert n_cam == len(want) and n_frames == len(want[0])
+    dets = {(int(l.split()[1]), int(l.split()[2])): [float(v) for v in l.split()[4:]] for l in out if l.startswith("det ")}
+    for c in range(n_cam):
+        for f in range(n_frames):
+            assert dets[(c, f)] == [v for p in want[c][f] for v in p]
+    assert len({len(want[c][f]) for c in range(n_cam) for f in range(n_frames)}) > 1  # ragged detection counts
+    n_det = sum(len(want[c][f]) for c in range(n_cam) for f in range(n_frames))
+    assert [l for l in out if l.startswith("csr")][0] == "csr %d %d %d" % (n_cam * (n_frames + 1), n_det, n_det)
+
+
+def test_cpp_csv_reader_gaps_and_truncation(host_bins, tmp_path):
+    """Missing frame numbers become empty frames, id-only rows are frames without detections, every token
+    goes through stoi (0.97 -> 0, 12.9 -> 12): DetectionsContainer.cpp:19-76."""
+    a = "0,1,2,3,4,100,200,0.97\n3,1,2,3,4,101.9,201,0.5,5,6,7,8,300,400,0.99\n4\n6,1,1,1,1,7,8,1\n"
+    b = "0,1,2,3,4,110,210,0.97\n1,1,2,3,4,111,211,0.9\n2\n3\n4,9,9,9,9,114,214,0.3\n5\n6,1,1,1,1,17,18,1\n"
+    (tmp_path / "camA.csv").write_text(a)
+    (tmp_path / "camB.csv").write_text(b)
+    out = subprocess.check_output([host_bins[0], G + "/R02_D1_cameras.xml", str(tmp_path)], text=True).splitlines()
+    want = py_twin.read_csv_files([str(tmp_path / "camA.csv"), str(tmp_path / "camB.csv")])
+    assert [l for l in out if l.startswith("container")][0] == "container 2 7"
+    dets = {(int(l.split()[1]), int(l.split()[2])): [float(v) for v in l.split()[4:]] for l in out if l.startswith("det ")}
+    for c in range(2):
+        for f in range(7):
+            assert dets[(c, f)] == [v for p in want[c][f] for v in p]
+    assert dets[(0, 1)] == [] and dets[(0, 2)] == [] and dets[(0, 4)] == [] and dets[(0, 3)] == [101.0, 201.0, 300.0, 400.0]
+    # unequal frame counts are rejected like the reference does
+    (tmp_path / "camB.csv").write_text(b + "7,1,1,1,1,1,1,1\n")
+    r = subprocess.run([host_bins[0], G + "/R02_D1_cameras.xml", str(tmp_path)], capture_output=True, text=True)
+    assert r.returncode != 0 and "Number of frames on all cameras must be the same" in r.stderr
+
+
+def test_cli_usage_errors(host_bins):
+    r = subprocess.run([host_bins[1]], capture_output=True, text=True)
+    assert r.returncode == 1 and "cameras_path" in r.stderr
+
+
+def write_csvs(tmp, dets_npz, n_frames=None):
+    offs, xy, nc, nf = O.load_dets(dets_npz)
+    nf = n_frames or nf
+    o = offs.reshape(nc, -1)
+    names = [str(n) for n in np.load(dets_npz)["files"]]
+    for c in range(nc):
+        with open(os.path.join(tmp, names[c]), "w") as fh:
+            for f in range(nf):
+                rec = [str(f)]
+                for x, y in xy[o[c, f]:o[c, f + 1]]:
+                    rec += [str(int(x) - 10), str(int(y) - 5), "20", "10", str(int(x)), str(int(y)), "0.9"]
+                if len(rec) > 1:  # the reference's CSVs simply omit frames without detections... or hold only the id
+                    fh.write(",".join(rec) + "\n")
+                elif f % 2 == 0:
+                    fh.write(str(f) + "\n")
+    return nc, nf
+
+
+def read_dump(path):
+    raw = open(path, "rb").read()
+    d, f, c = struct.unpack("iii", raw[:12])
+    p = np.frombuffer(raw, np.float64, d * f * 3, 12).reshape(d, f, 3)
+    a = np.frombuffer(raw, np.int8, d * f * c, 12 + 8 * d * f * 3).reshape(d, f, c)
+    ph = np.frombuffer(raw, np.uint8, d * f, 12 + 8 * d * f * 3 + d * f * c).reshape(d, f)
+    return p, a, ph
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,golden,frames,drones,data", [
+    ("matrix", "golden_R02_D1_classify_matrix.npz", None, 1, "R02_D1"),
+    ("ray", "golden_R02_D1_classify_ray.npz", 40, 1, "R02_D1"),
+    ("matrix", "golden_S09_D6_classify_matrix.npz", 120, 6, "S09_D6"),
+])
+def test_cli_end_to_end(host_bins, tmp_path, kind, golden, frames, drones, data):
+    """./main cameras.xml data/ --n_drones N --triangulator K: PLY files + 'Execution time', same paths and
+    assignment indices as the golden vectors."""
+    csv_dir = tmp_path / "data"
+    csv_dir.mkdir()
+    nc, nf = write_csvs(str(csv_dir), G + "/%s_dets.npz" % data, frames)
+    r = subprocess.run([host_bins[1], G + "/%s_cameras.xml" % data, str(csv_dir), "--n_drones", str(drones), "--triangulator", kind,
+                        "--dump", str(tmp_path / "dump.bin")], capture_output=True, text=True, cwd=str(tmp_path))
+    assert r.returncode == 0, r.stderr
+    assert "Execution time: " in r.stdout
+    g = np.load(G + "/" + golden)
+    p, a, ph = read_dump(str(tmp_path / "dump.bin"))
+    assert np.array_equal(a, g["assign"]) and np.array_equal(ph, g["phase"])
+    np.testing.assert_allclose(p, g["paths"], rtol=1e-9, atol=1e-5)
+    for d in range(drones):
+        lines = open(tmp_path / "results" / ("drone%d.ply" % (d + 1))).read().splitlines()
+        assert lines[0] == "ply" and lines[2] == "element vertex %d" % nf and lines[8] == "end_header"
+        got = np.array([[float(v) for v in l.split()] for l in lines[9:]])
+        np.testing.assert_allclose(got, g["paths"][d], rtol=2e-5, atol=1e-3)  # default ostream precision: 6 digits
+
+
+@pytest.mark.gpu
+def test_cli_rejects_unknown_triangulator(host_bins, tmp_path):
+    csv_dir = tmp_path / "data"
+    csv_dir.mkdir()
+    write_csvs(str(csv_dir), G + "/R02_D1_dets.npz", 5)
+    r = subprocess.run([host_bins[1], G + "/R02_D1_cameras.xml", str(csv_dir), "--triangulator", "svd"], capture_output=True, text=True,
+                       cwd=str(tmp_path))
+    assert r.returncode != 0 and "Invalid --triangulator argument" in r.stderr
