@@ -64,7 +64,8 @@ class ClassifyStats(C.Structure):
 
 
 EXPORTS = ["tri_version", "tri_last_error", "tri_device_count", "tri_create", "tri_destroy", "tri_engine_device",
-           "tri_engine_cameras", "tri_kernel_launches", "tri_triangulate_points", "tri_triangulate_points_device",
+           "tri_engine_cameras", "tri_kernel_launches", "tri_triangulate_points", "tri_triangulate_points_multi",
+           "tri_triangulate_points_device",
            "tri_device_status", "tri_triangulate_subsets", "tri_dist_from_ray", "tri_classify", "tri_host_alloc",
            "tri_host_free", "tri_device_alloc", "tri_device_free", "tri_copy_to_device", "tri_copy_to_host"]
 
@@ -90,6 +91,8 @@ def lib():
         L.tri_engine_cameras.argtypes = [C.c_void_p]
         L.tri_triangulate_points.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
                                              C.POINTER(_BatchOut), C.POINTER(C.c_int64)]
+        L.tri_triangulate_points_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_uint, C.c_void_p, C.c_int, C.c_int64,
+                                                   C.c_int64, C.POINTER(_BatchOut), C.POINTER(C.c_int64)]
         L.tri_triangulate_points_device.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_int, C.c_int64,
                                                     C.c_int64, C.POINTER(_BatchOut), C.c_void_p]
         L.tri_device_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
@@ -366,6 +369,23 @@ class Engine:
         _check(lib().tri_classify(self._h, mode, flags, n_drones, _np_ptr(offs), _np_ptr(xy), n_frames, _np_ptr(paths),
                                   _np_ptr(assign), _np_ptr(phase), C.byref(st)), mode)
         return dict(paths=paths, assign=assign, phase=phase, stats=st.as_dict())
+
+
+def triangulate_points_multi(engines, mode, xy, flags=0, want=("xyz_f64",)):
+    """tri_triangulate_points_multi: one host batch sharded over several engines (one per GPU)."""
+    xy = np.ascontiguousarray(xy)
+    fmt = _PIX_DTYPES[xy.dtype]
+    npc, nf = xy.shape[0], xy.shape[1]
+    out = {k: np.empty({"xyz_f32": (nf, 3), "xyz_f64": (nf, 3)}.get(k, (nf,)),
+                       {"xyz_f32": np.float32, "xyz_f64": np.float64, "mask": np.uint32, "err": np.float64, "iters": np.int32}[k])
+           for k in want}
+    bo = _BatchOut(*[out[k].ctypes.data if k in out else None for k in ("xyz_f32", "xyz_f64", "mask", "err", "iters")])
+    hs = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    bad = C.c_int64(-1)
+    st = lib().tri_triangulate_points_multi(hs, len(engines), mode, flags | fmt, _np_ptr(xy), npc, nf, nf, C.byref(bo), C.byref(bad))
+    out["first_bad_frame"] = bad.value
+    _check(st, mode)
+    return out
 
 
 def pinned_empty(shape, dtype):

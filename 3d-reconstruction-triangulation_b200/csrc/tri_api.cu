@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "tri_engine.cuh"
@@ -368,6 +369,50 @@ int tri_triangulate_points(tri_engine* e, int mode, unsigned flags, const void* 
     if (!(flags & TRI_ALLOW_TOO_FEW))
       return fail(TRI_ERR_TOO_FEW, mode == TRI_MATRIX ? "Too few rays are found" : "Too few detections are found");
   }
+  return TRI_OK;
+}
+
+int tri_triangulate_points_multi(tri_engine* const* engines, int n_engines, int mode, unsigned flags, const void* xy,
+                                 int n_point_cams, int64_t n_frames, int64_t cam_stride, const tri_batch_out* out,
+                                 int64_t* first_bad_frame) {
+  if (!engines || n_engines < 1) return fail(TRI_ERR_ARG, "no engines");
+  for (int g = 0; g < n_engines; g++)
+    if (!engines[g] || engines[g]->n_cams != engines[0]->n_cams) return fail(TRI_ERR_ARG, "engines must hold the same rig");
+  if (n_engines == 1) return tri_triangulate_points(engines[0], mode, flags, xy, n_point_cams, n_frames, cam_stride, out, first_bad_frame);
+  int fmt = 0, n_use = 0;
+  int st = check_batch_args(engines[0], mode, flags, xy, n_point_cams, n_frames, cam_stride, out, &n_use);
+  if (st != TRI_OK) return st;
+  if ((st = pix_format(flags, &fmt)) != TRI_OK) return st;
+  const size_t pb = pix_bytes(fmt);
+  std::vector<int> status(n_engines, TRI_OK);
+  std::vector<int64_t> bad(n_engines, -1);
+  std::vector<std::string> msg(n_engines);
+  std::vector<std::thread> workers;
+  auto cut = [&](int g) {  // even boundaries keep every shard's rows vector-aligned
+    int64_t b = n_frames * g / n_engines;
+    return g >= n_engines ? n_frames : std::min<int64_t>(n_frames, b + (b & 1));
+  };
+  for (int g = 0; g < n_engines; g++) {
+    workers.emplace_back([&, g]() {
+      const int64_t b = cut(g), e = cut(g + 1);
+      if (e <= b) return;
+      tri_batch_out o{out->xyz_f32 ? out->xyz_f32 + 3 * b : nullptr, out->xyz_f64 ? out->xyz_f64 + 3 * b : nullptr,
+                      out->mask ? out->mask + b : nullptr, out->err ? out->err + b : nullptr, out->iters ? out->iters + b : nullptr};
+      status[g] = tri_triangulate_points(engines[g], mode, flags | TRI_ALLOW_TOO_FEW, static_cast<const char*>(xy) + (size_t)b * pb,
+                                         n_point_cams, e - b, cam_stride, &o, &bad[g]);
+      if (status[g] != TRI_OK) msg[g] = tri_last_error();
+      if (bad[g] >= 0) bad[g] += b;
+    });
+  }
+  for (std::thread& t : workers) t.join();
+  int64_t first = -1;
+  for (int g = 0; g < n_engines; g++) {
+    if (status[g] != TRI_OK) return fail(status[g], msg[g]);
+    if (bad[g] >= 0 && (first < 0 || bad[g] < first)) first = bad[g];
+  }
+  if (first_bad_frame) *first_bad_frame = first;
+  if (first >= 0 && !(flags & TRI_ALLOW_TOO_FEW))
+    return fail(TRI_ERR_TOO_FEW, mode == TRI_MATRIX ? "Too few rays are found" : "Too few detections are found");
   return TRI_OK;
 }
 

@@ -182,7 +182,9 @@ def main():
     cams = S.ring_rig(N_CAMS)
     eng = T.Engine(cams, local)
     F = a.frames
-    frame0 = rank * F  # contiguous range of the global frame index space
+    from tri_b200 import sharding as SH
+    frame0, frame1 = SH.shard_range(world * F, rank, world)  # contiguous range of the global frame index space
+    assert frame1 - frame0 == F
     mode = T.MATRIX if a.mode == "matrix" else T.RAY
     flags = T.ALLOW_TOO_FEW | (T.F32 if a.precision == "f32" else 0)
     xy = S.generate_frames(cams, F, frame0=frame0, device=dev)  # [8, F, 2] float32, resident in HBM
@@ -238,7 +240,8 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
-            "kernel": "batch_pairs_kernel<%s, 8 cams, float2>" % ("DltPolicy" if a.mode == "matrix" else "RayPolicy"),
+            "kernel": ("stream_kernel<%s, 8 cams, float2>" % (("PolicyTile<DltPolicy<double>,2>" if a.precision == "f64" else "DltX2Tile (FFMA2)")
+                                                              if a.mode == "matrix" else "PolicyTile<RayPolicy>")),
             "algorithmic_bytes_per_frame": 8 * N_CAMS + 12, "kernel_ms": kernel_ms}
 
     res = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
@@ -254,7 +257,9 @@ def main():
     # the other arithmetic precision and the ray kernel on the same frames, for context
     other = {}
     for name, md, fl in (("dlt_f32" if a.precision == "f64" else "dlt_f64", T.MATRIX, flags ^ T.F32),
-                         ("ray_lm_f64", T.RAY, T.ALLOW_TOO_FEW), ("ray_closed_f32", T.RAY, T.ALLOW_TOO_FEW | T.F32)):
+                         ("ray_lm_f64", T.RAY, T.ALLOW_TOO_FEW), ("ray_closed_f64", T.RAY, T.ALLOW_TOO_FEW | T.RAY_CLOSED_FORM),
+                         ("ray_closed_f32", T.RAY, T.ALLOW_TOO_FEW | T.F32),
+                         ("stream_probe", T.MATRIX, T.ALLOW_TOO_FEW | T.F32 | T.DEBUG_STREAM)):
         def fn(md=md, fl=fl):
             eng.triangulate_points_device(md, xy, fl, out=out)
         tms, _, _ = timed(fn, max(3, a.steps // 2), 2)

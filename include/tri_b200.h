@@ -104,6 +104,14 @@ int tri_triangulate_points(tri_engine* e, int mode, unsigned flags, const void* 
                            int64_t n_frames, int64_t cam_stride, const tri_batch_out* out,
                            int64_t* first_bad_frame);
 
+/* The same batch sharded over several engines (one per GPU of the box) from ONE host process: frames
+ * are independent, so engine g takes the contiguous range [g*N/G, (g+1)*N/G) and the shards run
+ * concurrently (one host thread and one copy/compute pipeline per GPU); results land in the caller's
+ * host buffers in frame order, no collective needed.  All engines must hold the same rig. */
+int tri_triangulate_points_multi(tri_engine* const* engines, int n_engines, int mode, unsigned flags,
+                                 const void* xy, int n_point_cams, int64_t n_frames, int64_t cam_stride,
+                                 const tri_batch_out* out, int64_t* first_bad_frame);
+
 /* Same with DEVICE buffers, asynchronous on `stream` (a cudaStream_t, NULL = default stream).
  * The too-few-views condition is latched on the device; tri_device_status collects it. */
 int tri_triangulate_points_device(tri_engine* e, int mode, unsigned flags, const void* d_xy,

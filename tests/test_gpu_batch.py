@@ -282,3 +282,21 @@ def test_full_size_properties(torch):
     sh = eng.triangulate_points_device(T.MATRIX, xy[:, a:b], T.ALLOW_TOO_FEW, want=("xyz_f32",), n_frames=b - a)
     eng.device_status()
     assert torch.equal(sh["xyz_f32"], o["xyz_f32"][a:b])
+
+
+def test_multi_engine_host_batch(syn, torch):
+    """tri_triangulate_points_multi: the batch sharded over every GPU of the box (two engines on the same
+    GPU when there is only one) equals the single-engine result bit for bit."""
+    cams, eng, xy, host = syn
+    n_dev = torch.cuda.device_count()
+    engines = [T.Engine(cams, g % n_dev) for g in range(max(2, min(n_dev, 4)))]
+    for n in (200001, 1001, 3):
+        one = eng.triangulate_points(T.MATRIX, host[:, :n].copy(), T.ALLOW_TOO_FEW, want=("xyz_f64", "mask"))
+        many = T.triangulate_points_multi(engines, T.MATRIX, host[:, :n].copy(), T.ALLOW_TOO_FEW, want=("xyz_f64", "mask"))
+        assert np.array_equal(one["xyz_f64"], many["xyz_f64"]) and np.array_equal(one["mask"], many["mask"])
+        assert one["first_bad_frame"] == many["first_bad_frame"]
+    bad = host[:, :5000].copy()
+    bad[1:, 4321] = -1
+    with pytest.raises(T.TriError) as ei:
+        T.triangulate_points_multi(engines, T.MATRIX, bad)
+    assert ei.value.status == T.ERR_TOO_FEW
