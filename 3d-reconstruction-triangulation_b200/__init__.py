@@ -20,7 +20,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtri_b200.so")
+LIB_PATH = os.environ.get("TRI_B200_LIB") or os.path.join(HERE, "libtri_b200.so")  # override: tuning experiments only
 
 MATRIX, RAY = 0, 1
 OK, ERR_DIM, ERR_TOO_FEW, ERR_ARG, ERR_CUDA, ERR_NO_DEVICE, ERR_CAPACITY = range(7)

@@ -260,6 +260,7 @@ void tri_destroy(tri_engine* e) {
     if (e->slots[i].d_out) cudaFree(e->slots[i].d_out);
     if (e->slots[i].stream) cudaStreamDestroy(e->slots[i].stream);
   }
+  if (e->cls_work && e->cls_work_free) e->cls_work_free(e->cls_work);
   if (e->d_scratch) cudaFree(e->d_scratch);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->d_first_bad) cudaFree(e->d_first_bad);

@@ -34,6 +34,7 @@ constexpr int CLS_MAX_CAMS = 16;   // 4 bits per camera in a 64-bit combination
 constexpr int CLS_THREADS = 128;
 constexpr int LINK_THREADS = 256;
 constexpr int LINK_MAX_FINAL = 128;
+constexpr int LINK_STAGE_LEAVES = 2048;
 typedef unsigned long long u64;
 
 // DroneClassifier.h:11-17
@@ -271,6 +272,8 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
   __shared__ Best s_best[LINK_THREADS / 32];
   __shared__ int s_n_used, s_n_fin;
   __shared__ unsigned s_processed;
+  __shared__ u64 s_comb[LINK_STAGE_LEAVES];     // this frame's candidates, staged once: every path's arg-min
+  __shared__ double s_err[LINK_STAGE_LEAVES];   // and every greedy round of phase 2 re-scans them
   const int tid = threadIdx.x, C = p.n_cams, D = p.n_drones;
   const u64 cam_bits = C == 16 ? ~0ull : ((1ull << (4 * C)) - 1);
   for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += LINK_THREADS) ((int*)&S)[i] = ((const int*)state)[i];
@@ -295,9 +298,12 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
   for (int f = p.f0; f < p.f1; f++) {
     const int L = leaf_cnt[f - p.f0];
     const long long off = leaf_off[f - p.f0];
-    const u64* lc = leaf_comb + off;
-    const double* le = leaf_err + off;
+    const bool staged = L <= LINK_STAGE_LEAVES;
+    const u64* lc = staged ? s_comb : leaf_comb + off;
+    const double* le = staged ? s_err : leaf_err + off;
     const double* lx = leaf_xyz + 3 * off;
+    if (staged)
+      for (int i = tid; i < L; i += LINK_THREADS) { s_comb[i] = leaf_comb[off + i]; s_err[i] = leaf_err[off + i]; }
     if (tid == 0) { s_n_used = 0; s_processed = 0; }
     __syncthreads();
 
@@ -415,12 +421,27 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
   if (tid == 0) { atomicAdd(&ctr->phase1, n_phase1); atomicAdd(&ctr->phase2, n_phase2); atomicAdd(&ctr->ties, n_ties); }
 }
 
+// Grow-only device buffer: the classifier's work space lives on the engine across calls (cudaMalloc /
+// cudaFree of a few hundred MB per call cost up to a second, far more than the kernels).
 struct DevBuf {
   void* p = nullptr;
+  size_t cap = 0;
   ~DevBuf() { if (p) cudaFree(p); }
-  cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 1); }
+  cudaError_t alloc(size_t bytes) {
+    if (bytes <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e == cudaSuccess) cap = bytes ? bytes : 1;
+    return e;
+  }
   template <typename T> T* as() { return static_cast<T*>(p); }
 };
+
+struct ClsWork {
+  DevBuf offs, dets, paths, assign, phase, state, ctr, front, txyz, terr, lcomb, lerr, lxyz, loff, lcnt;
+};
+static void free_cls_work(void* w) { delete static_cast<ClsWork*>(w); }
 
 }  // namespace tri
 
@@ -463,7 +484,11 @@ extern "C" int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drone
   p.solver = mode == TRI_MATRIX ? 0 : (flags & TRI_RAY_REFERENCE_LM) ? 1 : 2;
   p.error_ = mode == TRI_MATRIX ? MAX_ERROR_MATRIX : MAX_ERROR_RAY;  // DroneClassifier.cpp:3-10
 
-  DevBuf d_offs, d_dets, d_paths, d_assign, d_phase, d_state, d_ctr, d_front, d_txyz, d_terr, d_lcomb, d_lerr, d_lxyz, d_loff, d_lcnt;
+  if (!e->cls_work) { e->cls_work = new ClsWork(); e->cls_work_free = free_cls_work; }
+  ClsWork& W = *static_cast<ClsWork*>(e->cls_work);
+  DevBuf &d_offs = W.offs, &d_dets = W.dets, &d_paths = W.paths, &d_assign = W.assign, &d_phase = W.phase, &d_state = W.state,
+         &d_ctr = W.ctr, &d_front = W.front, &d_txyz = W.txyz, &d_terr = W.terr, &d_lcomb = W.lcomb, &d_lerr = W.lerr,
+         &d_lxyz = W.lxyz, &d_loff = W.loff, &d_lcnt = W.lcnt;
   const size_t sz_paths = sizeof(double) * 3 * n_drones * (size_t)n_frames, sz_assign = (size_t)n_drones * n_frames * C,
                sz_phase = (size_t)n_drones * n_frames;
   TRI_CUDA(d_offs.alloc(sizeof(int32_t) * n_offs));
@@ -487,10 +512,6 @@ extern "C" int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drone
   int grid = 0;
   auto alloc_work = [&]() -> int {
     grid = std::max(1, std::min(batch, 2 * e->sm_count));
-    for (DevBuf* b : {&d_front, &d_txyz, &d_terr, &d_lcomb, &d_lerr, &d_lxyz, &d_loff, &d_lcnt}) {
-      if (b->p) cudaFree(b->p);
-      b->p = nullptr;
-    }
     TRI_CUDA(d_front.alloc(sizeof(u64) * 2 * (size_t)cap * grid));
     TRI_CUDA(d_txyz.alloc(sizeof(double) * 3 * (size_t)cap * grid));
     TRI_CUDA(d_terr.alloc(sizeof(double) * (size_t)cap * grid));

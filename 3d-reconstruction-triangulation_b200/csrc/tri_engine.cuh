@@ -10,6 +10,8 @@ constexpr int N_SLOTS = 3;  // host-buffer path: H2D of chunk k+1 | kernel of ch
 
 struct Slot {
   cudaStream_t stream = nullptr;
+  void* cls_work = nullptr;             // classifier work buffers (tri_classify.cu), grow-only
+  void (*cls_work_free)(void*) = nullptr;
   char* d_in = nullptr;
   size_t in_cap = 0;
   char* d_out = nullptr;
@@ -52,6 +54,8 @@ struct tri_engine {
   char* d_scratch = nullptr;
   size_t scratch_cap = 0;
   cudaStream_t stream = nullptr;
+  void* cls_work = nullptr;             // classifier work buffers (tri_classify.cu), grow-only
+  void (*cls_work_free)(void*) = nullptr;
 
   tri::LaunchCtx ctx(cudaStream_t s, int64_t frame_base = 0) {
     return tri::LaunchCtx{s, sm_count, d_first_bad, frame_base, &launches, false, variant};

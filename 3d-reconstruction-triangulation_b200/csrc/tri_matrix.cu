@@ -12,6 +12,10 @@
 // HBM traffic per frame: 8 B x n_cams in, 12 B out.
 #include "tri_pipe.cuh"
 
+#ifndef TRI_F64_HI_ONLY
+#define TRI_F64_HI_ONLY false
+#endif
+
 namespace tri {
 
 // one camera's 3x4 matrix as 16-byte vector loads (LDS.128 from the shared-memory rig)
@@ -26,71 +30,27 @@ __device__ __forceinline__ void load12(const float (&src)[12], float (&P)[12]) {
   for (int k = 0; k < 3; k++) { const float4 q = v[k]; P[4 * k] = q.x; P[4 * k + 1] = q.y; P[4 * k + 2] = q.z; P[4 * k + 3] = q.w; }
 }
 
-// FP64 accumulation of one view under a predicate (no branch, no reconvergence barrier): 26 @p DFMA.
-__device__ __forceinline__ void add_view_pred(bool valid, const double (&P)[12], double x, double y, double (&M)[6], double (&v)[3]) {
-  asm("{\n"
-      ".reg .pred p;\n"
-      ".reg .f64 a0, a1, a2, b, nx, ny, n3, n7;\n"
-      "setp.ne.u32 p, %9, 0;\n"
-      "neg.f64 nx, %10;\n"
-      "neg.f64 ny, %11;\n"
-      "neg.f64 n3, %15;\n"
-      "neg.f64 n7, %19;\n"
-      "@p fma.rn.f64 a0, nx, %20, %12;\n"
-      "@p fma.rn.f64 a1, nx, %21, %13;\n"
-      "@p fma.rn.f64 a2, nx, %22, %14;\n"
-      "@p fma.rn.f64 b, %10, %23, n3;\n"
-      "@p fma.rn.f64 %0, a0, a0, %0;\n"
-      "@p fma.rn.f64 %1, a0, a1, %1;\n"
-      "@p fma.rn.f64 %2, a0, a2, %2;\n"
-      "@p fma.rn.f64 %3, a1, a1, %3;\n"
-      "@p fma.rn.f64 %4, a1, a2, %4;\n"
-      "@p fma.rn.f64 %5, a2, a2, %5;\n"
-      "@p fma.rn.f64 %6, a0, b, %6;\n"
-      "@p fma.rn.f64 %7, a1, b, %7;\n"
-      "@p fma.rn.f64 %8, a2, b, %8;\n"
-      "@p fma.rn.f64 a0, ny, %20, %16;\n"
-      "@p fma.rn.f64 a1, ny, %21, %17;\n"
-      "@p fma.rn.f64 a2, ny, %22, %18;\n"
-      "@p fma.rn.f64 b, %11, %23, n7;\n"
-      "@p fma.rn.f64 %0, a0, a0, %0;\n"
-      "@p fma.rn.f64 %1, a0, a1, %1;\n"
-      "@p fma.rn.f64 %2, a0, a2, %2;\n"
-      "@p fma.rn.f64 %3, a1, a1, %3;\n"
-      "@p fma.rn.f64 %4, a1, a2, %4;\n"
-      "@p fma.rn.f64 %5, a2, a2, %5;\n"
-      "@p fma.rn.f64 %6, a0, b, %6;\n"
-      "@p fma.rn.f64 %7, a1, b, %7;\n"
-      "@p fma.rn.f64 %8, a2, b, %8;\n"
-      "}\n"
-      : "+d"(M[0]), "+d"(M[1]), "+d"(M[2]), "+d"(M[3]), "+d"(M[4]), "+d"(M[5]), "+d"(v[0]), "+d"(v[1]), "+d"(v[2])
-      : "r"((unsigned)valid), "d"(x), "d"(y), "d"(P[0]), "d"(P[1]), "d"(P[2]), "d"(P[3]), "d"(P[4]), "d"(P[5]), "d"(P[6]), "d"(P[7]),
-        "d"(P[8]), "d"(P[9]), "d"(P[10]), "d"(P[11]));
+// One row (a, b) into the normal equations.  An absent view is masked by clearing the row (selects on
+// the ALU pipe) rather than skipped or predicated: within a warp some lane almost always has the view,
+// so the FMAs issue either way; a divergent branch costs BSSY/BSYNC barriers (27 % of the stall samples
+// in profiles/ncu_r1c.md) and "@p fma.rn.f64" sequences measured 45 % slower than this form.
+template <bool HI_ONLY>
+__device__ __forceinline__ double keep_if(bool valid, double a) {
+  if constexpr (HI_ONLY) return __hiloint2double(valid ? __double2hiint(a) : 0, __double2loint(a));
+  return valid ? a : 0.0;
 }
-
-// FP64 tile solver with the predicated accumulation (one frame per thread)
-struct DltF64Tile {
-  static constexpr int FPT = 1;
-  using Rig = DltRig<double>;
-  template <int NC, int PIX>
-  static __device__ __forceinline__ void run(const Rig& rig, const typename RawPix<PIX, 1>::type (&raw)[NC], int, float (&X)[1][3],
-                                             uint32_t (&mask)[1]) {
-    double M[6] = {0, 0, 0, 0, 0, 0}, v[3] = {0, 0, 0};
-    uint32_t m = 0;
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-      const Views<double, PIX, 1> w = decode<double, PIX, 1>(raw[c]);
-      double P[12];
-      load12(rig.P[c], P);
-      add_view_pred(w.v[0], P, w.x[0], w.y[0], M, v);
-      m |= (w.v[0] ? 1u : 0u) << c;
-    }
-    double S[3] = {0, 0, 0};
-    if (__popc(m) >= 2) solve_sym3<double>(M, v, S);
-    X[0][0] = (float)S[0]; X[0][1] = (float)S[1]; X[0][2] = (float)S[2];
-    mask[0] = m;
-  }
-};
+__device__ __forceinline__ void acc_row(bool valid, double a0, double a1, double a2, double b, double (&M)[6], double (&v)[3]) {
+  a0 = keep_if<TRI_F64_HI_ONLY>(valid, a0); a1 = keep_if<TRI_F64_HI_ONLY>(valid, a1); a2 = keep_if<TRI_F64_HI_ONLY>(valid, a2);
+  M[0] = fma_(a0, a0, M[0]); M[1] = fma_(a0, a1, M[1]); M[2] = fma_(a0, a2, M[2]);
+  M[3] = fma_(a1, a1, M[3]); M[4] = fma_(a1, a2, M[4]); M[5] = fma_(a2, a2, M[5]);
+  v[0] = fma_(a0, b, v[0]); v[1] = fma_(a1, b, v[1]); v[2] = fma_(a2, b, v[2]);
+}
+__device__ __forceinline__ void acc_row(bool valid, float a0, float a1, float a2, float b, float (&M)[6], float (&v)[3]) {
+  a0 = valid ? a0 : 0.f; a1 = valid ? a1 : 0.f; a2 = valid ? a2 : 0.f;  // exact zeros: identical to the packed FFMA2 path
+  M[0] = fma_(a0, a0, M[0]); M[1] = fma_(a0, a1, M[1]); M[2] = fma_(a0, a2, M[2]);
+  M[3] = fma_(a1, a1, M[3]); M[4] = fma_(a1, a2, M[4]); M[5] = fma_(a2, a2, M[5]);
+  v[0] = fma_(a0, b, v[0]); v[1] = fma_(a1, b, v[1]); v[2] = fma_(a2, b, v[2]);
+}
 
 template <typename T_, bool CENTRED>
 struct DltPolicy {
@@ -100,23 +60,15 @@ struct DltPolicy {
     T M[6] = {0, 0, 0, 0, 0, 0};
     T v[3] = {0, 0, 0};
   };
-  // Branch-free: an absent view's rows are zeroed (one predicated register clear per value) instead of
-  // skipped -- within a warp some lane almost always has the view, so the FMAs issue either way, and
-  // the divergence barriers (BSSY/BSYNC, 27 % of the stall samples in profiles/r1c) disappear.
+  // Branch-free: an absent view is masked inside acc_row (predicated FMAs in FP64, exact-zero rows in FP32)
+  // instead of skipped -- the divergence barriers (BSSY/BSYNC, 27 % of the stall samples in
+  // profiles/ncu_r1c.md) disappear.
   static __device__ __forceinline__ void add(const Rig& rig, int c, T x, T y, bool valid, Acc& a) {
     T P[12];
     load12(rig.P[c], P);
     if constexpr (CENTRED) { x -= rig.pix0[c][0]; y -= rig.pix0[c][1]; }
-    T a0 = fma_(-x, P[8], P[0]), a1 = fma_(-x, P[9], P[1]), a2 = fma_(-x, P[10], P[2]), b = fma_(x, P[11], -P[3]);
-    a0 = valid ? a0 : T(0); a1 = valid ? a1 : T(0); a2 = valid ? a2 : T(0);
-    a.M[0] = fma_(a0, a0, a.M[0]); a.M[1] = fma_(a0, a1, a.M[1]); a.M[2] = fma_(a0, a2, a.M[2]);
-    a.M[3] = fma_(a1, a1, a.M[3]); a.M[4] = fma_(a1, a2, a.M[4]); a.M[5] = fma_(a2, a2, a.M[5]);
-    a.v[0] = fma_(a0, b, a.v[0]); a.v[1] = fma_(a1, b, a.v[1]); a.v[2] = fma_(a2, b, a.v[2]);
-    a0 = fma_(-y, P[8], P[4]); a1 = fma_(-y, P[9], P[5]); a2 = fma_(-y, P[10], P[6]); b = fma_(y, P[11], -P[7]);
-    a0 = valid ? a0 : T(0); a1 = valid ? a1 : T(0); a2 = valid ? a2 : T(0);
-    a.M[0] = fma_(a0, a0, a.M[0]); a.M[1] = fma_(a0, a1, a.M[1]); a.M[2] = fma_(a0, a2, a.M[2]);
-    a.M[3] = fma_(a1, a1, a.M[3]); a.M[4] = fma_(a1, a2, a.M[4]); a.M[5] = fma_(a2, a2, a.M[5]);
-    a.v[0] = fma_(a0, b, a.v[0]); a.v[1] = fma_(a1, b, a.v[1]); a.v[2] = fma_(a2, b, a.v[2]);
+    acc_row(valid, fma_(-x, P[8], P[0]), fma_(-x, P[9], P[1]), fma_(-x, P[10], P[2]), fma_(x, P[11], -P[3]), a.M, a.v);
+    acc_row(valid, fma_(-y, P[8], P[4]), fma_(-y, P[9], P[5]), fma_(-y, P[10], P[6]), fma_(y, P[11], -P[7]), a.M, a.v);
   }
   static __device__ __forceinline__ void solve(const Rig&, const Acc& a, int, T (&X)[3], int, int&) {
     solve_sym3<T>(a.M, a.v, X);

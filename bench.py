@@ -238,8 +238,14 @@ def main():
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:  # per-launch DRAM bytes of this kernel from the committed ncu --set full capture (same 100 M-frame launch)
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("%s_%s" % (a.mode, a.precision))
+        traffic = float(t) * (F / 100_000_000) if t else None
+    except Exception:
+        pass
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
+            "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
             "kernel": ("stream_kernel<%s, 8 cams, float2>" % (("PolicyTile<DltPolicy<double>,2>" if a.precision == "f64" else "DltX2Tile (FFMA2)")
                                                               if a.mode == "matrix" else "PolicyTile<RayPolicy>")),
             "algorithmic_bytes_per_frame": 8 * N_CAMS + 12, "kernel_ms": kernel_ms}
@@ -311,7 +317,28 @@ def main():
         torch.cuda.synchronize()
         same = bool(torch.equal(h_out[:4000000].to(dev), out["xyz_f32"][:4000000]))
         res["e2e"]["matches_device_path"] = same
-        del h_xy, h_out
+        # the same call with the compact ushort2 pixel format (integer detections, 4 B instead of 8 B over PCIe)
+        h16 = torch.empty((N_CAMS, F, 2), dtype=torch.uint16, pin_memory=True)
+        for c in range(N_CAMS):
+            v = xy[c]
+            h16[c].copy_(torch.where(v < 0, torch.full_like(v, 65535.0), v).to(torch.int32).to(torch.uint16))
+        torch.cuda.synchronize()
+
+        def e2e16():
+            eng.triangulate_points_raw(mode, flags | T.PIX_U16, h16.data_ptr(), N_CAMS, F, F, xyz_f32_ptr=h_out.data_ptr())
+        e2e16()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            e2e16()
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e16 = float(t.item()) / esteps
+        res["e2e_u16"] = {"value": valid_total / e16, "unit": UNIT, "h2d_bytes_per_step": 4 * N_CAMS * F, "d2h_bytes_per_step": 12 * F,
+                          "ms_per_step": e16 * 1e3, "matches_device_path": bool(torch.equal(h_out[:4000000].to(dev), out["xyz_f32"][:4000000]))}
+        del h_xy, h_out, h16
 
     if rank == 0 and world == 1 and not a.no_cpu:
         res["cpu_baseline"] = cpu_baseline(cams, a.mode, a.cpu_seconds, lambda n: xy[:, :n].cpu().numpy())
