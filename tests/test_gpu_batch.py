@@ -300,3 +300,37 @@ def test_multi_engine_host_batch(syn, torch):
     with pytest.raises(T.TriError) as ei:
         T.triangulate_points_multi(engines, T.MATRIX, bad)
     assert ei.value.status == T.ERR_TOO_FEW
+
+
+@pytest.mark.parametrize("n_cams", [2, 3, 5, 12, 32])
+def test_other_camera_counts(torch, n_cams):
+    """Rigs from 2 to TRI_MAX_CAMS cameras (BASELINE config 5 uses 32): unrolled (<= 8) and generic kernels."""
+    rings = ((6000.0, 3000.0),) if n_cams <= 8 else ((6000.0, 3000.0), (9000.0, 5000.0))
+    cams = S.ring_rig(n_cams, rings=rings)
+    eng = T.Engine(cams, 0)
+    n = 40001
+    xy = S.generate_frames(cams, n, device="cuda:0", p_missing=0.3)
+    host = xy.cpu().numpy()
+    oc = ocams(cams)
+    ref = O.triangulate_points(oc, host, O.MATRIX, allow_too_few=True, nthreads=8)
+    o = eng.triangulate_points_device(T.MATRIX, xy, T.ALLOW_TOO_FEW, want=("xyz_f64", "mask", "err"))
+    eng.device_status()
+    assert np.array_equal(o["mask"].cpu().numpy().view(np.uint32), ref["mask"])
+    assert rel_err(o["xyz_f64"].cpu().numpy(), ref["xyz"]) < 1e-8
+    ok = ref["err"] > 0
+    np.testing.assert_allclose(o["err"].cpu().numpy()[ok], ref["err"][ok], rtol=1e-8, atol=1e-6)
+    for fl in (0, T.F32):
+        q = eng.triangulate_points_device(T.MATRIX, xy, T.ALLOW_TOO_FEW | fl, want=("xyz_f32", "mask"))
+        eng.device_status()
+        assert np.array_equal(q["mask"].cpu().numpy().view(np.uint32), ref["mask"])
+        assert np.abs(q["xyz_f32"].cpu().numpy() - ref["xyz"]).max() < (1e-3 if fl == 0 else 0.2)
+    r = eng.triangulate_points_device(T.RAY, xy, T.ALLOW_TOO_FEW, want=("xyz_f64", "mask", "iters"))
+    c = eng.triangulate_points_device(T.RAY, xy, T.ALLOW_TOO_FEW | T.RAY_CLOSED_FORM, want=("xyz_f64",))
+    eng.device_status()
+    assert np.array_equal(r["mask"].cpu().numpy().view(np.uint32), ref["mask"])
+    assert float((r["xyz_f64"] - c["xyz_f64"]).abs().max()) < 1e-6
+    sel = np.nonzero(np.array([bin(int(m)).count("1") for m in ref["mask"]]) >= 3)[0][:300]
+    for f in sel[::10]:
+        sub = [k for k in range(n_cams) if ref["mask"][f] >> k & 1]
+        Xc = O.ray_closed_form(oc, sub, host[sub, f].astype(np.float64))
+        assert np.abs(c["xyz_f64"][f].cpu().numpy() - Xc).max() < 1e-6
