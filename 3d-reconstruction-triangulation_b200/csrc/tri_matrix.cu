@@ -15,6 +15,9 @@
 #ifndef TRI_F64_HI_ONLY
 #define TRI_F64_HI_ONLY false
 #endif
+#ifndef TRI_F64_REUSE_ORDER
+#define TRI_F64_REUSE_ORDER 0
+#endif
 
 namespace tri {
 
@@ -41,9 +44,27 @@ __device__ __forceinline__ double keep_if(bool valid, double a) {
 }
 __device__ __forceinline__ void acc_row(bool valid, double a0, double a1, double a2, double b, double (&M)[6], double (&v)[3]) {
   a0 = keep_if<TRI_F64_HI_ONLY>(valid, a0); a1 = keep_if<TRI_F64_HI_ONLY>(valid, a1); a2 = keep_if<TRI_F64_HI_ONLY>(valid, a2);
+#if TRI_F64_REUSE_ORDER
+  // A DFMA with three distinct register-pair sources issues every 3 cycles instead of 2 on sm_100
+  // (tools/micro/dfma_rf.cu: 1.33 vs 1.99 warp-inst/clk/SM); a source shared with the previous
+  // instruction in the same slot comes from the operand-reuse cache.  This order walks the nine products
+  // so that each shares a multiplicand with its predecessor: a0a0 a0a1 a1a1 a1a2 a2a2 a2b a1b a0b a0a2.
+  asm("fma.rn.f64 %0, %9, %9, %0;\n"
+      "fma.rn.f64 %1, %9, %10, %1;\n"
+      "fma.rn.f64 %3, %10, %10, %3;\n"
+      "fma.rn.f64 %4, %10, %11, %4;\n"
+      "fma.rn.f64 %5, %11, %11, %5;\n"
+      "fma.rn.f64 %8, %11, %12, %8;\n"
+      "fma.rn.f64 %7, %10, %12, %7;\n"
+      "fma.rn.f64 %6, %9, %12, %6;\n"
+      "fma.rn.f64 %2, %9, %11, %2;\n"
+      : "+d"(M[0]), "+d"(M[1]), "+d"(M[2]), "+d"(M[3]), "+d"(M[4]), "+d"(M[5]), "+d"(v[0]), "+d"(v[1]), "+d"(v[2])
+      : "d"(a0), "d"(a1), "d"(a2), "d"(b));
+#else
   M[0] = fma_(a0, a0, M[0]); M[1] = fma_(a0, a1, M[1]); M[2] = fma_(a0, a2, M[2]);
   M[3] = fma_(a1, a1, M[3]); M[4] = fma_(a1, a2, M[4]); M[5] = fma_(a2, a2, M[5]);
   v[0] = fma_(a0, b, v[0]); v[1] = fma_(a1, b, v[1]); v[2] = fma_(a2, b, v[2]);
+#endif
 }
 __device__ __forceinline__ void acc_row(bool valid, float a0, float a1, float a2, float b, float (&M)[6], float (&v)[3]) {
   a0 = valid ? a0 : 0.f; a1 = valid ? a1 : 0.f; a2 = valid ? a2 : 0.f;  // exact zeros: identical to the packed FFMA2 path
@@ -101,9 +122,6 @@ struct __align__(16) DltRigX2 {
   float origin[3];
 };
 
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
-__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
 
 template <bool SEL>
 struct DltX2Tile {
@@ -151,15 +169,8 @@ struct DltX2Tile {
         v[0] = fma2(w0, b, v[0]); v[1] = fma2(w1, b, v[1]); v[2] = fma2(w2, b, v[2]);
       }
     }
-    // adjugate solve, both frames at once (same operation order as solve_sym3<float>)
-    const float2 c00 = fma2(M[3], M[5], neg2(mul2(M[4], M[4]))), c01 = fma2(M[2], M[4], neg2(mul2(M[1], M[5]))),
-                 c02 = fma2(M[1], M[4], neg2(mul2(M[2], M[3]))), c11 = fma2(M[0], M[5], neg2(mul2(M[2], M[2]))),
-                 c12 = fma2(M[1], M[2], neg2(mul2(M[0], M[4]))), c22 = fma2(M[0], M[3], neg2(mul2(M[1], M[1])));
-    const float2 det = fma2(M[0], c00, fma2(M[1], c01, mul2(M[2], c02)));
-    const float2 inv = make_float2(1.0f / det.x, 1.0f / det.y);
-    const float2 X0 = mul2(fma2(c00, v[0], fma2(c01, v[1], mul2(c02, v[2]))), inv);
-    const float2 X1 = mul2(fma2(c01, v[0], fma2(c11, v[1], mul2(c12, v[2]))), inv);
-    const float2 X2 = mul2(fma2(c02, v[0], fma2(c12, v[1], mul2(c22, v[2]))), inv);
+    float2 X0, X1, X2;
+    solve_sym3_x2(M, v, X0, X1, X2);
     const bool ok0 = __popc(mask0) >= 2, ok1 = __popc(mask1) >= 2;
     X[0][0] = ok0 ? X0.x + rig.origin[0] : 0.f; X[0][1] = ok0 ? X1.x + rig.origin[1] : 0.f; X[0][2] = ok0 ? X2.x + rig.origin[2] : 0.f;
     X[1][0] = ok1 ? X0.y + rig.origin[0] : 0.f; X[1][1] = ok1 ? X1.y + rig.origin[1] : 0.f; X[1][2] = ok1 ? X2.y + rig.origin[2] : 0.f;

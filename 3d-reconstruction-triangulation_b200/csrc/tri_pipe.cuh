@@ -79,6 +79,23 @@ __device__ __forceinline__ Views<T, PIX, FPT> decode(const typename RawPix<PIX, 
   return r;
 }
 
+// ---- packed-pair FP32 helpers (FFMA2 / FMUL2 / FADD2, sm_100): two frames in the halves of a float2 ----
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+// adjugate solve of two 3x3 symmetric systems at once; same operation order as solve_sym3<float>
+__device__ __forceinline__ void solve_sym3_x2(const float2 (&M)[6], const float2 (&v)[3], float2& X0, float2& X1, float2& X2) {
+  const float2 c00 = fma2(M[3], M[5], neg2(mul2(M[4], M[4]))), c01 = fma2(M[2], M[4], neg2(mul2(M[1], M[5]))),
+               c02 = fma2(M[1], M[4], neg2(mul2(M[2], M[3]))), c11 = fma2(M[0], M[5], neg2(mul2(M[2], M[2]))),
+               c12 = fma2(M[1], M[2], neg2(mul2(M[0], M[4]))), c22 = fma2(M[0], M[3], neg2(mul2(M[1], M[1])));
+  const float2 det = fma2(M[0], c00, fma2(M[1], c01, mul2(M[2], c02)));
+  const float2 inv = make_float2(1.0f / det.x, 1.0f / det.y);
+  X0 = mul2(fma2(c00, v[0], fma2(c01, v[1], mul2(c02, v[2]))), inv);
+  X1 = mul2(fma2(c01, v[0], fma2(c11, v[1], mul2(c12, v[2]))), inv);
+  X2 = mul2(fma2(c02, v[0], fma2(c12, v[1], mul2(c22, v[2]))), inv);
+}
+
 // Tile solver built from a scalar policy (tri_batch.cuh): FPT frames per thread, one after the other.
 template <class S, int FPT_>
 struct PolicyTile {

@@ -133,6 +133,71 @@ struct RayPolicy {
   }
 };
 
+// ---- FP32 closed form, packed-pair SIMD (the ray counterpart of DltX2Tile) ----
+// Same operation order as RayPolicy<float> (which serves tails and optional outputs), so the points are
+// bit-identical; an absent view is masked by zeroing 1/|v|^2 and the constant terms' weight.
+struct __align__(16) RayRigX2 {
+  float2 U0[TRI_MAX_CAMS][3], U1[TRI_MAX_CAMS][3], U2[TRI_MAX_CAMS][3];
+  float2 ax[TRI_MAX_CAMS], bx[TRI_MAX_CAMS], ay[TRI_MAX_CAMS], by[TRI_MAX_CAMS], dd[TRI_MAX_CAMS], n4[TRI_MAX_CAMS];
+  float2 ob[TRI_MAX_CAMS][3], n4ob[TRI_MAX_CAMS][3];
+  float origin[3];
+};
+
+struct RayX2Tile {
+  static constexpr int FPT = 2;
+  using Rig = RayRigX2;
+  template <int NC, int PIX>
+  static __device__ __forceinline__ void run(const Rig& r, const typename RawPix<PIX, 2>::type (&raw)[NC], int, float (&X)[2][3],
+                                             uint32_t (&mask)[2]) {
+    const float2 z = make_float2(0.f, 0.f);
+    float2 uu[6] = {z, z, z, z, z, z}, cu[3] = {z, z, z}, cn[3] = {z, z, z}, tr = z;
+    uint32_t mask0 = 0, mask1 = 0;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const Views<float, PIX, 2> q = decode<float, PIX, 2>(raw[c]);
+      const float2 w = make_float2(q.v[0] ? 1.0f : 0.0f, q.v[1] ? 1.0f : 0.0f);
+      mask0 |= (q.v[0] ? 1u : 0u) << c;
+      mask1 |= (q.v[1] ? 1u : 0u) << c;
+      const float2 x = make_float2(q.x[0], q.x[1]), y = make_float2(q.y[0], q.y[1]);
+      const float2 u0 = fma2(r.U0[c][0], x, fma2(r.U1[c][0], y, r.U2[c][0]));
+      const float2 u1 = fma2(r.U0[c][1], x, fma2(r.U1[c][1], y, r.U2[c][1]));
+      const float2 u2 = fma2(r.U0[c][2], x, fma2(r.U1[c][2], y, r.U2[c][2]));
+      const float2 vx = fma2(r.ax[c], x, r.bx[c]), vy = fma2(r.ay[c], y, r.by[c]);
+      const float2 vv = fma2(vx, vx, fma2(vy, vy, r.dd[c]));
+      const float2 inv = make_float2(q.v[0] ? 1.0f / vv.x : 0.f, q.v[1] ? 1.0f / vv.y : 0.f);
+      const float2 s0 = mul2(u0, inv), s1 = mul2(u1, inv), s2 = mul2(u2, inv);
+      uu[0] = fma2(s0, u0, uu[0]); uu[1] = fma2(s0, u1, uu[1]); uu[2] = fma2(s0, u2, uu[2]);
+      uu[3] = fma2(s1, u1, uu[3]); uu[4] = fma2(s1, u2, uu[4]); uu[5] = fma2(s2, u2, uu[5]);
+      const float2 t = fma2(s0, r.ob[c][0], fma2(s1, r.ob[c][1], mul2(s2, r.ob[c][2])));
+      cu[0] = fma2(u0, t, cu[0]); cu[1] = fma2(u1, t, cu[1]); cu[2] = fma2(u2, t, cu[2]);
+      cn[0] = fma2(w, r.n4ob[c][0], cn[0]); cn[1] = fma2(w, r.n4ob[c][1], cn[1]); cn[2] = fma2(w, r.n4ob[c][2], cn[2]);
+      tr = fma2(w, r.n4[c], tr);
+    }
+    const float2 M[6] = {add2(tr, neg2(uu[0])), neg2(uu[1]), neg2(uu[2]), add2(tr, neg2(uu[3])), neg2(uu[4]), add2(tr, neg2(uu[5]))};
+    const float2 cc[3] = {add2(cn[0], neg2(cu[0])), add2(cn[1], neg2(cu[1])), add2(cn[2], neg2(cu[2]))};
+    float2 X0, X1, X2;
+    solve_sym3_x2(M, cc, X0, X1, X2);
+    const bool ok0 = __popc(mask0) >= 2, ok1 = __popc(mask1) >= 2;
+    X[0][0] = ok0 ? X0.x + r.origin[0] : 0.f; X[0][1] = ok0 ? X1.x + r.origin[1] : 0.f; X[0][2] = ok0 ? X2.x + r.origin[2] : 0.f;
+    X[1][0] = ok1 ? X0.y + r.origin[0] : 0.f; X[1][1] = ok1 ? X1.y + r.origin[1] : 0.f; X[1][2] = ok1 ? X2.y + r.origin[2] : 0.f;
+    mask[0] = mask0; mask[1] = mask1;
+  }
+};
+
+static RayRigX2 make_ray_x2(const RayFold<float>& f) {
+  RayRigX2 x;
+  auto d = [](float v) { return make_float2(v, v); };
+  for (int c = 0; c < TRI_MAX_CAMS; c++) {
+    for (int k = 0; k < 3; k++) {
+      x.U0[c][k] = d(f.U0[c][k]); x.U1[c][k] = d(f.U1[c][k]); x.U2[c][k] = d(f.U2[c][k]);
+      x.ob[c][k] = d(f.ob[c][k]); x.n4ob[c][k] = d(f.n4ob[c][k]);
+    }
+    x.ax[c] = d(f.ax[c]); x.bx[c] = d(f.bx[c]); x.ay[c] = d(f.ay[c]); x.by[c] = d(f.by[c]); x.dd[c] = d(f.dd[c]); x.n4[c] = d(f.n4[c]);
+  }
+  for (int k = 0; k < 3; k++) x.origin[k] = f.origin[k];
+  return x;
+}
+
 cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt, const RayFold<double>& r64,
                             const RayFold<float>& r32, const void* d_xy, int n_use, int64_t n_frames,
                             int64_t cam_stride, const BatchOut& out) {
@@ -141,11 +206,11 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
   using P64 = RayPolicy<double>;
   const int opt = lm ? 1 : 0;
   if (f32) {  // FP32: closed form only (the gain ratio of the LM loop needs S to ~1e-9 relative)
-    using T32 = PolicyTile<P32, 2>;
+    const RayRigX2 x2 = make_ray_x2(r32);
     switch (pixfmt) {
-      case PIX_F32: return launch_streamed<T32, P32, PIX_F32, 2, 2, 2, 0>(ctx, r32, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case PIX_F64: return launch_streamed<T32, P32, PIX_F64, 2, 2, 2, 0>(ctx, r32, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-      default: return launch_streamed<T32, P32, PIX_U16, 2, 2, 2, 0>(ctx, r32, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case PIX_F32: return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 2, 3, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case PIX_F64: return launch_streamed<RayX2Tile, P32, PIX_F64, 2, 2, 3, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      default: return launch_streamed<RayX2Tile, P32, PIX_U16, 2, 2, 3, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
     }
   }
   using T64 = PolicyTile<P64, 1>;
