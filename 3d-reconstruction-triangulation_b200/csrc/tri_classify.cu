@@ -33,8 +33,8 @@ namespace tri {
 constexpr int CLS_MAX_CAMS = 16;   // 4 bits per camera in a 64-bit combination
 constexpr int CLS_THREADS = 128;
 constexpr int LINK_THREADS = 256;
-constexpr int LINK_MAX_FINAL = 128;
-constexpr int LINK_STAGE_LEAVES = 2048;
+constexpr int LINK_MAX_FINAL = 64;
+constexpr int LINK_STAGE_LEAVES = 1792;
 typedef unsigned long long u64;
 
 // DroneClassifier.h:11-17
@@ -265,7 +265,13 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
             const long long* __restrict__ leaf_off, const int* __restrict__ leaf_cnt, LinkState* state,
             double* __restrict__ out_paths, int8_t* __restrict__ out_assign, uint8_t* __restrict__ out_phase, ClsCounters* ctr) {
   __shared__ LinkState S;
-  __shared__ unsigned s_gate[CLS_MAX_CAMS];
+  __shared__ unsigned s_gate[TRI_MAX_DRONES][CLS_MAX_CAMS];
+  __shared__ double s_dir[CLS_MAX_CAMS * TRI_MAX_DETS][3];
+  __shared__ bool s_ndet[CLS_MAX_CAMS * TRI_MAX_DETS];
+  __shared__ Best s_cand[TRI_MAX_DRONES];
+  __shared__ bool s_active[TRI_MAX_DRONES];
+  __shared__ int s_next;
+  __shared__ double s_pdist[LINK_MAX_FINAL][TRI_MAX_DRONES];
   __shared__ u64 s_used[TRI_MAX_DRONES];
   __shared__ u64 s_fin[LINK_MAX_FINAL];
   __shared__ int s_fin_idx[LINK_MAX_FINAL];
@@ -308,32 +314,90 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
     __syncthreads();
 
     // ---- phase 1: tracking (:119-135) ----
-    for (int np = 0; np < D; np++) {
+    // (i) the pixel rays of this frame's detections, once (they do not depend on the path)
+    for (int i = tid; i < C * TRI_MAX_DETS; i += LINK_THREADS) {
+      const int c = i / TRI_MAX_DETS, d = i % TRI_MAX_DETS;
+      const int a = offs[(size_t)c * (p.n_frames + 1) + f], b = offs[(size_t)c * (p.n_frames + 1) + f + 1];
+      s_ndet[i] = d < b - a;
+      if (d < b - a) ref::make_dir(ray, c, dets[2 * (size_t)(a + d)], dets[2 * (size_t)(a + d) + 1], s_dir[i]);
+    }
+    for (int i = tid; i < D * C; i += LINK_THREADS) s_gate[i / C][i % C] = 1u;  // choice 0 ("none") is always available
+    __syncthreads();
+    // (ii) the MAX_STEP ray gate of every (path, detection), :228-236 -- a path's last point is last frame's
+    for (int i = tid; i < D * C * TRI_MAX_DETS; i += LINK_THREADS) {
+      const int np = i / (C * TRI_MAX_DETS), k = i % (C * TRI_MAX_DETS), c = k / TRI_MAX_DETS, d = k % TRI_MAX_DETS;
       const int n = S.n[np];
-      if (n == 0) continue;
-      const double* lastp = S.tail[np][min(n, PATH_TAIL) - 1];
-      const double last[3] = {lastp[0], lastp[1], lastp[2]};
-      if (last[0] == 0 && last[1] == 0 && last[2] == 0) continue;  // :123
-      if (tid < C) s_gate[tid] = 1u;  // choice 0 ("none") is always available
-      __syncthreads();
-      for (int i = tid; i < C * TRI_MAX_DETS; i += LINK_THREADS) {  // MAX_STEP ray gate, :228-236
-        const int c = i / TRI_MAX_DETS, d = i % TRI_MAX_DETS;
-        const int a = offs[(size_t)c * (p.n_frames + 1) + f], b = offs[(size_t)c * (p.n_frames + 1) + f + 1];
-        if (d < b - a && ref::dist_from_ray(ray, c, dets[2 * (size_t)(a + d)], dets[2 * (size_t)(a + d) + 1], last) < MAX_STEP)
-          atomicOr(&s_gate[c], 1u << (d + 1));
+      if (n == 0 || !s_ndet[k]) continue;
+      const double* last = S.tail[np][min(n, PATH_TAIL) - 1];
+      if (ref::dist_to_ray(ray.pos[c], s_dir[k], last[0], last[1], last[2]) < MAX_STEP) atomicOr(&s_gate[np][c], 1u << (d + 1));
+    }
+    __syncthreads();
+    // (iii) one warp per path: best admissible candidate ignoring the combinations used by earlier paths
+    for (int np = tid >> 5; np < D; np += LINK_THREADS / 32) {
+      const int n = S.n[np];
+      Best mine{0x7fffffff, 0.0, 0, 0};
+      const double* last = S.tail[np][min(max(n, 1), PATH_TAIL) - 1];
+      const bool active = n != 0 && !(last[0] == 0 && last[1] == 0 && last[2] == 0);  // :121-123
+      if (active) {
+        for (int i = tid & 31; i < L; i += 32) {
+          const u64 comb = lc[i];
+          bool ok = true;
+          for (int c = 0; c < C; c++) ok = ok && ((s_gate[np][c] >> ((comb >> (4 * c)) & 15)) & 1u);
+          if (!ok) continue;
+          const double err = le[i];
+          if (!(err < p.error_)) continue;
+          if (!(dist3(lx + 3 * i, last) < MAX_STEP)) continue;  // cv::norm(c.point - pos) < MAX_STEP, :244
+          const Best cand{C - __popcll(nonzero_nibbles(comb & cam_bits)), err, i, 1};
+          mine = better(mine, cand);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+          Best u;
+          u.zeros = __shfl_down_sync(0xffffffffu, mine.zeros, o);
+          u.err = __shfl_down_sync(0xffffffffu, mine.err, o);
+          u.idx = __shfl_down_sync(0xffffffffu, mine.idx, o);
+          u.same = __shfl_down_sync(0xffffffffu, mine.same, o);
+          mine = better(mine, u);
+        }
+      }
+      if ((tid & 31) == 0) { s_cand[np] = mine; s_active[np] = active; }
+    }
+    __syncthreads();
+    // (iv) in path order: a candidate that does not collide with an earlier path's pick is that path's
+    // answer (it is also the best of the filtered set); otherwise re-scan with the used list
+    for (int np = 0; np < D;) {
+      if (tid == 0) {
+        int q = np;
+        for (; q < D; q++) {
+          if (!s_active[q] || s_cand[q].zeros == 0x7fffffff) continue;
+          const u64 comb = lc[s_cand[q].idx];
+          bool clash = false;
+          for (int u = 0; u < s_n_used; u++) clash = clash || conflicts(comb, s_used[u]);
+          if (clash) break;
+          s_used[s_n_used++] = comb;
+          s_processed |= 1u << q;
+          emit(q, f, comb, lx + 3 * s_cand[q].idx, 1);
+          n_phase1++;
+          if (s_cand[q].same > 1) n_ties++;
+        }
+        s_next = q;
       }
       __syncthreads();
+      np = s_next;
+      if (np >= D) break;
+      const int n = S.n[np];
+      const double* lastp = S.tail[np][min(n, PATH_TAIL) - 1];
+      const double last[3] = {lastp[0], lastp[1], lastp[2]};
       const int n_used = s_n_used;
       Best mine{0x7fffffff, 0.0, 0, 0};
       for (int i = tid; i < L; i += LINK_THREADS) {
         const u64 comb = lc[i];
         bool ok = true;
-        for (int c = 0; c < C; c++) ok = ok && ((s_gate[c] >> ((comb >> (4 * c)) & 15)) & 1u);
+        for (int c = 0; c < C; c++) ok = ok && ((s_gate[np][c] >> ((comb >> (4 * c)) & 15)) & 1u);
         for (int u = 0; u < n_used && ok; u++) ok = !conflicts(comb, s_used[u]);
         if (!ok) continue;
         const double err = le[i];
         if (!(err < p.error_)) continue;
-        if (!(dist3(lx + 3 * i, last) < MAX_STEP)) continue;  // cv::norm(c.point - pos) < MAX_STEP, :244
+        if (!(dist3(lx + 3 * i, last) < MAX_STEP)) continue;
         const Best cand{C - __popcll(nonzero_nibbles(comb & cam_bits)), err, i, 1};
         mine = better(mine, cand);
       }
@@ -346,6 +410,7 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
         if (best.same > 1) n_ties++;
       }
       __syncthreads();
+      np++;
     }
     if (__popc(s_processed) == D) continue;  // :137
 
@@ -376,23 +441,35 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
       }
       __syncthreads();
     }
-    // ---- classifyPaths (:262-332), one thread ----
+    // ---- classifyPaths (:262-332): the (combination, path) tail distances in parallel, the rest on one thread ----
+    {
+      const int nf = s_n_fin;
+      for (int i = tid; i < nf * D; i += LINK_THREADS) {
+        const int ci = i / D, j = i % D;
+        const int npc = min(S.n[j], PATH_TAIL);
+        double dist = -1;
+        if (npc > 0) {
+          const double* pt = lx + 3 * s_fin_idx[ci];
+          dist = 0;
+          for (int t = 0; t < npc; t++) dist += dist3(S.tail[j][t], pt);
+          dist /= (double)npc;
+        }
+        s_pdist[ci][j] = dist;
+      }
+    }
+    __syncthreads();
     if (tid == 0) {
       const int nf = s_n_fin;
       int cp_comb[LINK_MAX_FINAL], cp_path[LINK_MAX_FINAL];
       double cp_err[LINK_MAX_FINAL];
       unsigned processed = s_processed;
       for (int i = 0; i < nf; i++) {
-        const double* pt = lx + 3 * s_fin_idx[i];
         int bestPath = 0;
         double bestDist = -1;
         for (int j = 0; j < D; j++) {
           if (processed >> j & 1u) continue;
-          const int npc = min(S.n[j], PATH_TAIL);
-          if (npc == 0) continue;
-          double dist = 0;
-          for (int t = 0; t < npc; t++) dist += dist3(S.tail[j][t], pt);
-          dist /= (double)npc;
+          if (min(S.n[j], PATH_TAIL) == 0) continue;
+          const double dist = s_pdist[i][j];
           if (dist < bestDist || bestDist == -1) { bestDist = dist; bestPath = j; }
         }
         // std::sort(greater<>) of <= 16 elements is an insertion sort in libstdc++: stable, ascending error
