@@ -1,5 +1,7 @@
 #include "DetectionsContainer.h"
 
+#include "CsvIngest.h"
+
 #include <algorithm>
 #include <filesystem>
 #include <fstream>
@@ -25,34 +27,10 @@ std::vector<std::string> DetectionsContainer::getFiles(const char* path) {
 
 void DetectionsContainer::readFiles(const std::vector<std::string>& files, int offset, int recordSize, int startFrame,
                                     int endFrame) {
-  // Row = frame,(x,y,w,h,cx,cy,conf) x k.  Every token goes through std::stoi (so 0.97 -> 0); the
-  // detection is the box centre, fields 5 and 6 of the record; missing frame numbers become empty
-  // frames (DetectionsContainer.cpp:19-76).
-  for (const std::string& name : files) {
-    std::ifstream file(name);
-    data.emplace_back();
-    Cameras& cam = data.back();
-    std::string line, token;
-    int n_line = 0, frame = -1;
-    while (std::getline(file, line)) {
-      if (offset > n_line++) continue;
-      std::vector<int> fields;
-      std::istringstream iss(line);
-      while (std::getline(iss, token, ','))
-        if (!token.empty()) fields.push_back(std::stoi(token));
-      if (fields.empty()) throw std::runtime_error("Invalid CSV file!");
-      if ((fields[0] <= startFrame || fields[0] > endFrame) && startFrame != endFrame) {
-        frame = fields[0];
-        continue;
-      }
-      for (int i = 0; i < fields[0] - frame - 1; i++) cam.emplace_back();
-      frame = fields[0];
-      if ((fields.size() - 1) % (size_t)recordSize != 0) throw std::runtime_error("Invalid CSV file!");
-      cam.emplace_back();
-      for (size_t j = 0; j < fields.size() / (size_t)recordSize; j++)
-        cam.back().emplace_back((double)fields[j * recordSize + 5], (double)fields[j * recordSize + 6]);
-    }
-  }
+  // Row = frame,(x,y,w,h,cx,cy,conf) x k.  Every token goes through stoi (so 0.97 -> 0); the detection is
+  // the box centre, fields 5 and 6 of the record; missing frame numbers become empty frames
+  // (DetectionsContainer.cpp:19-76).  The parsing itself is CsvIngest.cpp (mmap, one thread per camera).
+  ingestDetectionFiles(files, offset, recordSize, startFrame, endFrame, data);
   if (data.size() < 2) throw std::runtime_error("There must be at least 2 cameras");
   for (size_t i = 1; i < data.size(); i++)
     if (data[i - 1].size() != data[i].size()) throw std::runtime_error("Number of frames on all cameras must be the same");

@@ -153,3 +153,18 @@ def test_classify_argument_checks(r02):
     ref = O.classify(ocams(cams), O.MATRIX, 1, new.reshape(-1).astype(np.int32), xy2[keep], nc, 20)
     assert np.array_equal(r["phase"], ref["phase"]) and np.array_equal(r["assign"], ref["assign"])
     assert np.all(r["phase"][0, 10:12] == 0) and np.all(r["paths"][0, 10:12] == 0)
+
+
+def test_accuracy_against_ground_truth(s09):
+    """End-to-end sanity (the reference's only 'expected results' are accuracy figures): the six
+    S09_D6 paths land within centimetres of the simulator's drone positions."""
+    import torch
+    from tri_b200 import evaluation as EV
+    cams, eng, (offs, xy, nc, nf) = s09
+    r = eng.classify(T.MATRIX, 6, offs, xy, nf)
+    truth = torch.tensor(np.load(G + "/S09_D6_truth.npz")["pos_m"], dtype=torch.float64, device="cuda:0") * 1000.0
+    stats = EV.evaluate(torch.tensor(r["paths"], device="cuda:0"), truth)
+    assert len(stats) == 6 and all(s is not None for s in stats)
+    assert sorted(s["label"] for s in stats) == list(range(6))  # every drone is followed by exactly one path
+    for s in stats:
+        assert s["median"] < 80.0 and s["frames_with_point"] > 0.9 * nf, s

@@ -76,3 +76,20 @@ def test_synthetic_rig_looks_at_the_volume():
     for c in cams:
         h = c.P @ X
         assert h[2] > 0 and abs(h[0] / h[2] - c.cx) < 1 and abs(h[1] / h[2] - c.cy) < 1
+
+
+def test_camera_tooling_reproduces_the_fixture_xmls(tmp_path):
+    """XCP / stationary_camera_data.csv -> cameras.xml: byte-identical to the committed
+    fixtures the goldens were generated from; numpy-free arithmetic vs the numpy recipe of the oracle tools."""
+    from tri_b200 import camera_tools as CT
+    src = os.path.join(G, "camera_sources")
+    CT.write_cameras_xml(CT.cameras_from_xcp(src + "/R02_D1_excerpt.xcp"), str(tmp_path / "a.xml"))
+    assert open(tmp_path / "a.xml").read() == open(G + "/R02_D1_cameras.xml").read()
+    CT.write_cameras_xml(CT.cameras_from_stationary_csv(src + "/S09_D6_stationary_camera_data.csv"), str(tmp_path / "b.xml"))
+    got = T.load_cameras_xml(str(tmp_path / "b.xml"))
+    want = T.load_cameras_xml(G + "/S09_D6_cameras.xml")
+    assert len(got) == len(want) == 8
+    for a, b in zip(got, want):
+        assert (a.cam_id, a.width, a.height) == (b.cam_id, b.width, b.height)
+        np.testing.assert_allclose(a.P, b.P, rtol=1e-12, atol=1e-7)
+    assert CT.main(["camera_tools", "xcp", src + "/R02_D1_excerpt.xcp", str(tmp_path / "c.xml")]) == 0
