@@ -250,6 +250,15 @@ def main():
                                                               if a.mode == "matrix" else "PolicyTile<RayPolicy>")),
             "algorithmic_bytes_per_frame": 8 * N_CAMS + 12, "kernel_ms": kernel_ms}
 
+    if a.precision == "f64" and a.mode == "matrix":
+        # secondary roofline: the FP64 pipe.  Peak = measured DFMA issue rate (tools/micro/fma_rate.cu: 1.94 warp-inst/clk/SM
+        # = 62 lanes) x 148 SMs x 1965 MHz x 2; flops per frame = 56 * C_valid + 80, C_valid = 6.4 for p_missing = 0.2.
+        dfma_peak = 1.94 * 32 * 148 * 1.965e9 * 2 / 1e12
+        fl = (56 * 6.4 + 80) * F / (kernel_ms * 1e-3) / 1e12
+        roof["fp64_pipe"] = {"achieved_tflops": fl, "peak_tflops": dfma_peak, "frac": fl / dfma_peak,
+                             "executed_frac": (56 * 8 + 80) * F / (kernel_ms * 1e-3) / 1e12 / dfma_peak,
+                             "note": "absent views still issue (masked), so the pipe executes 56*8+80 flops per frame; DFMAs with three "
+                                     "distinct register sources issue at 2/3 rate (tools/micro/dfma_rf.cu)"}
     res = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": a.precision, "data": "synthetic",
