@@ -34,7 +34,7 @@ constexpr int CLS_MAX_CAMS = 16;   // 4 bits per camera in a 64-bit combination
 constexpr int CLS_THREADS = 128;
 constexpr int LINK_THREADS = 256;
 constexpr int LINK_MAX_FINAL = 64;
-constexpr int LINK_STAGE_LEAVES = 1792;
+constexpr int LINK_STAGE_LEAVES = 4096;  // leaves of one frame staged in (dynamic) shared memory: 40 B each
 typedef unsigned long long u64;
 
 // DroneClassifier.h:11-17
@@ -189,6 +189,7 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
       }
       m = min(out_base, p.cap);
       if (tid == 0) atomicMax(&ctr->max_frontier, out_base);
+      if (last && m > 64 * LINK_THREADS && tid == 0) atomicExch(&ctr->bad_input, 2);  // the linking pass keeps one live bit per leaf in a u64 per thread
       u64* t = fin; fin = fout; fout = t;
       if (m == 0) break;
       if (last) {
@@ -201,11 +202,31 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
         __syncthreads();
         const long long off = s_off;
         if (off >= 0) {
+          // ... in PRIORITY order: rank of leaf i = number of leaves the reference's priority_queue pops
+          // before it = those with fewer unused cameras, then smaller error (Combination::operator<,
+          // :12-20), ties by DFS order.  Rank by counting (m is ~1e3; frames are independent, so this is
+          // parallel work) and scatter; the sequential linking kernel then only walks prefixes.
+          const u64 cam_bits = C == 16 ? ~0ull : ((1ull << (4 * C)) - 1);
+          u64 n_tie = 0;
           for (int i = tid; i < m; i += CLS_THREADS) {
-            leaf_comb[off + i] = fin[i];
-            leaf_err[off + i] = t_err[i];
-            leaf_xyz[3 * (off + i)] = t_xyz[3 * i]; leaf_xyz[3 * (off + i) + 1] = t_xyz[3 * i + 1]; leaf_xyz[3 * (off + i) + 2] = t_xyz[3 * i + 2];
+            const u64 ci = fin[i];
+            const double ei = t_err[i];
+            const int zi = C - __popcll(nonzero_nibbles(ci & cam_bits));
+            int rank = 0;
+            bool tie = false;
+            for (int j = 0; j < m; j++) {
+              const int zj = C - __popcll(nonzero_nibbles(fin[j] & cam_bits));
+              const double ej = t_err[j];
+              const bool eq = zj == zi && ej == ei;
+              rank += (zj < zi) || (zj == zi && ej < ei) || (eq && j < i);
+              tie = tie || (eq && j != i);
+            }
+            n_tie += tie;
+            leaf_comb[off + rank] = ci;
+            leaf_err[off + rank] = ei;
+            leaf_xyz[3 * (off + rank)] = t_xyz[3 * i]; leaf_xyz[3 * (off + rank) + 1] = t_xyz[3 * i + 1]; leaf_xyz[3 * (off + rank) + 2] = t_xyz[3 * i + 2];
           }
+          if (n_tie) atomicAdd(&ctr->ties, n_tie);
           if (tid == 0) { leaf_off[f - p.f0] = off; leaf_cnt[f - p.f0] = m; atomicAdd(&ctr->leaves, (u64)m); }
         } else if (tid == 0) {
           leaf_off[f - p.f0] = 0; leaf_cnt[f - p.f0] = 0;
@@ -225,35 +246,6 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
 }
 
 // ---- (B) linking -------------------------------------------------------------------------------
-struct Best {
-  int zeros;   // INT_MAX = none
-  double err;
-  int idx, same;  // same = admissible leaves seen with this (zeros, err)
-};
-__device__ __forceinline__ Best better(const Best& a, const Best& b) {
-  if (a.zeros == 0x7fffffff) return b;
-  if (b.zeros == 0x7fffffff) return a;
-  if (a.zeros == b.zeros && a.err == b.err) { Best r = a.idx < b.idx ? a : b; r.same = a.same + b.same; return r; }
-  if (a.zeros != b.zeros) return a.zeros < b.zeros ? a : b;  // Combination::operator< (:12-20)
-  return a.err < b.err ? a : b;
-}
-__device__ inline Best block_best(Best v, Best* s_best) {
-  for (int o = 16; o > 0; o >>= 1) {
-    Best u;
-    u.zeros = __shfl_down_sync(0xffffffffu, v.zeros, o);
-    u.err = __shfl_down_sync(0xffffffffu, v.err, o);
-    u.idx = __shfl_down_sync(0xffffffffu, v.idx, o);
-    u.same = __shfl_down_sync(0xffffffffu, v.same, o);
-    v = better(v, u);
-  }
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = v;
-  __syncthreads();
-  Best r = s_best[0];
-  for (int w = 1; w < LINK_THREADS / 32; w++) r = better(r, s_best[w]);
-  return r;
-}
-
 __device__ __forceinline__ double dist3(const double* a, const double* b) {  // cv::norm(a - b)
   const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
   return sqrt(x * x + y * y + z * z);
@@ -268,22 +260,24 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
   __shared__ unsigned s_gate[TRI_MAX_DRONES][CLS_MAX_CAMS];
   __shared__ double s_dir[CLS_MAX_CAMS * TRI_MAX_DETS][3];
   __shared__ bool s_ndet[CLS_MAX_CAMS * TRI_MAX_DETS];
-  __shared__ Best s_cand[TRI_MAX_DRONES];
+  __shared__ int s_cand[TRI_MAX_DRONES];
   __shared__ bool s_active[TRI_MAX_DRONES];
-  __shared__ int s_next;
   __shared__ double s_pdist[LINK_MAX_FINAL][TRI_MAX_DRONES];
   __shared__ u64 s_used[TRI_MAX_DRONES];
   __shared__ u64 s_fin[LINK_MAX_FINAL];
   __shared__ int s_fin_idx[LINK_MAX_FINAL];
-  __shared__ Best s_best[LINK_THREADS / 32];
-  __shared__ int s_n_used, s_n_fin;
+  __shared__ int s_n_fin, s_n_used;
+  __shared__ int s_first[2][LINK_THREADS / 32];
   __shared__ unsigned s_processed;
-  __shared__ u64 s_comb[LINK_STAGE_LEAVES];     // this frame's candidates, staged once: every path's arg-min
-  __shared__ double s_err[LINK_STAGE_LEAVES];   // and every greedy round of phase 2 re-scans them
+  // this frame's candidates (combination, error, point), staged once: the sequential part of the frame then
+  // never waits on global memory (a lone CTA cannot hide a ~1 us round trip behind anything)
+  extern __shared__ __align__(16) unsigned char link_dyn[];
+  u64* s_comb = reinterpret_cast<u64*>(link_dyn);
+  double* s_err = reinterpret_cast<double*>(link_dyn + sizeof(u64) * LINK_STAGE_LEAVES);
+  double* s_xyz = reinterpret_cast<double*>(link_dyn + (sizeof(u64) + sizeof(double)) * LINK_STAGE_LEAVES);
   const int tid = threadIdx.x, C = p.n_cams, D = p.n_drones;
-  const u64 cam_bits = C == 16 ? ~0ull : ((1ull << (4 * C)) - 1);
   for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += LINK_THREADS) ((int*)&S)[i] = ((const int*)state)[i];
-  u64 n_phase1 = 0, n_phase2 = 0, n_ties = 0;  // thread 0 only
+  u64 n_phase1 = 0, n_phase2 = 0;  // thread 0 only
   __syncthreads();
 
   auto emit = [&](int path, int f, u64 comb, const double* pt, int phase) {  // thread 0: push a point to a path
@@ -307,10 +301,11 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
     const bool staged = L <= LINK_STAGE_LEAVES;
     const u64* lc = staged ? s_comb : leaf_comb + off;
     const double* le = staged ? s_err : leaf_err + off;
-    const double* lx = leaf_xyz + 3 * off;
-    if (staged)
+    const double* lx = staged ? s_xyz : leaf_xyz + 3 * off;
+    if (staged) {
       for (int i = tid; i < L; i += LINK_THREADS) { s_comb[i] = leaf_comb[off + i]; s_err[i] = leaf_err[off + i]; }
-    if (tid == 0) { s_n_used = 0; s_processed = 0; }
+      for (int i = tid; i < 3 * L; i += LINK_THREADS) s_xyz[i] = leaf_xyz[3 * off + i];
+    }
     __syncthreads();
 
     // ---- phase 1: tracking (:119-135) ----
@@ -332,115 +327,98 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
       if (ref::dist_to_ray(ray.pos[c], s_dir[k], last[0], last[1], last[2]) < MAX_STEP) atomicOr(&s_gate[np][c], 1u << (d + 1));
     }
     __syncthreads();
-    // (iii) one warp per path: best admissible candidate ignoring the combinations used by earlier paths
-    for (int np = tid >> 5; np < D; np += LINK_THREADS / 32) {
+    // (iii) one warp per path.  The leaves are stored in priority order, so "the first element the
+    // reference's priority_queue pops that passes :241-246" is the FIRST admissible leaf: walk the list 32
+    // at a time and stop at the first hit.  Combinations used by earlier paths are ignored here ...
+    const int lane = tid & 31, warp = tid >> 5;
+    auto gate_ok = [&](int np, u64 comb) {
+      bool ok = true;
+      for (int c = 0; c < C; c++) ok = ok && ((s_gate[np][c] >> ((comb >> (4 * c)) & 15)) & 1u);
+      return ok;
+    };
+    for (int np = warp; np < D; np += LINK_THREADS / 32) {
       const int n = S.n[np];
-      Best mine{0x7fffffff, 0.0, 0, 0};
       const double* last = S.tail[np][min(max(n, 1), PATH_TAIL) - 1];
       const bool active = n != 0 && !(last[0] == 0 && last[1] == 0 && last[2] == 0);  // :121-123
-      if (active) {
-        for (int i = tid & 31; i < L; i += 32) {
-          const u64 comb = lc[i];
-          bool ok = true;
-          for (int c = 0; c < C; c++) ok = ok && ((s_gate[np][c] >> ((comb >> (4 * c)) & 15)) & 1u);
-          if (!ok) continue;
-          const double err = le[i];
-          if (!(err < p.error_)) continue;
-          if (!(dist3(lx + 3 * i, last) < MAX_STEP)) continue;  // cv::norm(c.point - pos) < MAX_STEP, :244
-          const Best cand{C - __popcll(nonzero_nibbles(comb & cam_bits)), err, i, 1};
-          mine = better(mine, cand);
-        }
-        for (int o = 16; o > 0; o >>= 1) {
-          Best u;
-          u.zeros = __shfl_down_sync(0xffffffffu, mine.zeros, o);
-          u.err = __shfl_down_sync(0xffffffffu, mine.err, o);
-          u.idx = __shfl_down_sync(0xffffffffu, mine.idx, o);
-          u.same = __shfl_down_sync(0xffffffffu, mine.same, o);
-          mine = better(mine, u);
-        }
+      int found = -1;
+      for (int base = 0; active && base < L && found < 0; base += 32) {
+        const int i = base + lane;
+        bool ok = i < L && gate_ok(np, lc[i]) && le[i] < p.error_;
+        if (ok) ok = dist3(lx + 3 * i, last) < MAX_STEP;  // cv::norm(c.point - pos) < MAX_STEP, :244
+        const unsigned hit = __ballot_sync(0xffffffffu, ok);
+        if (hit) found = base + __ffs(hit) - 1;
       }
-      if ((tid & 31) == 0) { s_cand[np] = mine; s_active[np] = active; }
+      if (lane == 0) { s_cand[np] = found; s_active[np] = active; }
     }
     __syncthreads();
-    // (iv) in path order: a candidate that does not collide with an earlier path's pick is that path's
-    // answer (it is also the best of the filtered set); otherwise re-scan with the used list
-    for (int np = 0; np < D;) {
-      if (tid == 0) {
-        int q = np;
-        for (; q < D; q++) {
-          if (!s_active[q] || s_cand[q].zeros == 0x7fffffff) continue;
-          const u64 comb = lc[s_cand[q].idx];
-          bool clash = false;
-          for (int u = 0; u < s_n_used; u++) clash = clash || conflicts(comb, s_used[u]);
-          if (clash) break;
-          s_used[s_n_used++] = comb;
-          s_processed |= 1u << q;
-          emit(q, f, comb, lx + 3 * s_cand[q].idx, 1);
+    // (iv) ... and resolved here in path order by warp 0: a candidate that does not collide with an earlier
+    // path's pick is also the first of the filtered list; otherwise walk the list again with the filter.
+    // Phase 2 (pickBestCombinations, :200-217) follows on the same warp: ONE pass in priority order keeping
+    // every leaf that collides with nothing kept so far -- literally the reference's pop loop.
+    if (warp == 0) {
+      int n_used = 0;
+      unsigned processed = 0;
+      for (int np = 0; np < D; np++) {
+        if (!s_active[np]) continue;
+        int cand = s_cand[np];
+        if (cand < 0) continue;
+        bool clash = false;
+        for (int u = 0; u < n_used; u++) clash = clash || conflicts(lc[cand], s_used[u]);
+        if (clash) {
+          const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
+          cand = -1;
+          for (int base = 0; base < L && cand < 0; base += 32) {
+            const int i = base + lane;
+            bool ok = i < L && gate_ok(np, lc[i]) && le[i] < p.error_;
+            for (int u = 0; u < n_used && ok; u++) ok = !conflicts(lc[i], s_used[u]);
+            if (ok) ok = dist3(lx + 3 * i, last) < MAX_STEP;
+            const unsigned hit = __ballot_sync(0xffffffffu, ok);
+            if (hit) cand = base + __ffs(hit) - 1;
+          }
+          if (cand < 0) continue;
+        }
+        if (lane == 0) {
+          s_used[n_used] = lc[cand];
+          emit(np, f, lc[cand], lx + 3 * cand, 1);
           n_phase1++;
-          if (s_cand[q].same > 1) n_ties++;
         }
-        s_next = q;
+        n_used++;
+        processed |= 1u << np;
+        __syncwarp();
       }
-      __syncthreads();
-      np = s_next;
-      if (np >= D) break;
-      const int n = S.n[np];
-      const double* lastp = S.tail[np][min(n, PATH_TAIL) - 1];
-      const double last[3] = {lastp[0], lastp[1], lastp[2]};
-      const int n_used = s_n_used;
-      Best mine{0x7fffffff, 0.0, 0, 0};
-      for (int i = tid; i < L; i += LINK_THREADS) {
-        const u64 comb = lc[i];
-        bool ok = true;
-        for (int c = 0; c < C; c++) ok = ok && ((s_gate[np][c] >> ((comb >> (4 * c)) & 15)) & 1u);
-        for (int u = 0; u < n_used && ok; u++) ok = !conflicts(comb, s_used[u]);
-        if (!ok) continue;
-        const double err = le[i];
-        if (!(err < p.error_)) continue;
-        if (!(dist3(lx + 3 * i, last) < MAX_STEP)) continue;
-        const Best cand{C - __popcll(nonzero_nibbles(comb & cam_bits)), err, i, 1};
-        mine = better(mine, cand);
-      }
-      const Best best = block_best(mine, s_best);
-      if (tid == 0 && best.zeros != 0x7fffffff) {
-        s_used[s_n_used++] = lc[best.idx];
-        s_processed |= 1u << np;
-        emit(np, f, lc[best.idx], lx + 3 * best.idx, 1);
-        n_phase1++;
-        if (best.same > 1) n_ties++;
-      }
-      __syncthreads();
-      np++;
+      if (lane == 0) { s_processed = processed; s_n_used = n_used; s_n_fin = 0; }
     }
-    if (__popc(s_processed) == D) continue;  // :137
-
-    // ---- phase 2: pickBestCombinations (:200-217) ----
-    if (tid == 0) s_n_fin = 0;
     __syncthreads();
-    for (;;) {
-      const int n_used = s_n_used, n_fin = s_n_fin;
-      Best mine{0x7fffffff, 0.0, 0, 0};
-      for (int i = tid; i < L; i += LINK_THREADS) {
-        const u64 comb = lc[i];
-        bool ok = true;
-        for (int u = 0; u < n_fin && ok; u++) ok = !conflicts(comb, s_fin[u]);
-        for (int u = 0; u < n_used && ok; u++) ok = !conflicts(comb, s_used[u]);
-        if (!ok) continue;
-        const double err = le[i];
-        if (!(err < p.error_)) continue;
-        const Best cand{C - __popcll(nonzero_nibbles(comb & cam_bits)), err, i, 1};
-        mine = better(mine, cand);
+    if (__popc(s_processed) == D) continue;  // :137
+    // ---- phase 2: pickBestCombinations (:200-217).  The reference pops the whole queue in priority order
+    // and keeps every combination that collides with nothing kept so far; with the leaves in priority
+    // order that is: repeatedly take the FIRST live leaf and kill everything that collides with it.  All
+    // threads filter (each owns leaves tid, tid+256, ...; live flags in a register), one block-wide
+    // min-index reduction per kept combination.
+    {
+      const int n_used = s_n_used;
+      u64 live = 0;  // bit k <=> leaf tid + k * LINK_THREADS is still a candidate (L <= 64 * LINK_THREADS, checked in (A))
+      for (int k = 0, i = tid; i < L; k++, i += LINK_THREADS) {
+        bool ok = le[i] < p.error_;
+        for (int u = 0; u < n_used && ok; u++) ok = !conflicts(lc[i], s_used[u]);
+        live |= (ok ? 1ull : 0ull) << k;
       }
-      const Best best = block_best(mine, s_best);
-      if (best.zeros == 0x7fffffff || n_fin >= LINK_MAX_FINAL) break;
-      if (tid == 0) {
-        s_fin[n_fin] = lc[best.idx];
-        s_fin_idx[n_fin] = best.idx;
-        s_n_fin = n_fin + 1;
-        if (best.same > 1) n_ties++;
+      for (int round = 0; round < LINK_MAX_FINAL; round++) {
+        int first = live ? tid + (__ffsll((long long)live) - 1) * LINK_THREADS : 0x7fffffff;
+        for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+        if (lane == 0) s_first[round & 1][warp] = first;
+        __syncthreads();
+        first = s_first[round & 1][0];
+        for (int w = 1; w < LINK_THREADS / 32; w++) first = min(first, s_first[round & 1][w]);
+        if (first == 0x7fffffff) break;
+        const u64 pick = lc[first];
+        if (tid == 0) { s_fin[round] = pick; s_fin_idx[round] = first; s_n_fin = round + 1; }
+        for (int k = 0, i = tid; i < L; k++, i += LINK_THREADS)
+          if ((live >> k & 1ull) && (i == first || conflicts(lc[i], pick))) live &= ~(1ull << k);
       }
-      __syncthreads();
     }
+    __syncthreads();
+
     // ---- classifyPaths (:262-332): the (combination, path) tail distances in parallel, the rest on one thread ----
     {
       const int nf = s_n_fin;
@@ -495,7 +473,7 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
   }
   __syncthreads();
   for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += LINK_THREADS) ((int*)state)[i] = ((const int*)&S)[i];
-  if (tid == 0) { atomicAdd(&ctr->phase1, n_phase1); atomicAdd(&ctr->phase2, n_phase2); atomicAdd(&ctr->ties, n_ties); }
+  if (tid == 0) { atomicAdd(&ctr->phase1, n_phase1); atomicAdd(&ctr->phase2, n_phase2); }
 }
 
 // Grow-only device buffer: the classifier's work space lives on the engine across calls (cudaMalloc /
@@ -601,6 +579,8 @@ extern "C" int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drone
   };
   int st = alloc_work();
   if (st != TRI_OK) return st;
+  constexpr int LINK_DYN_BYTES = (int)((sizeof(u64) + 4 * sizeof(double)) * LINK_STAGE_LEAVES);
+  TRI_CUDA(cudaFuncSetAttribute(link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LINK_DYN_BYTES));
 
   ClsCounters h{};
   int max_frontier = 0;
@@ -618,6 +598,7 @@ extern "C" int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drone
     TRI_CUDA(cudaGetLastError());
     TRI_CUDA(cudaMemcpyAsync(&h, d_ctr.p, sizeof(h), cudaMemcpyDeviceToHost, s));
     TRI_CUDA(cudaStreamSynchronize(s));
+    if (h.bad_input == 2) return fail(TRI_ERR_CAPACITY, "more than 16384 candidate combinations in one frame");
     if (h.bad_input) return fail(TRI_ERR_ARG, "malformed detection offsets");
     if (h.overflow_frontier || h.overflow_leaves) {
       // grow the work buffers (or shrink the batch) and redo this batch; the statistics of the
@@ -631,7 +612,7 @@ extern "C" int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drone
       continue;
     }
     max_frontier = std::max(max_frontier, h.max_frontier);
-    link_kernel<<<1, LINK_THREADS, 0, s>>>(e->ray, p, d_offs.as<int32_t>(), d_dets.as<double>(), d_lcomb.as<u64>(), d_lerr.as<double>(),
+    link_kernel<<<1, LINK_THREADS, LINK_DYN_BYTES, s>>>(e->ray, p, d_offs.as<int32_t>(), d_dets.as<double>(), d_lcomb.as<u64>(), d_lerr.as<double>(),
                                             d_lxyz.as<double>(), d_loff.as<long long>(), d_lcnt.as<int>(), d_state.as<LinkState>(),
                                             d_paths.as<double>(), out_assign ? d_assign.as<int8_t>() : nullptr,
                                             out_phase ? d_phase.as<uint8_t>() : nullptr, d_ctr.as<ClsCounters>());
