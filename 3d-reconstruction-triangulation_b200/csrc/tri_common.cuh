@@ -92,6 +92,19 @@ __device__ __forceinline__ float fma_(float a, float b, float c) { return fmaf(a
 __device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ float mul_(float a, float b) { return __fmul_rn(a, b); }
 
+// Reciprocal for the solves.  FP64: MUFU.RCP64H seed + two Newton steps (5 FP64 instructions, <= 1 ulp)
+// instead of the ~35-instruction IEEE division -- the FP64 pipe is the bound of every FP64 kernel here
+// (the ray solve has one reciprocal per view).  Deterministic, so all kernel variants stay bit-identical.
+// FP32 keeps the correctly rounded division.  The oracle-order code (tri_ref.cuh) does not use this.
+__device__ __forceinline__ double rcp_(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  r = fma(fma(-x, r, 1.0), r, r);
+  r = fma(fma(-x, r, 1.0), r, r);
+  return r;
+}
+__device__ __forceinline__ float rcp_(float x) { return 1.0f / x; }
+
 template <typename T>
 __device__ __forceinline__ void solve_sym3(const T M[6], const T v[3], T X[3]) {
   const T c00 = fma_(M[3], M[5], -mul_(M[4], M[4]));
@@ -101,7 +114,7 @@ __device__ __forceinline__ void solve_sym3(const T M[6], const T v[3], T X[3]) {
   const T c12 = fma_(M[1], M[2], -mul_(M[0], M[4]));
   const T c22 = fma_(M[0], M[3], -mul_(M[1], M[1]));
   const T det = fma_(M[0], c00, fma_(M[1], c01, mul_(M[2], c02)));
-  const T inv = T(1) / det;
+  const T inv = rcp_(det);
   X[0] = mul_(fma_(c00, v[0], fma_(c01, v[1], mul_(c02, v[2]))), inv);
   X[1] = mul_(fma_(c01, v[0], fma_(c11, v[1], mul_(c12, v[2]))), inv);
   X[2] = mul_(fma_(c02, v[0], fma_(c12, v[1], mul_(c22, v[2]))), inv);

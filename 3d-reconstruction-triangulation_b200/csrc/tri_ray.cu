@@ -37,7 +37,7 @@ struct RayPolicy {
     u[1] = fma_(r.U0[c][1], x, fma_(r.U1[c][1], y, r.U2[c][1]));
     u[2] = fma_(r.U0[c][2], x, fma_(r.U1[c][2], y, r.U2[c][2]));
     const T vx = fma_(r.ax[c], x, r.bx[c]), vy = fma_(r.ay[c], y, r.by[c]);
-    inv = T(1) / fma_(vx, vx, fma_(vy, vy, r.dd[c]));
+    inv = rcp_(fma_(vx, vx, fma_(vy, vy, r.dd[c])));
   }
   static __device__ __forceinline__ void add(const Rig& r, int c, T x, T y, bool valid, Acc& a) {
     if (!valid) return;
@@ -73,7 +73,7 @@ struct RayPolicy {
     // scaling fixed at the start point, eps = FLT_EPSILON, 1000 iterations: RayTriangulator.h:9-11,
     // RayTriangulator.cpp:100-104) on the analytic normal equations A = M, v = M p - c.
     const T k = a.kn - a.ku;
-    const T rn = T(1) / (T)n;
+    const T rn = rcp_((T)n);
     T p[3] = {a.so[0] * rn, a.so[1] * rn, a.so[2] * rn};
     const T D[3] = {M[0], M[3], M[5]};
     T lambda = 1, lc = T(0.75);
@@ -90,19 +90,20 @@ struct RayPolicy {
       const T Md0 = M[0] * d[0] + M[1] * d[1] + M[2] * d[2], Md1 = M[1] * d[0] + M[3] * d[1] + M[4] * d[2],
               Md2 = M[2] * d[0] + M[4] * d[1] + M[5] * d[2];
       const T dS = d[0] * (2 * g[0] - Md0) + d[1] * (2 * g[1] - Md1) + d[2] * (2 * g[2] - Md2);
-      const T R = (S - Sd) / (fabs(dS) > (T)DBL_EPSILON ? dS : T(1));
+      const T R = (S - Sd) * rcp_(fabs(dS) > (T)DBL_EPSILON ? dS : T(1));
       if (R > T(0.75)) {
         lambda *= T(0.5);
         if (lambda < lc) lambda = 0;
       } else if (R < T(0.25)) {
         const T t = d[0] * g[0] + d[1] * g[1] + d[2] * g[2];
-        T nu = (Sd - S) / (fabs(t) > (T)DBL_EPSILON ? t : T(1)) + 2;
+        T nu = (Sd - S) * rcp_(fabs(t) > (T)DBL_EPSILON ? t : T(1)) + 2;
         nu = fmin(fmax(nu, T(2)), T(10));
         if (lambda == 0) {  // re-inflate from diag(M^-1)
           const T c00 = M[3] * M[5] - M[4] * M[4], c11 = M[0] * M[5] - M[2] * M[2], c22 = M[0] * M[3] - M[1] * M[1];
           const T det = M[0] * c00 + M[1] * (M[2] * M[4] - M[1] * M[5]) + M[2] * (M[1] * M[4] - M[2] * M[3]);
-          const T mx = fmax(fmax(fabs(c00 / det), fabs(c11 / det)), fmax(fabs(c22 / det), (T)DBL_EPSILON));
-          lambda = lc = T(1) / mx;
+          const T idet = rcp_(det);
+          const T mx = fmax(fmax(fabs(c00 * idet), fabs(c11 * idet)), fmax(fabs(c22 * idet), (T)DBL_EPSILON));
+          lambda = lc = rcp_(mx);
           nu *= T(0.5);
         }
         lambda *= nu;
