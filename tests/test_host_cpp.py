@@ -20,7 +20,7 @@ G = os.path.join(ROOT, "tests", "golden")
 @pytest.fixture(scope="module")
 def host_bins():
     subprocess.check_call(["make", "-s", "-C", HOST])
-    return os.path.join(HOST, "host_selftest"), os.path.join(HOST, "tri_main")
+    return os.path.join(HOST, "host_selftest"), os.path.join(HOST, "tri_main"), os.path.join(HOST, "host_gpu_selftest")
 
 
 def test_cpp_loaders_match_python_host_and_twin(host_bins):
@@ -133,3 +133,36 @@ def test_cli_rejects_unknown_triangulator(host_bins, tmp_path):
     r = subprocess.run([host_bins[1], G + "/R02_D1_cameras.xml", str(csv_dir), "--triangulator", "svd"], capture_output=True, text=True,
                        cwd=str(tmp_path))
     assert r.returncode != 0 and "Invalid --triangulator argument" in r.stderr
+
+
+@pytest.mark.gpu
+def test_cpp_triangulator_adapters(host_bins, tmp_path):
+    """The C++ MatrixTriangulator / RayTriangulator adapters called the way the reference's code calls them:
+    triangulatePoints, triangulatePoint on a subset, static getDistFromRay, and the reference's exception texts."""
+    csv_dir = tmp_path / "data"
+    csv_dir.mkdir()
+    nc, nf = write_csvs(str(csv_dir), G + "/R02_D1_dets.npz", 60)
+    out = subprocess.check_output([host_bins[2], G + "/R02_D1_cameras.xml", str(csv_dir)], text=True).splitlines()
+    assert out[0] == "types matrix ray 4"
+    g = np.load(G + "/golden_R02_D1_batch.npz")
+    m = np.array([[float(v) for v in l.split()[2:]] for l in out if l.startswith("matrix ")])
+    r = np.array([[float(v) for v in l.split()[2:]] for l in out if l.startswith("ray ")])
+    assert m.shape == (60, 3) and r.shape == (60, 3)
+    np.testing.assert_allclose(m, g["matrix_xyz"][:60], rtol=1e-9, atol=1e-7)
+    same = np.ones(60, bool)
+    np.testing.assert_allclose(r[same], g["ray_xyz"][:60][same], rtol=0, atol=1e-5)  # RayTriangulator defaults to the exact LM
+    cams = O.load_cameras(G + "/R02_D1_cameras.xml")
+    offs, xy, _, nfull = O.load_dets(G + "/R02_D1_dets.npz")
+    pts = O.dets_to_points(offs, xy, nc, nfull)
+    Xm, em = O.matrix_point(cams, [0, 2], pts[[0, 2], 0])
+    got = [float(v) for v in [l for l in out if l.startswith("point_matrix")][0].split()[1:]]
+    np.testing.assert_allclose(got, [*Xm, em], rtol=1e-9)
+    Xr, er, _ = O.ray_point(cams, [0, 2], pts[[0, 2], 0])
+    got = [float(v) for v in [l for l in out if l.startswith("point_ray")][0].split()[1:]]
+    assert got == [*Xr, er]  # trajectory-exact
+    want = O.lib().orc_dist_from_ray(O.C.byref(cams[1]), O.C.c_double(pts[1, 0, 0]), O.C.c_double(pts[1, 0, 1]), O._p(np.ascontiguousarray(Xm)))
+    d = float([l for l in out if l.startswith("dist ")][0].split()[1])
+    assert abs(d - want) <= 1e-9 * max(1.0, abs(want))
+    assert "throw_dim Every camera should have the same number of points" in out
+    assert "throw_few Too few rays are found" in out and "throw_few Too few detections are found" in out
+    assert "throw_one Too few rays are found" in out
