@@ -334,3 +334,24 @@ def test_other_camera_counts(torch, n_cams):
         sub = [k for k in range(n_cams) if ref["mask"][f] >> k & 1]
         Xc = O.ray_closed_form(oc, sub, host[sub, f].astype(np.float64))
         assert np.abs(c["xyz_f64"][f].cpu().numpy() - Xc).max() < 1e-6
+
+
+def test_host_path_multi_chunk_pipeline(torch):
+    """More frames than one staging chunk (1 Mi frames): the three-slot H2D / kernel / D2H pipeline returns
+    exactly what one device-resident launch returns, for every output, in both solvers' default precisions."""
+    cams = S.ring_rig(8)
+    eng = T.Engine(cams, 0)
+    n = 2_621_447  # 2.5 chunks, odd
+    xy = S.generate_frames(cams, n, device="cuda:0")
+    host = xy.cpu().numpy()
+    for mode, flags in ((T.MATRIX, 0), (T.MATRIX, T.F32), (T.RAY, 0), (T.RAY, T.RAY_CLOSED_FORM | T.F32)):
+        d = eng.triangulate_points_device(mode, xy, flags | T.ALLOW_TOO_FEW, want=("xyz_f32", "mask"))
+        st, bad = eng.device_status()
+        h = eng.triangulate_points(mode, host, flags | T.ALLOW_TOO_FEW, want=("xyz_f32", "mask"))
+        assert np.array_equal(h["xyz_f32"], d["xyz_f32"].cpu().numpy())
+        assert np.array_equal(h["mask"], d["mask"].cpu().numpy().view(np.uint32))
+        assert h["first_bad_frame"] == bad
+    full = eng.triangulate_points(T.MATRIX, host, T.ALLOW_TOO_FEW, want=("xyz_f64", "err", "mask"))
+    dd = eng.triangulate_points_device(T.MATRIX, xy, T.ALLOW_TOO_FEW, want=("xyz_f64", "err"))
+    eng.device_status()
+    assert np.array_equal(full["xyz_f64"], dd["xyz_f64"].cpu().numpy()) and np.array_equal(full["err"], dd["err"].cpu().numpy())
