@@ -12,12 +12,6 @@
 // HBM traffic per frame: 8 B x n_cams in, 12 B out.
 #include "tri_pipe.cuh"
 
-#ifndef TRI_F64_HI_ONLY
-#define TRI_F64_HI_ONLY false
-#endif
-#ifndef TRI_F64_REUSE_ORDER
-#define TRI_F64_REUSE_ORDER 0
-#endif
 
 namespace tri {
 
@@ -37,34 +31,13 @@ __device__ __forceinline__ void load12(const float (&src)[12], float (&P)[12]) {
 // the ALU pipe) rather than skipped or predicated: within a warp some lane almost always has the view,
 // so the FMAs issue either way; a divergent branch costs BSSY/BSYNC barriers (27 % of the stall samples
 // in profiles/ncu_r1c.md) and "@p fma.rn.f64" sequences measured 45 % slower than this form.
-template <bool HI_ONLY>
-__device__ __forceinline__ double keep_if(bool valid, double a) {
-  if constexpr (HI_ONLY) return __hiloint2double(valid ? __double2hiint(a) : 0, __double2loint(a));
-  return valid ? a : 0.0;
-}
 __device__ __forceinline__ void acc_row(bool valid, double a0, double a1, double a2, double b, double (&M)[6], double (&v)[3]) {
-  a0 = keep_if<TRI_F64_HI_ONLY>(valid, a0); a1 = keep_if<TRI_F64_HI_ONLY>(valid, a1); a2 = keep_if<TRI_F64_HI_ONLY>(valid, a2);
-#if TRI_F64_REUSE_ORDER
-  // A DFMA with three distinct register-pair sources issues every 3 cycles instead of 2 on sm_100
-  // (tools/micro/dfma_rf.cu: 1.33 vs 1.99 warp-inst/clk/SM); a source shared with the previous
-  // instruction in the same slot comes from the operand-reuse cache.  This order walks the nine products
-  // so that each shares a multiplicand with its predecessor: a0a0 a0a1 a1a1 a1a2 a2a2 a2b a1b a0b a0a2.
-  asm("fma.rn.f64 %0, %9, %9, %0;\n"
-      "fma.rn.f64 %1, %9, %10, %1;\n"
-      "fma.rn.f64 %3, %10, %10, %3;\n"
-      "fma.rn.f64 %4, %10, %11, %4;\n"
-      "fma.rn.f64 %5, %11, %11, %5;\n"
-      "fma.rn.f64 %8, %11, %12, %8;\n"
-      "fma.rn.f64 %7, %10, %12, %7;\n"
-      "fma.rn.f64 %6, %9, %12, %6;\n"
-      "fma.rn.f64 %2, %9, %11, %2;\n"
-      : "+d"(M[0]), "+d"(M[1]), "+d"(M[2]), "+d"(M[3]), "+d"(M[4]), "+d"(M[5]), "+d"(v[0]), "+d"(v[1]), "+d"(v[2])
-      : "d"(a0), "d"(a1), "d"(a2), "d"(b));
-#else
+  a0 = valid ? a0 : 0.0; a1 = valid ? a1 : 0.0; a2 = valid ? a2 : 0.0;
+  // (ptxas picks the order; an inline-PTX order built for operand reuse measured the same, and clearing
+  // only the high word of the three values measured the same -- the FP64 pipe's register ports are the limit)
   M[0] = fma_(a0, a0, M[0]); M[1] = fma_(a0, a1, M[1]); M[2] = fma_(a0, a2, M[2]);
   M[3] = fma_(a1, a1, M[3]); M[4] = fma_(a1, a2, M[4]); M[5] = fma_(a2, a2, M[5]);
   v[0] = fma_(a0, b, v[0]); v[1] = fma_(a1, b, v[1]); v[2] = fma_(a2, b, v[2]);
-#endif
 }
 __device__ __forceinline__ void acc_row(bool valid, float a0, float a1, float a2, float b, float (&M)[6], float (&v)[3]) {
   a0 = valid ? a0 : 0.f; a1 = valid ? a1 : 0.f; a2 = valid ? a2 : 0.f;  // exact zeros: identical to the packed FFMA2 path
@@ -225,29 +198,20 @@ cudaError_t launch_dlt(const LaunchCtx& ctx, bool f32, int pixfmt, const DltRig<
     if (ctx.debug_stream && pixfmt == PIX_F32)
       return launch_streamed<StreamProbeTile, P32, PIX_F32, 2, 3, 2, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
     if (pixfmt == PIX_F32) {
-      switch (ctx.variant) {  // tuning variants (TRI_VARIANT)
-        case 1: return launch_streamed<DltX2Tile<false>, P32, PIX_F32, 2, 2, 3, 1>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        case 2: return launch_streamed<DltX2Tile<true>, P32, PIX_F32, 2, 2, 3, 0>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        case 3: return launch_streamed<DltX2Tile<true>, P32, PIX_F32, 2, 3, 2, 0>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        case 4: return launch_streamed<DltX2Tile<true>, P32, PIX_F32, 2, 2, 3, -1>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        case 5: return launch_streamed<DltX2Tile<false>, P32, PIX_F32, 2, 2, 3, 0>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        case 6: return launch_streamed<DltX2Tile<false>, P32, PIX_F32, 2, 3, 2, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        default: return launch_streamed<DltX2Tile<true>, P32, PIX_F32, 2, 2, 3, 0>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      switch (ctx.variant) {  // TRI_VARIANT: earlier generations kept for A/B measurements (profiles/r1_variants*.log)
+        case 1: return launch_streamed<DltX2Tile<false>, P32, PIX_F32, 2, 3, 2, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);  // gen 2: TMA + mbarrier ring
+        case 2: return launch_batch_policy<P32, PIX_F32, 2, 3>(ctx, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);                          // gen 1: scalar, one tile per CTA
+        default: return launch_streamed<DltX2Tile<true>, P32, PIX_F32, 2, 2, 3, 0>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);  // gen 3: cp.async per-thread pipeline
       }
     }
-    if (pixfmt == PIX_F64) return launch_streamed<DltX2Tile<false>, P32, PIX_F64, 2, 3, 2, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+    if (pixfmt == PIX_F64) return launch_streamed<DltX2Tile<true>, P32, PIX_F64, 2, 2, 3, 0>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
     return launch_streamed<DltX2Tile<true>, P32, PIX_U16, 2, 2, 3, 0>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
   }
   if (pixfmt == PIX_F32) {
     switch (ctx.variant) {
-      case 1: return launch_streamed<T64, P64, PIX_F32, 1, 2, 4, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case 2: return launch_streamed<T64, P64, PIX_F32, 1, 3, 4, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case 3: return launch_streamed<T64, P64, PIX_F32, 1, 3, 3, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case 4: return launch_streamed<T64, P64, PIX_F32, 1, 3, 4, -1>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case 5: return launch_streamed<T64, P64, PIX_F32, 1, 4, 5, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case 6: return launch_streamed<PolicyTile<P64, 2>, P64, PIX_F32, 2, 3, 2, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case 7: return launch_streamed<PolicyTile<P64, 2>, P64, PIX_F32, 2, 2, 3, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case 8: return launch_streamed<T64, P64, PIX_F32, 1, 4, 3, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 1: return launch_streamed<T64, P64, PIX_F32, 1, 4, 3, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);  // gen 2
+      case 2: return launch_batch_policy<P64, PIX_F32, 1, 3>(ctx, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);                // gen 1
+      case 3: return launch_streamed<T64, P64, PIX_F32, 1, 3, 4, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);  // gen 3, one frame per thread
       default: return launch_streamed<PolicyTile<P64, 2>, P64, PIX_F32, 2, 3, 2, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
     }
   }

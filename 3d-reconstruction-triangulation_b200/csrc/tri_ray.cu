@@ -217,8 +217,6 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
   using T64 = PolicyTile<P64, 1>;
   switch (pixfmt) {
     case PIX_F32:
-      if (ctx.variant == 1) return launch_streamed<PolicyTile<P64, 2>, P64, PIX_F32, 2, 2, 1, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
-      if (ctx.variant == 2) return launch_streamed<T64, P64, PIX_F32, 1, 3, 3, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
       return launch_streamed<T64, P64, PIX_F32, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
     case PIX_F64: return launch_streamed<T64, P64, PIX_F64, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
     default: return launch_streamed<T64, P64, PIX_U16, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
