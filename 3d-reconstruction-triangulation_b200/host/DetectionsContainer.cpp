@@ -12,7 +12,9 @@ DetectionsContainer::DetectionsContainer(const char* path, int offset, int recor
   readFiles(getFiles(path), offset, recordSize, startFrame, endFrame);
 }
 
-DetectionsContainer::DetectionsContainer(int camCount) : n_cameras(camCount), data((size_t)camCount) {}
+DetectionsContainer::DetectionsContainer(int camCount, bool useOffset) : n_cameras(camCount), data((size_t)camCount) {
+  if (useOffset) offsetVector.resize((size_t)camCount);
+}
 
 std::vector<std::string> DetectionsContainer::getFiles(const char* path) {
   // every *.csv below `path`, camera order = sorted path order (DetectionsContainer.cpp:78-92)
@@ -50,12 +52,28 @@ std::vector<int> DetectionsContainer::getDetectionsCount(int frame) const {
   return n;
 }
 
-void DetectionsContainer::addEmptyFrame() {
-  for (Cameras& cam : data) cam.emplace_back();
+void DetectionsContainer::addEmptyFrame() {  // :121-130
+  for (size_t i = 0; i < data.size(); i++) {
+    data[i].emplace_back();
+    if (!offsetVector.empty()) {
+      offsetVector[i].emplace_back();
+      offsetVector[i].back()[0] = 0;  // index 0 = "no detection" maps to itself
+    }
+  }
   n_frames = (int)data[0].size();
 }
 
-void DetectionsContainer::addDetectionToCamera(cv::Point2d det, int cam) { data[cam].back().push_back(det); }
+void DetectionsContainer::addDetectionToCamera(cv::Point2d det, int cam, int originalIndex) {  // :132-139
+  data[cam].back().push_back(det);
+  if (originalIndex > -1 && !offsetVector.empty()) offsetVector[cam].back()[(int)data[cam].back().size()] = originalIndex + 1;
+}
+
+std::vector<int> DetectionsContainer::getOriginalCombination(const std::vector<int>& combination, int frame) const {
+  if (offsetVector.empty()) return combination;
+  std::vector<int> original;
+  for (size_t i = 0; i < combination.size(); i++) original.push_back(offsetVector[i][frame].at(combination[i]));
+  return original;
+}
 
 std::vector<std::vector<cv::Point2d>> DetectionsContainer::getDataForTriangulation() {
   std::vector<std::vector<cv::Point2d>> result((size_t)n_cameras);
