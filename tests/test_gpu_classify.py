@@ -168,3 +168,33 @@ def test_accuracy_against_ground_truth(s09):
     assert sorted(s["label"] for s in stats) == list(range(6))  # every drone is followed by exactly one path
     for s in stats:
         assert s["median"] < 80.0 and s["frames_with_point"] > 0.9 * nf, s
+
+
+@pytest.mark.parametrize("name,mode,flags,gname", [("R04_D2", T.MATRIX, 0, "golden_R04_D2_classify_matrix.npz"),
+                                                   ("S01_D2_A", T.MATRIX, 0, "golden_S01_D2_A_classify_matrix.npz"),
+                                                   ("R04_D2", T.RAY, T.RAY_REFERENCE_LM, "golden_R04_D2_classify_ray.npz")])
+def test_two_drone_datasets_golden(name, mode, flags, gname):
+    cams = T.load_cameras_xml(G + "/%s_cameras.xml" % name)
+    eng = T.Engine(cams, 0)
+    offs, xy, nc, nf = O.load_dets(G + "/%s_dets.npz" % name)
+    g = np.load(G + "/" + gname)
+    fr = g["paths"].shape[1]
+    o, x, _, _ = O.slice_frames(offs, xy, nc, nf, 0, fr)
+    r = eng.classify(mode, 2, o, x, fr, flags)
+    check(r, g, atol=1e-5)
+
+
+@pytest.mark.parametrize("name", ["R04_D2", "S01_D2_A"])
+def test_two_drone_datasets_full_vs_oracle(name):
+    cams = T.load_cameras_xml(G + "/%s_cameras.xml" % name)
+    eng = T.Engine(cams, 0)
+    offs, xy, nc, nf = O.load_dets(G + "/%s_dets.npz" % name)
+    ref = O.classify(ocams(cams), O.MATRIX, 2, offs, xy, nc, nf)
+    r = eng.classify(T.MATRIX, 2, offs, xy, nf)
+    assert np.array_equal(r["assign"], ref["assign"]) and np.array_equal(r["phase"], ref["phase"])
+    np.testing.assert_allclose(r["paths"], ref["paths"], rtol=1e-9, atol=1e-5)
+    # more drones asked for than present: the extra paths stay empty or pick up spurious combinations identically
+    ref3 = O.classify(ocams(cams), O.MATRIX, 3, offs, xy, nc, min(nf, 300))
+    o, x, _, _ = O.slice_frames(offs, xy, nc, nf, 0, min(nf, 300))
+    r3 = eng.classify(T.MATRIX, 3, o, x, min(nf, 300))
+    assert np.array_equal(r3["assign"], ref3["assign"]) and np.array_equal(r3["phase"], ref3["phase"])

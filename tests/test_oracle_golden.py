@@ -145,3 +145,14 @@ def test_batch_api_errors(r02):
     assert O.triangulate_points(cams, pts, O.MATRIX)["status"] == O.ERR_TOO_FEW
     r = O.triangulate_points(cams, pts, O.MATRIX, allow_too_few=True)
     assert r["status"] == O.OK and r["mask"][3] == 1 and np.all(r["xyz"][3] == 0)
+
+
+@pytest.mark.parametrize("name,mode,gname", [("R04_D2", O.MATRIX, "golden_R04_D2_classify_matrix.npz"),
+                                             ("S01_D2_A", O.MATRIX, "golden_S01_D2_A_classify_matrix.npz"),
+                                             ("R04_D2", O.RAY, "golden_R04_D2_classify_ray.npz")])
+def test_classify_two_drone_datasets(name, mode, gname):
+    """Two-drone sequences (real 4-camera rig and simulated 8-camera rig): the C oracle follows the cv2 twin."""
+    cams = O.load_cameras(G + "/%s_cameras.xml" % name)
+    dets = O.load_dets(G + "/%s_dets.npz" % name)
+    r, g = _check_classify(cams, mode, 2, dets, gname, None)
+    assert (r["phase"] > 0).sum() > 0.5 * r["phase"].size
