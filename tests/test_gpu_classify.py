@@ -194,7 +194,7 @@ def test_two_drone_datasets_full_vs_oracle(name):
     assert np.array_equal(r["assign"], ref["assign"]) and np.array_equal(r["phase"], ref["phase"])
     np.testing.assert_allclose(r["paths"], ref["paths"], rtol=1e-9, atol=1e-5)
     # more drones asked for than present: the extra paths stay empty or pick up spurious combinations identically
-    ref3 = O.classify(ocams(cams), O.MATRIX, 3, offs, xy, nc, min(nf, 300))
     o, x, _, _ = O.slice_frames(offs, xy, nc, nf, 0, min(nf, 300))
+    ref3 = O.classify(ocams(cams), O.MATRIX, 3, o, x, nc, min(nf, 300))
     r3 = eng.classify(T.MATRIX, 3, o, x, min(nf, 300))
     assert np.array_equal(r3["assign"], ref3["assign"]) and np.array_equal(r3["phase"], ref3["phase"])
