@@ -355,3 +355,42 @@ def test_host_path_multi_chunk_pipeline(torch):
     dd = eng.triangulate_points_device(T.MATRIX, xy, T.ALLOW_TOO_FEW, want=("xyz_f64", "err"))
     eng.device_status()
     assert np.array_equal(full["xyz_f64"], dd["xyz_f64"].cpu().numpy()) and np.array_equal(full["err"], dd["err"].cpu().numpy())
+
+
+def test_unnormalised_quaternions_and_subpixel_detections(torch):
+    """The reference never normalises ORIENTATION (Triangulator.cpp:15-25, Camera.h:274-287): with |q| != 1 the
+    rays are weighted by |q|^4 and the extrinsic R is not orthonormal.  Sub-pixel (non-integer, non-float32)
+    detections go through the double2 pixel format."""
+    base = S.ring_rig(6)
+    scales = [1.0, 1.3, 0.8, 1.05, 0.95, 1.2]
+    cams = [T.Camera(c.cam_id, c.width, c.height, c.focal, c.position, tuple(s * v for v in c.quat)) for c, s in zip(base, scales)]
+    eng = T.Engine(cams, 0)
+    oc = ocams(cams)
+    n = 6001
+    rng = np.random.default_rng(7)
+    # detections: project points with the reference's own (now non-orthonormal) P, add sub-pixel noise
+    X = np.column_stack([rng.uniform(-1500, 1500, n), rng.uniform(-1500, 1500, n), rng.uniform(300, 2000, n), np.ones(n)])
+    xy = np.zeros((6, n, 2))
+    for c, cam in enumerate(cams):
+        h = X @ cam.P.T
+        xy[c] = h[:, :2] / h[:, 2:3] + rng.normal(0, 0.7, (n, 2))
+    xy[rng.random((6, n)) < 0.25] = -1.0
+    for omode, mode in ((O.MATRIX, T.MATRIX), (O.RAY, T.RAY)):
+        ref = O.triangulate_points(oc, xy, omode, allow_too_few=True, nthreads=8, want_iters=True)
+        out = eng.triangulate_points(mode, xy, T.ALLOW_TOO_FEW, want=("xyz_f64", "mask", "err"))
+        assert np.array_equal(out["mask"], ref["mask"])
+        ok = np.array([bin(int(m)).count("1") >= 2 for m in ref["mask"]])
+        if mode == T.RAY:
+            ok &= (ref["iters"] < 1000)  # where the reference's own LM converged
+            assert ok.mean() > 0.7
+            assert np.abs(out["xyz_f64"][ok] - ref["xyz"][ok]).max() < 1e-2  # the reference stops its LM within ~1e-3 mm of the minimiser
+            np.testing.assert_allclose(out["err"][ok], ref["err"][ok], rtol=1e-5)
+            ex = eng.triangulate_points(T.RAY, xy[:, :1500], T.ALLOW_TOO_FEW | T.RAY_REFERENCE_LM, want=("xyz_f64", "iters"))
+            assert np.array_equal(ex["iters"], ref["iters"][:1500]) and np.array_equal(ex["xyz_f64"], ref["xyz"][:1500])
+        else:
+            assert rel_err(out["xyz_f64"][ok], ref["xyz"][ok]) < 1e-8
+            np.testing.assert_allclose(out["err"][ok], ref["err"][ok], rtol=1e-8, atol=1e-6)
+    # the float2 path rounds the sub-pixel values to float32 first: same masks, points within the FP32 pixel rounding
+    o32 = eng.triangulate_points(T.MATRIX, xy.astype(np.float32), T.ALLOW_TOO_FEW, want=("xyz_f64",))
+    ref = O.triangulate_points(oc, xy, O.MATRIX, allow_too_few=True, nthreads=8)
+    assert np.abs(o32["xyz_f64"] - ref["xyz"]).max() < 0.05

@@ -198,3 +198,16 @@ def test_two_drone_datasets_full_vs_oracle(name):
     ref3 = O.classify(ocams(cams), O.MATRIX, 3, o, x, nc, min(nf, 300))
     r3 = eng.classify(T.MATRIX, 3, o, x, min(nf, 300))
     assert np.array_equal(r3["assign"], ref3["assign"]) and np.array_equal(r3["phase"], ref3["phase"])
+
+
+def test_s09_ray_reference_lm_matches_oracle_short(s09):
+    """--triangulator ray with 6 drones and 8 cameras: thousands of cv::LMSolver emulations per frame, many of
+    them the non-converging 2-view kind -- decisions and points identical to the oracle."""
+    cams, eng, (offs, xy, nc, nf) = s09
+    fr = 6
+    o, x, _, _ = O.slice_frames(offs, xy, nc, nf, 0, fr)
+    ref = O.classify(ocams(cams), O.RAY, 6, o, x, nc, fr)
+    r = eng.classify(T.RAY, 6, o, x, fr, T.RAY_REFERENCE_LM)
+    assert np.array_equal(r["assign"], ref["assign"]) and np.array_equal(r["phase"], ref["phase"])
+    assert np.array_equal(r["paths"], ref["paths"])
+    assert r["stats"]["lm_iters"] > 1e5
