@@ -121,7 +121,7 @@ def cpu_baseline(cams, mode, seconds, make_sample):
             "sample": "first %d frames of the workload, %d valid points, %.2f s, OpenMP over frames" % (n2, valid, dt)}
 
 
-def reference_arm(a):
+def reference_arm(a, emit):
     """--impl reference: the reference's CPU implementation of the path (oracle port) on this box."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -145,20 +145,31 @@ def reference_arm(a):
         tot_t += dt
     val = tot_valid / tot_t
     sample = "%d frames per step (first frames of the workload), OpenMP over frames" % n
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic 8-camera ring rig, 20%% missing detections, DLT (%s); CPU sample %s" % (a.mode, sample)},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 def main():
     a = parse()
+    # stdout carries exactly ONE JSON line: anything a library prints there meanwhile (NCCL's version banner does)
+    # is sent to stderr; the real stdout comes back for the final print.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+
     if a.impl == "reference":
-        return reference_arm(a)
+        return reference_arm(a, emit)
     import torch
     import torch.distributed as dist
     import tri_b200 as T
@@ -353,10 +364,11 @@ def main():
 
     if rank == 0 and world == 1 and not a.no_cpu:
         res["cpu_baseline"] = cpu_baseline(cams, a.mode, a.cpu_seconds, lambda n: xy[:, :n].cpu().numpy())
-    if rank == 0:
-        print(json.dumps(res))
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
+    if rank == 0:
+        emit(res)
 
 
 if __name__ == "__main__":
