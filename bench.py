@@ -90,6 +90,26 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this rank's threads to the CPU cores next to its GPU (NVML's ideal affinity), so that the page-locked
+    host buffers it allocates afterwards live on that NUMA node: with 8 ranks streaming 64 B per frame each,
+    remote-socket buffers halve the per-GPU PCIe rate."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if word >> b & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)[0], len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def oracle_cams(cams):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O  # cpu_baseline / reference arm only
@@ -182,6 +202,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    all_cpus = os.sched_getaffinity(0)
+    numa = bind_to_gpu_numa_node(local)  # the pinned host buffers of the e2e leg are first-touched after this
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -334,7 +356,8 @@ def main():
         res["e2e"] = {"value": valid_total / e_s, "unit": UNIT, "h2d_bytes_per_step": 8 * N_CAMS * F,
                       "d2h_bytes_per_step": 12 * F, "ms_per_step": e_s * 1e3, "steps": esteps,
                       "api": "tri_triangulate_points (host buffers, pinned), per rank",
-                      "pcie_gbs": (8 * N_CAMS * F + 12 * F) / e_s / 1e9, "kernel_launches": eng.kernel_launches - l0}
+                      "pcie_gbs": (8 * N_CAMS * F + 12 * F) / e_s / 1e9, "kernel_launches": eng.kernel_launches - l0,
+                      "cpu_affinity": numa}
         step()
         torch.cuda.synchronize()
         same = bool(torch.equal(h_out[:4000000].to(dev), out["xyz_f32"][:4000000]))
@@ -362,6 +385,7 @@ def main():
                           "ms_per_step": e16 * 1e3, "matches_device_path": bool(torch.equal(h_out[:4000000].to(dev), out["xyz_f32"][:4000000]))}
         del h_xy, h_out, h16
 
+    os.sched_setaffinity(0, all_cpus)  # the CPU baseline uses every host core again
     if rank == 0 and world == 1 and not a.no_cpu:
         res["cpu_baseline"] = cpu_baseline(cams, a.mode, a.cpu_seconds, lambda n: xy[:, :n].cpu().numpy())
     if world > 1:
