@@ -23,7 +23,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "3D points/sec (8-cam DLT, 20% missing)"
+METRIC = "3D points/sec (8-cam DLT, 20% missing)"  # --mode ray swaps in the ray solver, named in config.workload
 UNIT = "points/s"
 N_CAMS = 8
 

@@ -211,3 +211,34 @@ def test_s09_ray_reference_lm_matches_oracle_short(s09):
     assert np.array_equal(r["assign"], ref["assign"]) and np.array_equal(r["phase"], ref["phase"])
     assert np.array_equal(r["paths"], ref["paths"])
     assert r["stats"]["lm_iters"] > 1e5
+
+
+def test_long_sequence_crosses_frame_batches(s09):
+    """More frames than one enumeration batch (8192): the tracking state (last point + tail per path) is
+    carried across batches on the device.  S09_D6 played forwards, backwards, forwards, backwards."""
+    cams, eng, (offs, xy, nc, nf) = s09
+    o = offs.reshape(nc, nf + 1)
+    reps = 4
+    new_offs = np.zeros((nc, reps * nf + 1), np.int64)
+    parts = []
+    base = 0
+    for c in range(nc):
+        cnt = np.diff(o[c])
+        seq_cnt, seq_xy = [], []
+        for r in range(reps):
+            order = range(nf) if r % 2 == 0 else range(nf - 1, -1, -1)
+            for f in order:
+                seq_cnt.append(cnt[f])
+                seq_xy.append(xy[o[c, f]:o[c, f + 1]])
+        new_offs[c, 0] = base
+        new_offs[c, 1:] = base + np.cumsum(seq_cnt)
+        base = new_offs[c, -1]
+        parts.append(np.concatenate(seq_xy, axis=0))
+    big_offs = new_offs.astype(np.int32).reshape(-1)
+    big_xy = np.concatenate(parts, axis=0)
+    n = reps * nf
+    assert n > 8192
+    ref = O.classify(ocams(cams), O.MATRIX, 6, big_offs, big_xy, nc, n)
+    r = eng.classify(T.MATRIX, 6, big_offs, big_xy, n)
+    assert np.array_equal(r["assign"], ref["assign"]) and np.array_equal(r["phase"], ref["phase"])
+    np.testing.assert_allclose(r["paths"], ref["paths"], rtol=1e-9, atol=1e-5)
