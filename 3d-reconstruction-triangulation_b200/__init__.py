@@ -66,7 +66,8 @@ class ClassifyStats(C.Structure):
 EXPORTS = ["tri_version", "tri_last_error", "tri_device_count", "tri_create", "tri_destroy", "tri_engine_device",
            "tri_engine_cameras", "tri_kernel_launches", "tri_triangulate_points", "tri_triangulate_points_multi",
            "tri_triangulate_points_device",
-           "tri_device_status", "tri_triangulate_subsets", "tri_dist_from_ray", "tri_classify", "tri_host_alloc",
+           "tri_device_status", "tri_enable_peer_access", "tri_ipc_export", "tri_ipc_open", "tri_ipc_close",
+           "tri_copy_device", "tri_triangulate_subsets", "tri_dist_from_ray", "tri_classify", "tri_host_alloc",
            "tri_host_free", "tri_device_alloc", "tri_device_free", "tri_copy_to_device", "tri_copy_to_host"]
 
 _lib = None
@@ -95,6 +96,13 @@ def lib():
                                                    C.c_int64, C.POINTER(_BatchOut), C.POINTER(C.c_int64)]
         L.tri_triangulate_points_device.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_void_p, C.c_int, C.c_int64,
                                                     C.c_int64, C.POINTER(_BatchOut), C.c_void_p]
+        L.tri_enable_peer_access.argtypes = [C.c_void_p, C.c_int]
+        L.tri_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+        L.tri_ipc_open.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.tri_ipc_close.argtypes = [C.c_void_p, C.c_void_p]
+        L.tri_copy_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.tri_device_alloc.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint64]
+        L.tri_device_free.argtypes = [C.c_void_p, C.c_void_p]
         L.tri_device_status.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.tri_triangulate_subsets.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int64, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -289,6 +297,41 @@ class Engine:
         _check(lib().tri_triangulate_points_device(self._h, mode, flags | fmt, C.c_void_p(xy.data_ptr()), npc, nf, stride,
                                                    C.byref(bo), C.c_void_p(stream)), mode)
         return out
+
+    def enable_peer_access(self, peer_device):
+        """Let this engine's kernels store straight into `peer_device`'s memory (fused gather over NVLink)."""
+        _check(lib().tri_enable_peer_access(self._h, int(peer_device)))
+
+    # ---- raw device buffers + CUDA IPC (fused gather into another rank's result array) ----
+    def device_alloc(self, nbytes):
+        p = C.c_void_p()
+        _check(lib().tri_device_alloc(self._h, C.byref(p), int(nbytes)))
+        return p.value
+
+    def device_free(self, ptr):
+        _check(lib().tri_device_free(self._h, C.c_void_p(ptr)))
+
+    def ipc_export(self, ptr):
+        buf = C.create_string_buffer(64)
+        _check(lib().tri_ipc_export(self._h, C.c_void_p(ptr), buf))
+        return buf.raw
+
+    def ipc_open(self, handle):
+        p = C.c_void_p()
+        _check(lib().tri_ipc_open(self._h, handle, C.byref(p)))
+        return p.value
+
+    def ipc_close(self, ptr):
+        _check(lib().tri_ipc_close(self._h, C.c_void_p(ptr)))
+
+    def copy_device(self, dst_ptr, src_ptr, nbytes):
+        _check(lib().tri_copy_device(self._h, C.c_void_p(dst_ptr), C.c_void_p(src_ptr), int(nbytes)))
+
+    def triangulate_points_device_raw(self, mode, flags, xy_ptr, npc, nf, stride, xyz_f32_ptr, stream=None):
+        """Device entry point with raw addresses (the output may be a peer / IPC pointer)."""
+        bo = _BatchOut(xyz_f32_ptr, None, None, None, None)
+        _check(lib().tri_triangulate_points_device(self._h, mode, flags, C.c_void_p(xy_ptr), npc, nf, stride, C.byref(bo),
+                                                   C.c_void_p(stream)), mode)
 
     def device_status(self):
         """Synchronise the current stream; raises TriError(ERR_TOO_FEW) if a frame had < 2 views."""

@@ -292,6 +292,52 @@ int tri_triangulate_points_device(tri_engine* e, int mode, unsigned flags, const
   return launch_batch(e, e->ctx((cudaStream_t)stream), mode, flags, fmt, d_xy, n_use, n_frames, cam_stride, out);
 }
 
+int tri_enable_peer_access(tri_engine* e, int peer_device) {
+  if (!e) return fail(TRI_ERR_ARG, "null engine");
+  if (peer_device == e->device) return TRI_OK;
+  DeviceGuard g(e->device);
+  int can = 0;
+  TRI_CUDA(cudaDeviceCanAccessPeer(&can, e->device, peer_device));
+  if (!can) return fail(TRI_ERR_ARG, "no peer access between these GPUs");
+  cudaError_t err = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (err == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); return TRI_OK; }
+  if (err != cudaSuccess) return cuda_fail(err, "cudaDeviceEnablePeerAccess");
+  return TRI_OK;
+}
+
+int tri_ipc_export(tri_engine* e, void* d_ptr, unsigned char handle[64]) {
+  if (!e || !d_ptr || !handle) return fail(TRI_ERR_ARG, "null pointer");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  DeviceGuard g(e->device);
+  cudaIpcMemHandle_t h;
+  TRI_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+  memcpy(handle, &h, 64);
+  return TRI_OK;
+}
+
+int tri_ipc_open(tri_engine* e, const unsigned char handle[64], void** d_ptr) {
+  if (!e || !d_ptr || !handle) return fail(TRI_ERR_ARG, "null pointer");
+  DeviceGuard g(e->device);
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  TRI_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return TRI_OK;
+}
+
+int tri_ipc_close(tri_engine* e, void* d_ptr) {
+  if (!e) return fail(TRI_ERR_ARG, "null engine");
+  DeviceGuard g(e->device);
+  if (d_ptr) TRI_CUDA(cudaIpcCloseMemHandle(d_ptr));
+  return TRI_OK;
+}
+
+int tri_copy_device(tri_engine* e, void* d_dst, const void* d_src, uint64_t bytes) {
+  if (!e) return fail(TRI_ERR_ARG, "null engine");
+  DeviceGuard g(e->device);
+  TRI_CUDA(cudaMemcpy(d_dst, d_src, bytes, cudaMemcpyDefault));
+  return TRI_OK;
+}
+
 int tri_device_status(tri_engine* e, void* stream, int64_t* first_bad_frame) {
   if (!e) return fail(TRI_ERR_ARG, "null engine");
   DeviceGuard g(e->device);

@@ -55,3 +55,27 @@ def first_bad_frame(local_bad: int, begin: int, device, world: int, group=None):
         dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
     v = int(t.item())
     return -1 if v == big else v
+
+
+def open_root_buffer(engine, nbytes: int, rank: int, world: int, root: int = 0, group=None):
+    """`root` allocates `nbytes` of device memory through the engine; every other rank maps it (CUDA IPC, peer
+    access enabled lazily), so kernels on any rank can store their shard of the result directly into the root's
+    array over NVLink -- the gather fused into the producing kernel instead of a collective after it.
+    Returns the raw device address valid in THIS process."""
+    import torch.distributed as dist
+    box = [None]
+    ptr = None
+    if rank == root:
+        ptr = engine.device_alloc(nbytes)
+        box = [engine.ipc_export(ptr)]
+    dist.broadcast_object_list(box, src=root, group=group)
+    if rank != root:
+        ptr = engine.ipc_open(box[0])
+    return ptr
+
+
+def close_root_buffer(engine, ptr, rank: int, root: int = 0):
+    if rank == root:
+        engine.device_free(ptr)
+    else:
+        engine.ipc_close(ptr)

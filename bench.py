@@ -328,6 +328,29 @@ def main():
         tms, _, _ = timed(step_gather, a.steps, 2)
         res["gathered"] = {"ms_per_step": tms / a.steps, "value": valid_total / (tms / a.steps * 1e-3), "unit": UNIT,
                            "collective": "ncclAllGather of float3 points, %.2f GB per rank" % (12 * F / 1e9)}
+        # the same gather FUSED into the kernel: every rank's epilogue stores its points straight into rank 0's
+        # result array over NVLink (CUDA-IPC alias of the root buffer), no collective on the data path
+        try:
+            root_ptr = SH.open_root_buffer(eng, world * F * 12, rank, world)
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            stride = xy.stride(0) // 2
+
+            def step_fused():
+                eng.triangulate_points_device_raw(mode, flags, xy.data_ptr(), N_CAMS, F, stride, root_ptr + rank * F * 12, stream)
+            tms, _, _ = timed(step_fused, a.steps, 2)
+            ok = True
+            if rank == 0:  # the root's array now holds every rank's points, in global frame order
+                chk = torch.empty((world * F, 3), dtype=torch.float32, device=dev)
+                eng.copy_device(chk.data_ptr(), root_ptr, world * F * 12)
+                ok = bool(torch.equal(chk, allp))
+                del chk
+            res["gathered_fused"] = {"ms_per_step": tms / a.steps, "value": valid_total / (tms / a.steps * 1e-3), "unit": UNIT,
+                                     "how": "kernel epilogue stores into rank 0's array over NVLink (CUDA IPC peer memory), gather to root",
+                                     "matches_nccl_gather": ok}
+            barrier()
+            SH.close_root_buffer(eng, root_ptr, rank)
+        except Exception as ex:  # e.g. no peer access between the GPUs of this box
+            res["gathered_fused"] = {"unavailable": str(ex)[:200]}
         del allp
     clk.__exit__()
     res["clocks"] = clk.summary()

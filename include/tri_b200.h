@@ -117,6 +117,18 @@ int tri_triangulate_points_multi(tri_engine* const* engines, int n_engines, int 
 int tri_triangulate_points_device(tri_engine* e, int mode, unsigned flags, const void* d_xy,
                                   int n_point_cams, int64_t n_frames, int64_t cam_stride,
                                   const tri_batch_out* d_out, void* stream);
+/* Fused gather over NVLink: the device entry point writes its points with plain stores, so `d_out->xyz_f32`
+ * may point into ANOTHER GPU's memory (a peer-mapped or CUDA-IPC-opened buffer, e.g. rank 0's result array at
+ * this rank's frame offset): the gather then happens inside the kernel's epilogue, tile by tile, instead of as a
+ * separate collective.  This enables the peer mapping from the engine's GPU to `peer_device` once. */
+int tri_enable_peer_access(tri_engine* e, int peer_device);
+/* CUDA IPC for that: export a buffer obtained from tri_device_alloc (64-byte handle to hand to the other
+ * processes of the box), open such a handle on this engine's GPU (peer access is enabled lazily), close it. */
+int tri_ipc_export(tri_engine* e, void* d_ptr, unsigned char handle[64]);
+int tri_ipc_open(tri_engine* e, const unsigned char handle[64], void** d_ptr);
+int tri_ipc_close(tri_engine* e, void* d_ptr);
+int tri_copy_device(tri_engine* e, void* d_dst, const void* d_src, uint64_t bytes);
+
 /* Synchronises `stream`, returns TRI_ERR_TOO_FEW if a frame was latched since the last call. */
 int tri_device_status(tri_engine* e, void* stream, int64_t* first_bad_frame);
 
