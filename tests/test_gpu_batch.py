@@ -394,3 +394,25 @@ def test_unnormalised_quaternions_and_subpixel_detections(torch):
     o32 = eng.triangulate_points(T.MATRIX, xy.astype(np.float32), T.ALLOW_TOO_FEW, want=("xyz_f64",))
     ref = O.triangulate_points(oc, xy, O.MATRIX, allow_too_few=True, nthreads=8)
     assert np.abs(o32["xyz_f64"] - ref["xyz"]).max() < 0.05
+
+
+def test_fused_gather_into_peer_memory(syn, torch):
+    """The device entry point stores with plain stores, so its output may live on ANOTHER GPU: a kernel on GPU 1
+    writes its shard of the points straight into GPU 0's result array over NVLink (the fused gather of DESIGN 6).
+    Needs two GPUs in one box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cams, eng0, xy, host = syn
+    n = 100_000
+    eng1 = T.Engine(cams, 1)
+    eng1.enable_peer_access(0)
+    whole = eng0.triangulate_points_device(T.MATRIX, xy[:, :2 * n].contiguous(), T.ALLOW_TOO_FEW, want=("xyz_f32",))
+    eng0.device_status()
+    root = torch.zeros((2 * n, 3), dtype=torch.float32, device="cuda:0")
+    eng0.triangulate_points_device(T.MATRIX, xy[:, :n].contiguous(), T.ALLOW_TOO_FEW, out={"xyz_f32": root[:n]})
+    xy1 = xy[:, n:2 * n].contiguous().to("cuda:1")
+    with torch.cuda.device(1):
+        eng1.triangulate_points_device(T.MATRIX, xy1, T.ALLOW_TOO_FEW, out={"xyz_f32": root[n:]})
+        torch.cuda.synchronize()
+    torch.cuda.synchronize()
+    assert torch.equal(root, whole["xyz_f32"])
