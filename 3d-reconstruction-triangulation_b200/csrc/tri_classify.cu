@@ -295,6 +295,30 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
     if (out_phase) out_phase[(size_t)path * p.n_frames + f] = (uint8_t)phase;
   };
 
+  // the same, spread over the lanes of one warp (called by all 32 lanes; a lone thread executes dependent
+  // instructions at ~5 cycles each, so the sequential part of a frame is kept as wide as it can be)
+  auto emit_warp = [&](int lane_, int path, int f, u64 comb, const double* pt, int phase) {
+    const int n = S.n[path];
+    __syncwarp();
+    if (lane_ < 3) {
+      const double v = pt[lane_];
+      if (n >= PATH_TAIL) {
+        for (int k = 0; k < PATH_TAIL - 1; k++) S.tail[path][k][lane_] = S.tail[path][k + 1][lane_];
+        S.tail[path][PATH_TAIL - 1][lane_] = v;
+      } else {
+        S.tail[path][n][lane_] = v;
+      }
+      out_paths[((size_t)path * p.n_frames + f) * 3 + lane_] = v;
+    } else if (lane_ == 3) {
+      if (n < 0x3fffffff) S.n[path] = n + 1;
+      if (out_phase) out_phase[(size_t)path * p.n_frames + f] = (uint8_t)phase;
+    } else if (lane_ >= 8 && lane_ < 8 + C) {
+      const int c = lane_ - 8;
+      if (out_assign) out_assign[((size_t)path * p.n_frames + f) * C + c] = (int8_t)((comb >> (4 * c)) & 15);
+    }
+    __syncwarp();
+  };
+
   for (int f = p.f0; f < p.f1; f++) {
     const int L = leaf_cnt[f - p.f0];
     const long long off = leaf_off[f - p.f0];
@@ -362,8 +386,8 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
         if (!s_active[np]) continue;
         int cand = s_cand[np];
         if (cand < 0) continue;
-        bool clash = false;
-        for (int u = 0; u < n_used; u++) clash = clash || conflicts(lc[cand], s_used[u]);
+        const u64 pick0 = lc[cand];
+        const bool clash = __any_sync(0xffffffffu, lane < n_used && conflicts(pick0, s_used[lane < n_used ? lane : 0]));
         if (clash) {
           const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
           cand = -1;
@@ -377,11 +401,8 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
           }
           if (cand < 0) continue;
         }
-        if (lane == 0) {
-          s_used[n_used] = lc[cand];
-          emit(np, f, lc[cand], lx + 3 * cand, 1);
-          n_phase1++;
-        }
+        if (lane == 0) { s_used[n_used] = lc[cand]; n_phase1++; }
+        emit_warp(lane, np, f, lc[cand], lx + 3 * cand, 1);
         n_used++;
         processed |= 1u << np;
         __syncwarp();
