@@ -1,64 +1,60 @@
-// DFMA issue rate by operand source: constant-bank operand (2 register sources) vs three register pairs.
-// Shapes follow the two candidate DLT accumulations: "direct" M_ij += a_i a_j (registers only) and the
-// monomial form N_ij += x C1_ij + y C2_ij + s C3_ij (one constant-bank operand per DFMA).
+// DFMA issue rate by operand source on sm_100a: register-only forms vs a uniform-register (constant bank)
+// operand, with and without the LDCU that feeds it.  16 independent accumulator chains per thread.
 #include <cstdio>
 #include <cuda_runtime.h>
-struct K { double c[64]; };
+struct K { double c[512]; };
 template <int KIND>
-__global__ void k(const __grid_constant__ K kc, const double* in, double* out, int iters) {
-  double x[6], y[6], acc[9];
-  for (int i = 0; i < 6; i++) { x[i] = in[threadIdx.x + 32 * i]; y[i] = in[threadIdx.x + 32 * (i + 6)]; }
-  for (int i = 0; i < 9; i++) acc[i] = 0;
+__global__ void __launch_bounds__(512) k(const __grid_constant__ K kc, const double* in, double* out, int iters) {
+  double x[4], acc[16];
+  for (int i = 0; i < 4; i++) x[i] = in[threadIdx.x + 32 * i];
+  for (int i = 0; i < 16; i++) acc[i] = in[threadIdx.x + 32 * (4 + i)];
   for (int it = 0; it < iters; it++) {
+    const int base = (it * 32) & 511;  // uniform, loop-dependent: the constants cannot be hoisted
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-      if (KIND == 0) {  // monomial: 27 DFMA, each with a constant operand
+    for (int u = 0; u < 4; u++) {
 #pragma unroll
-        for (int i = 0; i < 9; i++) {
-          acc[i] = fma(x[0], kc.c[(u * 27 + i) & 63], acc[i]);
-          acc[i] = fma(x[1], kc.c[(u * 27 + 9 + i) & 63], acc[i]);
-          acc[i] = fma(x[2], kc.c[(u * 27 + 18 + i) & 63], acc[i]);
-        }
-      }
-      if (KIND == 1) {  // direct: rows from constants (8) + 18 register-only
-#pragma unroll
-        for (int r = 0; r < 2; r++) {
-          const double a0 = fma(x[r], kc.c[(u * 8 + 0) & 63], kc.c[(u * 8 + 1) & 63]);
-          const double a1 = fma(x[r], kc.c[(u * 8 + 2) & 63], kc.c[(u * 8 + 3) & 63]);
-          const double a2 = fma(x[r], kc.c[(u * 8 + 4) & 63], kc.c[(u * 8 + 5) & 63]);
-          const double b = fma(x[r], kc.c[(u * 8 + 6) & 63], kc.c[(u * 8 + 7) & 63]);
-          acc[0] = fma(a0, a0, acc[0]); acc[1] = fma(a0, a1, acc[1]); acc[2] = fma(a0, a2, acc[2]);
-          acc[3] = fma(a1, a1, acc[3]); acc[4] = fma(a1, a2, acc[4]); acc[5] = fma(a2, a2, acc[5]);
-          acc[6] = fma(a0, b, acc[6]); acc[7] = fma(a1, b, acc[7]); acc[8] = fma(a2, b, acc[8]);
-        }
+      for (int i = 0; i < 16; i++) {
+        if (KIND == 0) acc[i] = fma(x[u], x[(u + 1) & 3], acc[i]);        // 3 distinct register pairs, two of them shared by 16 in a row
+        if (KIND == 1) acc[i] = fma(x[u], acc[(i + 1) & 15], acc[i]);     // 3 distinct register pairs, one shared
+        if (KIND == 2) acc[i] = fma(x[u], kc.c[i & 7], acc[i]);           // UR operand, 8 loop-invariant constants (no LDCU in the loop)
+        if (KIND == 3) acc[i] = fma(x[u], kc.c[base + ((u * 16 + i) >> 1)], acc[i]);  // UR operand, one LDCU.64 per two DFMAs
+        if (KIND == 4) acc[i] = fma(x[u], kc.c[base + ((u * 16 + i) >> 2)], acc[i]);  // UR operand, one LDCU.64 per four DFMAs
+        if (KIND == 5) acc[i] = fma(acc[i], acc[i], x[u]);                // 2 distinct
       }
     }
   }
   double s = 0;
-  for (int i = 0; i < 9; i++) s += acc[i];
+  for (int i = 0; i < 16; i++) s += acc[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 int main() {
-  double *in, *out; cudaMalloc(&in, 4096 * 8); cudaMalloc(&out, 148 * 8 * 1024 * 8);
-  double h[4096]; for (int i = 0; i < 4096; i++) h[i] = 1.0 + 1e-9 * (i % 977);
+  double *in, *out; cudaMalloc(&in, 8192 * 8); cudaMalloc(&out, 148 * 8 * 1024 * 8);
+  double h[8192]; for (int i = 0; i < 8192; i++) h[i] = 1.0 + 1e-9 * (i % 977);
   cudaMemcpy(in, h, sizeof(h), cudaMemcpyHostToDevice);
-  K kc; for (int i = 0; i < 64; i++) kc.c[i] = 1e-3 * (i + 1);
+  K kc; for (int i = 0; i < 512; i++) kc.c[i] = 1e-3 * (i + 1);
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
-  const char* names[2] = {"monomial (const operand)", "direct (registers)"};
-  const int per_iter[2] = {8 * 27, 8 * 26};
-  for (int warps = 4; warps <= 32; warps *= 2)
-    for (int kind = 0; kind < 2; kind++) {
-      const int iters = 2000, grid = p.multiProcessorCount, block = warps * 32;
+  const char* names[6] = {"3 reg pairs, 2 shared", "3 reg pairs, 1 shared", "UR operand, invariant", "UR operand, LDCU per 2", "UR operand, LDCU per 4", "2 reg pairs"};
+  for (int warps = 8; warps <= 16; warps *= 2)
+    for (int kind = 0; kind < 6; kind++) {
+      const int iters = 4000, grid = p.multiProcessorCount, block = warps * 32;
       cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
       for (int rep = 0; rep < 2; rep++) {
         cudaEventRecord(e0);
-        if (kind == 0) k<0><<<grid, block>>>(kc, in, out, iters); else k<1><<<grid, block>>>(kc, in, out, iters);
+        switch (kind) {
+          case 0: k<0><<<grid, block>>>(kc, in, out, iters); break;
+          case 1: k<1><<<grid, block>>>(kc, in, out, iters); break;
+          case 2: k<2><<<grid, block>>>(kc, in, out, iters); break;
+          case 3: k<3><<<grid, block>>>(kc, in, out, iters); break;
+          case 4: k<4><<<grid, block>>>(kc, in, out, iters); break;
+          default: k<5><<<grid, block>>>(kc, in, out, iters); break;
+        }
         cudaEventRecord(e1); cudaEventSynchronize(e1);
       }
       float ms; cudaEventElapsedTime(&ms, e0, e1);
-      double inst = (double)grid * block / 32 * iters * per_iter[kind];
-      printf("warps/SM=%2d %-26s %.3f ms  %.2f DFMA warp-inst/clk/SM  (%.1f clk per 8-view frame per SM-warp)\n", warps, names[kind], ms,
-             inst / (ms * 1e-3) / (p.clockRate * 1e3) / p.multiProcessorCount, ms * 1e-3 * p.clockRate * 1e3 / iters / (block / 32));
+      cudaError_t err = cudaGetLastError();
+      double inst = (double)grid * block / 32 * iters * 64;
+      printf("warps/SM=%2d %-26s %.3f ms  %.2f DFMA warp-inst/clk/SM %s\n", warps, names[kind], ms,
+             inst / (ms * 1e-3) / (p.clockRate * 1e3) / p.multiProcessorCount, err == cudaSuccess ? "" : cudaGetErrorString(err));
     }
   return 0;
 }
