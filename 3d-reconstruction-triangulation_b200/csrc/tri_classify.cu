@@ -257,7 +257,8 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
             const long long* __restrict__ leaf_off, const int* __restrict__ leaf_cnt, LinkState* state,
             double* __restrict__ out_paths, int8_t* __restrict__ out_assign, uint8_t* __restrict__ out_phase, ClsCounters* ctr) {
   __shared__ LinkState S;
-  __shared__ unsigned s_gate[TRI_MAX_DRONES][CLS_MAX_CAMS];
+  __shared__ unsigned s_gate[CLS_MAX_CAMS][16];  // [camera][choice] -> bit np: path np may use that choice (choice 0 = "none")
+  __shared__ unsigned s_active_mask;
   __shared__ double s_dir[CLS_MAX_CAMS * TRI_MAX_DETS][3];
   __shared__ bool s_ndet[CLS_MAX_CAMS * TRI_MAX_DETS];
   __shared__ int s_cand[TRI_MAX_DRONES];
@@ -340,40 +341,63 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
       s_ndet[i] = d < b - a;
       if (d < b - a) ref::make_dir(ray, c, dets[2 * (size_t)(a + d)], dets[2 * (size_t)(a + d) + 1], s_dir[i]);
     }
-    for (int i = tid; i < D * C; i += LINK_THREADS) s_gate[i / C][i % C] = 1u;  // choice 0 ("none") is always available
+    for (int i = tid; i < C * 16; i += LINK_THREADS) s_gate[i / 16][i % 16] = (i % 16) == 0 ? 0xffffffffu : 0u;  // choice 0 ("none") is always available
+    if (tid < D) {
+      const int n = S.n[tid];
+      const double* last = S.tail[tid][min(max(n, 1), PATH_TAIL) - 1];
+      s_active[tid] = n != 0 && !(last[0] == 0 && last[1] == 0 && last[2] == 0);  // :121-123
+      s_cand[tid] = 0x7fffffff;
+    }
     __syncthreads();
+    if (tid == 0) {
+      unsigned m = 0;
+      for (int np = 0; np < D; np++) m |= (s_active[np] ? 1u : 0u) << np;
+      s_active_mask = m;
+    }
     // (ii) the MAX_STEP ray gate of every (path, detection), :228-236 -- a path's last point is last frame's
     for (int i = tid; i < D * C * TRI_MAX_DETS; i += LINK_THREADS) {
       const int np = i / (C * TRI_MAX_DETS), k = i % (C * TRI_MAX_DETS), c = k / TRI_MAX_DETS, d = k % TRI_MAX_DETS;
       const int n = S.n[np];
       if (n == 0 || !s_ndet[k]) continue;
       const double* last = S.tail[np][min(n, PATH_TAIL) - 1];
-      if (ref::dist_to_ray(ray.pos[c], s_dir[k], last[0], last[1], last[2]) < MAX_STEP) atomicOr(&s_gate[np][c], 1u << (d + 1));
+      if (ref::dist_to_ray(ray.pos[c], s_dir[k], last[0], last[1], last[2]) < MAX_STEP) atomicOr(&s_gate[c][d + 1], 1u << np);
     }
     __syncthreads();
-    // (iii) one warp per path.  The leaves are stored in priority order, so "the first element the
-    // reference's priority_queue pops that passes :241-246" is the FIRST admissible leaf: walk the list 32
-    // at a time and stop at the first hit.  Combinations used by earlier paths are ignored here ...
+    // (iii) The leaves are stored in priority order, so "the first element the reference's priority_queue pops
+    // that passes :241-246" is, per path, the admissible leaf of SMALLEST index.  All threads scan the list 256
+    // leaves at a time; one AND over the cameras of the transposed gate words gives the set of paths a leaf is
+    // gated for, the distance test runs only for those, and the winners are taken with atomicMin.  The scan
+    // stops as soon as every tracked path has a candidate.  Combinations used by earlier paths are ignored here ...
     const int lane = tid & 31, warp = tid >> 5;
     auto gate_ok = [&](int np, u64 comb) {
       bool ok = true;
-      for (int c = 0; c < C; c++) ok = ok && ((s_gate[np][c] >> ((comb >> (4 * c)) & 15)) & 1u);
+      for (int c = 0; c < C; c++) ok = ok && ((s_gate[c][(comb >> (4 * c)) & 15] >> np) & 1u);
       return ok;
     };
-    for (int np = warp; np < D; np += LINK_THREADS / 32) {
-      const int n = S.n[np];
-      const double* last = S.tail[np][min(max(n, 1), PATH_TAIL) - 1];
-      const bool active = n != 0 && !(last[0] == 0 && last[1] == 0 && last[2] == 0);  // :121-123
-      int found = -1;
-      for (int base = 0; active && base < L && found < 0; base += 32) {
-        const int i = base + lane;
-        bool ok = i < L && gate_ok(np, lc[i]) && le[i] < p.error_;
-        if (ok) ok = dist3(lx + 3 * i, last) < MAX_STEP;  // cv::norm(c.point - pos) < MAX_STEP, :244
-        const unsigned hit = __ballot_sync(0xffffffffu, ok);
-        if (hit) found = base + __ffs(hit) - 1;
+    {
+      const unsigned active_mask = s_active_mask;
+      for (int base = 0; active_mask && base < L; base += LINK_THREADS) {
+        const int i = base + tid;
+        if (i < L) {
+          const u64 comb = lc[i];
+          unsigned ap = active_mask;
+          for (int c = 0; c < C; c++) ap &= s_gate[c][(comb >> (4 * c)) & 15];
+          if (ap && le[i] < p.error_) {
+            while (ap) {
+              const int np = __ffs(ap) - 1;
+              ap &= ap - 1;
+              const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
+              if (dist3(lx + 3 * i, last) < MAX_STEP) atomicMin(&s_cand[np], i);  // cv::norm(c.point - pos) < MAX_STEP, :244
+            }
+          }
+        }
+        __syncthreads();
+        bool all_found = true;
+        for (int np = 0; np < D; np++) all_found = all_found && (!(active_mask >> np & 1u) || s_cand[np] != 0x7fffffff);
+        if (__syncthreads_and(all_found)) break;  // (second barrier: everyone has read s_cand before the next round writes it)
       }
-      if (lane == 0) { s_cand[np] = found; s_active[np] = active; }
     }
+    if (tid < D && s_cand[tid] == 0x7fffffff) s_cand[tid] = -1;
     __syncthreads();
     // (iv) ... and resolved here in path order by warp 0: a candidate that does not collide with an earlier
     // path's pick is also the first of the filtered list; otherwise walk the list again with the filter.

@@ -1,0 +1,11 @@
+import os, sys, time
+ROOT = "/root/repo"
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import oracle_py as O
+import tri_b200 as T
+G = os.path.join(ROOT, "tests", "golden")
+cams = T.load_cameras_xml(G + "/S09_D6_cameras.xml")
+offs, xy, nc, nf = O.load_dets(G + "/S09_D6_dets.npz")
+eng = T.Engine(cams, 0)
+eng.classify(T.MATRIX, 6, offs, xy, nf, 0)
+t0 = time.perf_counter(); eng.classify(T.MATRIX, 6, offs, xy, nf, 0); print("gpu_s", time.perf_counter() - t0)
