@@ -34,7 +34,7 @@ constexpr int CLS_MAX_CAMS = 16;   // 4 bits per camera in a 64-bit combination
 constexpr int CLS_THREADS = 128;
 constexpr int LINK_THREADS = 256;
 constexpr int LINK_MAX_FINAL = 64;
-constexpr int LINK_STAGE_LEAVES = 4096;  // leaves of one frame staged in (dynamic) shared memory: 40 B each
+constexpr int LINK_STAGE_LEAVES = 2048;  // leaves of one frame staged in (dynamic) shared memory, 40 B each; two buffers
 typedef unsigned long long u64;
 
 // DroneClassifier.h:11-17
@@ -246,6 +246,9 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
 }
 
 // ---- (B) linking -------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ double dist3(const double* a, const double* b) {  // cv::norm(a - b)
   const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
   return sqrt(x * x + y * y + z * z);
@@ -270,18 +273,17 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
   __shared__ int s_n_fin, s_n_used;
   __shared__ int s_first[2][LINK_THREADS / 32];
   __shared__ unsigned s_processed;
-  // this frame's candidates (combination, error, point), staged once: the sequential part of the frame then
-  // never waits on global memory (a lone CTA cannot hide a ~1 us round trip behind anything)
+  // This frame's candidates (combination, error, point) are staged in shared memory, and the NEXT frame's are
+  // already on their way (cp.async into the other buffer) while this one is processed: a lone CTA cannot hide a
+  // ~1 us global round trip behind anything else.
   extern __shared__ __align__(16) unsigned char link_dyn[];
-  u64* s_comb = reinterpret_cast<u64*>(link_dyn);
-  double* s_err = reinterpret_cast<double*>(link_dyn + sizeof(u64) * LINK_STAGE_LEAVES);
-  double* s_xyz = reinterpret_cast<double*>(link_dyn + (sizeof(u64) + sizeof(double)) * LINK_STAGE_LEAVES);
+  constexpr int LINK_BUF_BYTES = (int)((sizeof(u64) + 4 * sizeof(double)) * LINK_STAGE_LEAVES);
   const int tid = threadIdx.x, C = p.n_cams, D = p.n_drones;
   for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += LINK_THREADS) ((int*)&S)[i] = ((const int*)state)[i];
   u64 n_phase1 = 0, n_phase2 = 0;  // thread 0 only
   __syncthreads();
 
-  auto emit = [&](int path, int f, u64 comb, const double* pt, int phase) {  // thread 0: push a point to a path
+  auto emit = [&](int path, int f, u64 comb, const double* pt, int phase) {  // one thread: push a point to a path
     const int n = S.n[path];
     if (n >= PATH_TAIL) {
       for (int k = 0; k < PATH_TAIL - 1; k++) for (int j = 0; j < 3; j++) S.tail[path][k][j] = S.tail[path][k + 1][j];
@@ -296,50 +298,60 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
     if (out_phase) out_phase[(size_t)path * p.n_frames + f] = (uint8_t)phase;
   };
 
-  // the same, spread over the lanes of one warp (called by all 32 lanes; a lone thread executes dependent
-  // instructions at ~5 cycles each, so the sequential part of a frame is kept as wide as it can be)
-  auto emit_warp = [&](int lane_, int path, int f, u64 comb, const double* pt, int phase) {
-    const int n = S.n[path];
-    __syncwarp();
-    if (lane_ < 3) {
-      const double v = pt[lane_];
-      if (n >= PATH_TAIL) {
-        for (int k = 0; k < PATH_TAIL - 1; k++) S.tail[path][k][lane_] = S.tail[path][k + 1][lane_];
-        S.tail[path][PATH_TAIL - 1][lane_] = v;
-      } else {
-        S.tail[path][n][lane_] = v;
-      }
-      out_paths[((size_t)path * p.n_frames + f) * 3 + lane_] = v;
-    } else if (lane_ == 3) {
-      if (n < 0x3fffffff) S.n[path] = n + 1;
-      if (out_phase) out_phase[(size_t)path * p.n_frames + f] = (uint8_t)phase;
-    } else if (lane_ >= 8 && lane_ < 8 + C) {
-      const int c = lane_ - 8;
-      if (out_assign) out_assign[((size_t)path * p.n_frames + f) * C + c] = (int8_t)((comb >> (4 * c)) & 15);
+  auto stage = [&](int buf, int L, long long off) {  // cp.async of one frame's candidate list (8-byte pieces: off is arbitrary)
+    unsigned char* base = link_dyn + (size_t)buf * LINK_BUF_BYTES;
+    u64* d_comb = reinterpret_cast<u64*>(base);
+    double* d_err = reinterpret_cast<double*>(base + sizeof(u64) * LINK_STAGE_LEAVES);
+    double* d_xyz = reinterpret_cast<double*>(base + (sizeof(u64) + sizeof(double)) * LINK_STAGE_LEAVES);
+    if (L <= LINK_STAGE_LEAVES) {
+      for (int i = tid; i < L; i += LINK_THREADS) { cp_async8(d_comb + i, leaf_comb + off + i); cp_async8(d_err + i, leaf_err + off + i); }
+      for (int i = tid; i < 3 * L; i += LINK_THREADS) cp_async8(d_xyz + i, leaf_xyz + 3 * off + i);
     }
-    __syncwarp();
+    asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  // software pipeline over the frames: candidate-list extents two frames ahead, the list itself and the
+  // detections one frame ahead
+  const int nf = p.f1 - p.f0;
+  int L_next = nf > 0 ? leaf_cnt[0] : 0, L_next2 = nf > 1 ? leaf_cnt[1] : 0;
+  long long off_next = nf > 0 ? leaf_off[0] : 0, off_next2 = nf > 1 ? leaf_off[1] : 0;
+  const int det_c = tid / TRI_MAX_DETS, det_d = tid % TRI_MAX_DETS;  // thread tid < C * TRI_MAX_DETS owns detection slot (c, d)
+  const bool det_thread = tid < C * TRI_MAX_DETS;
+  bool det_has_next = false;
+  double det_x_next = 0, det_y_next = 0;
+  auto fetch_det = [&](int f, bool& has, double& x, double& y) {
+    has = false;
+    if (det_thread && f < p.f1) {
+      const int a = offs[(size_t)det_c * (p.n_frames + 1) + f], b = offs[(size_t)det_c * (p.n_frames + 1) + f + 1];
+      has = det_d < b - a;
+      if (has) { x = dets[2 * (size_t)(a + det_d)]; y = dets[2 * (size_t)(a + det_d) + 1]; }
+    }
+  };
+  fetch_det(p.f0, det_has_next, det_x_next, det_y_next);
+  stage(0, L_next, off_next);
 
   for (int f = p.f0; f < p.f1; f++) {
-    const int L = leaf_cnt[f - p.f0];
-    const long long off = leaf_off[f - p.f0];
+    const int k = f - p.f0;
+    const int L = L_next;
+    const long long off = off_next;
+    L_next = L_next2; off_next = off_next2;
+    const bool det_has = det_has_next;
+    const double det_x = det_x_next, det_y = det_y_next;
     const bool staged = L <= LINK_STAGE_LEAVES;
-    const u64* lc = staged ? s_comb : leaf_comb + off;
-    const double* le = staged ? s_err : leaf_err + off;
-    const double* lx = staged ? s_xyz : leaf_xyz + 3 * off;
-    if (staged) {
-      for (int i = tid; i < L; i += LINK_THREADS) { s_comb[i] = leaf_comb[off + i]; s_err[i] = leaf_err[off + i]; }
-      for (int i = tid; i < 3 * L; i += LINK_THREADS) s_xyz[i] = leaf_xyz[3 * off + i];
-    }
-    __syncthreads();
+    const unsigned char* cur = link_dyn + (size_t)(k & 1) * LINK_BUF_BYTES;
+    const u64* lc = staged ? reinterpret_cast<const u64*>(cur) : leaf_comb + off;
+    const double* le = staged ? reinterpret_cast<const double*>(cur + sizeof(u64) * LINK_STAGE_LEAVES) : leaf_err + off;
+    const double* lx = staged ? reinterpret_cast<const double*>(cur + (sizeof(u64) + sizeof(double)) * LINK_STAGE_LEAVES) : leaf_xyz + 3 * off;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // this frame's list has landed; everyone is done with the previous frame (and its buffer)
+    if (k + 1 < nf) stage((k + 1) & 1, L_next, off_next); else asm volatile("cp.async.commit_group;" ::: "memory");
+    if (k + 2 < nf) { L_next2 = leaf_cnt[k + 2]; off_next2 = leaf_off[k + 2]; }
+    fetch_det(f + 1, det_has_next, det_x_next, det_y_next);
 
     // ---- phase 1: tracking (:119-135) ----
     // (i) the pixel rays of this frame's detections, once (they do not depend on the path)
-    for (int i = tid; i < C * TRI_MAX_DETS; i += LINK_THREADS) {
-      const int c = i / TRI_MAX_DETS, d = i % TRI_MAX_DETS;
-      const int a = offs[(size_t)c * (p.n_frames + 1) + f], b = offs[(size_t)c * (p.n_frames + 1) + f + 1];
-      s_ndet[i] = d < b - a;
-      if (d < b - a) ref::make_dir(ray, c, dets[2 * (size_t)(a + d)], dets[2 * (size_t)(a + d) + 1], s_dir[i]);
+    if (det_thread) {
+      s_ndet[tid] = det_has;
+      if (det_has) ref::make_dir(ray, det_c, det_x, det_y, s_dir[tid]);
     }
     for (int i = tid; i < C * 16; i += LINK_THREADS) s_gate[i / 16][i % 16] = (i % 16) == 0 ? 0xffffffffu : 0u;  // choice 0 ("none") is always available
     if (tid < D) {
@@ -404,34 +416,38 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
     // Phase 2 (pickBestCombinations, :200-217) follows on the same warp: ONE pass in priority order keeping
     // every leaf that collides with nothing kept so far -- literally the reference's pop loop.
     if (warp == 0) {
-      int n_used = 0;
-      unsigned processed = 0;
+      // lane np owns path np's speculative pick; the picks are confirmed in path order with shuffles (the
+      // common case touches no memory), and all confirmed paths are written at once, one lane per path
+      int cand = (lane < D && s_active[lane]) ? s_cand[lane] : -1;
+      u64 comb = cand >= 0 ? lc[cand] : 0ull;
+      bool clashed = false;  // my pick collides with a confirmed earlier one
+      unsigned accepted = 0;
       for (int np = 0; np < D; np++) {
-        if (!s_active[np]) continue;
-        int cand = s_cand[np];
-        if (cand < 0) continue;
-        const u64 pick0 = lc[cand];
-        const bool clash = __any_sync(0xffffffffu, lane < n_used && conflicts(pick0, s_used[lane < n_used ? lane : 0]));
-        if (clash) {
+        int c_np = __shfl_sync(0xffffffffu, cand, np);
+        if (c_np < 0) continue;
+        if (__shfl_sync(0xffffffffu, (int)clashed, np)) {  // rare (404 of 14 738 picks on S09_D6): walk the list again with the used filter
+          const int n_used = __popc(accepted);
           const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
-          cand = -1;
-          for (int base = 0; base < L && cand < 0; base += 32) {
+          c_np = -1;
+          for (int base = 0; base < L && c_np < 0; base += 32) {
             const int i = base + lane;
             bool ok = i < L && gate_ok(np, lc[i]) && le[i] < p.error_;
             for (int u = 0; u < n_used && ok; u++) ok = !conflicts(lc[i], s_used[u]);
             if (ok) ok = dist3(lx + 3 * i, last) < MAX_STEP;
             const unsigned hit = __ballot_sync(0xffffffffu, ok);
-            if (hit) cand = base + __ffs(hit) - 1;
+            if (hit) c_np = base + __ffs(hit) - 1;
           }
-          if (cand < 0) continue;
+          if (lane == np) { cand = c_np; comb = c_np >= 0 ? lc[c_np] : 0ull; }
+          if (c_np < 0) continue;
         }
-        if (lane == 0) { s_used[n_used] = lc[cand]; n_phase1++; }
-        emit_warp(lane, np, f, lc[cand], lx + 3 * cand, 1);
-        n_used++;
-        processed |= 1u << np;
+        const u64 pick = __shfl_sync(0xffffffffu, comb, np);
+        if (lane == np) s_used[__popc(accepted)] = pick;
+        accepted |= 1u << np;
+        if (lane > np && cand >= 0) clashed = clashed || conflicts(comb, pick);
         __syncwarp();
       }
-      if (lane == 0) { s_processed = processed; s_n_used = n_used; s_n_fin = 0; }
+      if (accepted >> lane & 1u) emit(lane, f, comb, lx + 3 * cand, 1);
+      if (lane == 0) { n_phase1 += __popc(accepted); s_processed = accepted; s_n_used = __popc(accepted); s_n_fin = 0; }
     }
     __syncthreads();
     if (__popc(s_processed) == D) continue;  // :137
@@ -624,7 +640,7 @@ extern "C" int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drone
   };
   int st = alloc_work();
   if (st != TRI_OK) return st;
-  constexpr int LINK_DYN_BYTES = (int)((sizeof(u64) + 4 * sizeof(double)) * LINK_STAGE_LEAVES);
+  constexpr int LINK_DYN_BYTES = 2 * (int)((sizeof(u64) + 4 * sizeof(double)) * LINK_STAGE_LEAVES);
   TRI_CUDA(cudaFuncSetAttribute(link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LINK_DYN_BYTES));
 
   ClsCounters h{};
