@@ -261,7 +261,7 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
             double* __restrict__ out_paths, int8_t* __restrict__ out_assign, uint8_t* __restrict__ out_phase, ClsCounters* ctr) {
   __shared__ LinkState S;
   __shared__ unsigned s_gate[CLS_MAX_CAMS][16];  // [camera][choice] -> bit np: path np may use that choice (choice 0 = "none")
-  __shared__ unsigned s_active_mask;
+  __shared__ unsigned s_active_mask, s_found_mask;
   __shared__ double s_dir[CLS_MAX_CAMS * TRI_MAX_DETS][3];
   __shared__ bool s_ndet[CLS_MAX_CAMS * TRI_MAX_DETS];
   __shared__ int s_cand[TRI_MAX_DRONES];
@@ -365,6 +365,7 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
       unsigned m = 0;
       for (int np = 0; np < D; np++) m |= (s_active[np] ? 1u : 0u) << np;
       s_active_mask = m;
+      s_found_mask = 0;
     }
     // (ii) the MAX_STEP ray gate of every (path, detection), :228-236 -- a path's last point is last frame's
     for (int i = tid; i < D * C * TRI_MAX_DETS; i += LINK_THREADS) {
@@ -399,14 +400,15 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
               const int np = __ffs(ap) - 1;
               ap &= ap - 1;
               const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
-              if (dist3(lx + 3 * i, last) < MAX_STEP) atomicMin(&s_cand[np], i);  // cv::norm(c.point - pos) < MAX_STEP, :244
+              if (dist3(lx + 3 * i, last) < MAX_STEP) {  // cv::norm(c.point - pos) < MAX_STEP, :244
+                atomicMin(&s_cand[np], i);
+                atomicOr(&s_found_mask, 1u << np);
+              }
             }
           }
         }
         __syncthreads();
-        bool all_found = true;
-        for (int np = 0; np < D; np++) all_found = all_found && (!(active_mask >> np & 1u) || s_cand[np] != 0x7fffffff);
-        if (__syncthreads_and(all_found)) break;  // (second barrier: everyone has read s_cand before the next round writes it)
+        if (__syncthreads_and(s_found_mask == active_mask)) break;  // (second barrier: everyone has read the mask before the next round writes it)
       }
     }
     if (tid < D && s_cand[tid] == 0x7fffffff) s_cand[tid] = -1;

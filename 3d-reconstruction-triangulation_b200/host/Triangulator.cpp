@@ -74,17 +74,36 @@ std::vector<cv::Point3d> Triangulator::triangulatePoints(std::vector<std::vector
     if (points[i - 1].size() != points[i].size()) throw std::runtime_error("Every camera should have the same number of points");
   const int64_t n_frames = points.empty() ? 0 : (int64_t)points[0].size();
   const int n_rows = (int)points.size();
-  // pack [cam][frame] pixel pairs; float2 when every value is exactly representable, else double2
-  bool exact32 = true;
-  for (const auto& row : points)
-    for (const cv::Point2d& p : row)
+  // pack [cam][frame] pixel pairs in the narrowest format that holds every value exactly: ushort2 (integer pixels
+  // below 65535 -- what DetectionsContainer::readFiles produces, DetectionsContainer.cpp:36 -- with 0xFFFF,0xFFFF
+  // for a pair the reference would skip, MatrixTriangulator.cpp:86), float2, else double2
+  bool exact16 = true, exact32 = true;
+  for (const auto& row : points) {
+    for (const cv::Point2d& p : row) {
       if ((double)(float)p.x != p.x || (double)(float)p.y != p.y) { exact32 = false; break; }
+      if (exact16 && !(p.x == -1 || p.y == -1) &&
+          !(p.x >= 0 && p.x < 65535 && p.y >= 0 && p.y < 65535 && p.x == (double)(uint16_t)p.x && p.y == (double)(uint16_t)p.y))
+        exact16 = false;
+    }
+    if (!exact32) break;
+  }
+  exact16 = exact16 && exact32;
   std::vector<double> xyz(3 * (size_t)n_frames);
   tri_batch_out out{};
   out.xyz_f64 = xyz.data();
   int64_t bad = -1;
   int st;
-  if (exact32) {
+  if (exact16) {
+    std::vector<uint16_t> xy(2 * (size_t)n_rows * n_frames);
+    for (int c = 0; c < n_rows; c++)
+      for (int64_t f = 0; f < n_frames; f++) {
+        const cv::Point2d& p = points[c][f];
+        const bool missing = p.x == -1 || p.y == -1;
+        xy[2 * ((size_t)c * n_frames + f)] = missing ? (uint16_t)0xFFFF : (uint16_t)p.x;
+        xy[2 * ((size_t)c * n_frames + f) + 1] = missing ? (uint16_t)0xFFFF : (uint16_t)p.y;
+      }
+    st = tri_triangulate_points(engine_, mode_, flags_ | TRI_PIX_U16, xy.data(), n_rows, n_frames, n_frames, &out, &bad);
+  } else if (exact32) {
     std::vector<float> xy(2 * (size_t)n_rows * n_frames);
     for (int c = 0; c < n_rows; c++)
       for (int64_t f = 0; f < n_frames; f++) {

@@ -23,6 +23,13 @@ int main(int argc, const char** argv) {
   std::vector<std::vector<cv::Point2d>> pts = box.getDataForTriangulation();
   dump("matrix", matrix->triangulatePoints(pts));
   dump("ray", ray->triangulatePoints(pts));
+  // the same detections shifted off the integer grid: the adapter then packs float2 (+0.25) / double2 (+1e-7)
+  // instead of ushort2
+  for (double shift : {0.25, 1e-7}) {
+    std::vector<std::vector<cv::Point2d>> q = pts;
+    for (auto& row : q) for (cv::Point2d& p : row) { p.x += shift; p.y += shift; }
+    dump(shift == 0.25 ? "matrix_f32" : "matrix_f64", matrix->triangulatePoints(q));
+  }
 
   // triangulatePoint on a camera subset, the way fillCombinationQueue builds it
   std::vector<Triangulator::CamPointPair> images;

@@ -154,6 +154,12 @@ def test_cpp_triangulator_adapters(host_bins, tmp_path):
     cams = O.load_cameras(G + "/R02_D1_cameras.xml")
     offs, xy, _, nfull = O.load_dets(G + "/R02_D1_dets.npz")
     pts = O.dets_to_points(offs, xy, nc, nfull)
+    # integer detections travel as ushort2; off the integer grid the adapter packs float2 / double2
+    for tag, shift in (("matrix_f32 ", 0.25), ("matrix_f64 ", 1e-7)):
+        got = np.array([[float(v) for v in l.split()[2:]] for l in out if l.startswith(tag)])
+        want = O.triangulate_points(cams, np.ascontiguousarray(pts[:, :60] + shift), O.MATRIX)["xyz"]
+        assert got.shape == (60, 3)
+        np.testing.assert_allclose(got, want, rtol=1e-9, atol=1e-7)
     Xm, em = O.matrix_point(cams, [0, 2], pts[[0, 2], 0])
     got = [float(v) for v in [l for l in out if l.startswith("point_matrix")][0].split()[1:]]
     np.testing.assert_allclose(got, [*Xm, em], rtol=1e-9)
