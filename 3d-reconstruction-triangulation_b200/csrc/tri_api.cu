@@ -103,6 +103,35 @@ static void fold_ray(const tri_engine* e, int c, const double c0[3], RayFold<T>&
   f.n4ob2[c] = (T)(n4 * ob2);
 }
 
+// RayFold<T>::mask_table (host copy): the presence-only sums of the ray normal equations per 8-bit validity mask,
+// accumulated in T in camera order -- exactly what RayPolicy<T>::add_const does view by view.
+template <typename T>
+static std::vector<T> ray_mask_table(const RayFold<T>& f, int n_cams) {
+  std::vector<T> tab((size_t)8 << TRI_RAY_TABLE_CAMS, (T)0);
+  const int n = std::min(n_cams, TRI_RAY_TABLE_CAMS);
+  for (int m = 0; m < (1 << TRI_RAY_TABLE_CAMS); m++) {
+    T cn[3] = {0, 0, 0}, so[3] = {0, 0, 0}, tr = 0, kn = 0;
+    for (int c = 0; c < n; c++) {
+      if (!(m >> c & 1)) continue;
+      for (int k = 0; k < 3; k++) { cn[k] = cn[k] + f.n4ob[c][k]; so[k] = so[k] + f.ob[c][k]; }
+      tr = tr + f.n4[c];
+      kn = kn + f.n4ob2[c];
+    }
+    T* row = &tab[(size_t)8 * m];
+    row[0] = cn[0]; row[1] = cn[1]; row[2] = cn[2]; row[3] = tr; row[4] = so[0]; row[5] = so[1]; row[6] = so[2]; row[7] = kn;
+  }
+  return tab;
+}
+template <typename T>
+static cudaError_t upload_ray_table(RayFold<T>& f, int n_cams) {
+  const std::vector<T> tab = ray_mask_table(f, n_cams);
+  T* d = nullptr;
+  cudaError_t err = cudaMalloc((void**)&d, tab.size() * sizeof(T));
+  if (err == cudaSuccess) err = cudaMemcpy(d, tab.data(), tab.size() * sizeof(T), cudaMemcpyHostToDevice);
+  f.mask_table = d;
+  return err;
+}
+
 static void build_rigs(tri_engine* e) {
   memset(&e->fold64, 0, sizeof(e->fold64));
   memset(&e->fold32, 0, sizeof(e->fold32));
@@ -240,6 +269,8 @@ int tri_create(int n_cams, const tri_camera* cams, int device, tri_engine** out)
   build_rigs(e);
   cudaError_t err = cudaMalloc((void**)&e->d_first_bad, sizeof(unsigned long long));
   if (err == cudaSuccess) err = cudaMemset(e->d_first_bad, 0xff, sizeof(unsigned long long));
+  if (err == cudaSuccess) err = upload_ray_table(e->fold64, n_cams);
+  if (err == cudaSuccess) err = upload_ray_table(e->fold32, n_cams);
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
   for (int i = 0; i < N_SLOTS && err == cudaSuccess; i++) err = cudaStreamCreateWithFlags(&e->slots[i].stream, cudaStreamNonBlocking);
   if (err != cudaSuccess) {
@@ -264,6 +295,8 @@ void tri_destroy(tri_engine* e) {
   if (e->d_scratch) cudaFree(e->d_scratch);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->d_first_bad) cudaFree(e->d_first_bad);
+  if (e->fold64.mask_table) cudaFree(const_cast<double*>(e->fold64.mask_table));
+  if (e->fold32.mask_table) cudaFree(const_cast<float*>(e->fold32.mask_table));
   delete e;
 }
 

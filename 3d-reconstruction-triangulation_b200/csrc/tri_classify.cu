@@ -21,6 +21,7 @@
 //     path-assignment logic on one thread.  Ties on (unused cameras, error) are broken by DFS order
 //     (the reference's heap order is an artefact of libstdc++); they are counted in stats.ties.
 #include <float.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -629,7 +630,13 @@ extern "C" int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drone
   long long leaf_cap = 4ll << 20;
   int grid = 0;
   auto alloc_work = [&]() -> int {
-    grid = std::max(1, std::min(batch, 2 * e->sm_count));
+    // every resident CTA slot gets a frame: the tree expansion is latency-bound (dependent FP64 chains, idle
+    // lanes on narrow levels), so occupancy is what hides it -- 4 CTAs per SM instead of 2: S09_D6 with the
+    // exact LM 3.88 -> 2.82 s (profiles/r1_cls_grid_sweep.log)
+    int per_sm = 2;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, enumerate_kernel, CLS_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+    if (const char* v = getenv("TRI_CLS_CTAS_PER_SM")) per_sm = std::max(1, atoi(v));  // tuning override
+    grid = std::max(1, std::min(batch, per_sm * e->sm_count));
     TRI_CUDA(d_front.alloc(sizeof(u64) * 2 * (size_t)cap * grid));
     TRI_CUDA(d_txyz.alloc(sizeof(double) * 3 * (size_t)cap * grid));
     TRI_CUDA(d_terr.alloc(sizeof(double) * (size_t)cap * grid));

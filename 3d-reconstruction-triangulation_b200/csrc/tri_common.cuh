@@ -42,7 +42,11 @@ struct __align__(16) RayFold {
   T n4ob[TRI_MAX_CAMS][3];  // n4 * ob
   T n4ob2[TRI_MAX_CAMS];    // n4 * |ob|^2
   T origin[3];
+  // device, [256][8]: the sums that depend on the validity mask alone -- n4ob (3), n4, ob (3), n4ob2 -- over the
+  // cameras of an 8-bit mask, added in camera order (bit-identical to adding them view by view)
+  const T* mask_table;
 };
+constexpr int TRI_RAY_TABLE_CAMS = 8;
 
 struct BatchOut {
   float* xyz_f32;
@@ -104,6 +108,14 @@ __device__ __forceinline__ double rcp_(double x) {
   return r;
 }
 __device__ __forceinline__ float rcp_(float x) { return 1.0f / x; }
+// 1 / |v|^2 of a pixel ray (|v|^2 >= depth^2 > 0, finite): FP64 as above; FP32 one MUFU.RCP (<= 1 ulp) instead of
+// the ~9-instruction IEEE division with its slow-path branch -- the FP32 ray kernel is issue-bound.
+__device__ __forceinline__ double rcp_ray(double x) { return rcp_(x); }
+__device__ __forceinline__ float rcp_ray(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 
 template <typename T>
 __device__ __forceinline__ void solve_sym3(const T M[6], const T v[3], T X[3]) {

@@ -37,9 +37,10 @@ struct RayPolicy {
     u[1] = fma_(r.U0[c][1], x, fma_(r.U1[c][1], y, r.U2[c][1]));
     u[2] = fma_(r.U0[c][2], x, fma_(r.U1[c][2], y, r.U2[c][2]));
     const T vx = fma_(r.ax[c], x, r.bx[c]), vy = fma_(r.ay[c], y, r.by[c]);
-    inv = rcp_(fma_(vx, vx, fma_(vy, vy, r.dd[c])));
+    inv = rcp_ray(fma_(vx, vx, fma_(vy, vy, r.dd[c])));
   }
-  static __device__ __forceinline__ void add(const Rig& r, int c, T x, T y, bool valid, Acc& a) {
+  // the pixel-dependent terms of one view ...
+  static __device__ __forceinline__ void add_pixel(const Rig& r, int c, T x, T y, bool valid, Acc& a) {
     if (!valid) return;
     T u[3], inv;
     ray(r, c, x, y, u, inv);
@@ -50,10 +51,18 @@ struct RayPolicy {
     const T w = fma_(u[0], r.ob[c][0], fma_(u[1], r.ob[c][1], mul_(u[2], r.ob[c][2])));
     a.cu[0] = fma_(u[0], t, a.cu[0]); a.cu[1] = fma_(u[1], t, a.cu[1]); a.cu[2] = fma_(u[2], t, a.cu[2]);
     a.ku = fma_(t, w, a.ku);
+  }
+  // ... and the ones that depend on its presence alone (the streaming tiles take these from rig.mask_table)
+  static __device__ __forceinline__ void add_const(const Rig& r, int c, bool valid, Acc& a) {
+    if (!valid) return;
     a.cn[0] += r.n4ob[c][0]; a.cn[1] += r.n4ob[c][1]; a.cn[2] += r.n4ob[c][2];
     a.so[0] += r.ob[c][0]; a.so[1] += r.ob[c][1]; a.so[2] += r.ob[c][2];
     a.tr += r.n4[c];
     a.kn += r.n4ob2[c];
+  }
+  static __device__ __forceinline__ void add(const Rig& r, int c, T x, T y, bool valid, Acc& a) {
+    add_pixel(r, c, x, y, valid, a);
+    add_const(r, c, valid, a);
   }
   static __device__ __forceinline__ T quad(const T (&M)[6], const T (&c)[3], T k, const T (&p)[3]) {
     const T Mp0 = fma_(M[0], p[0], fma_(M[1], p[1], mul_(M[2], p[2])));
@@ -134,6 +143,48 @@ struct RayPolicy {
   }
 };
 
+// ---- streaming tile of the scalar policy, one frame per thread: the validity mask first, its table row
+// requested at once (it is needed only after the camera loop, so the load hides behind it), the solver a
+// compile-time choice (the closed form then drops the terms only the LM loop reads) ----
+template <typename T_, bool LM>
+struct RayTableTile {
+  static constexpr int FPT = 1;
+  using S = RayPolicy<T_>;
+  using Rig = typename S::Rig;
+  template <int NC, int PIX>
+  static __device__ __forceinline__ void run(const Rig& rig, const typename RawPix<PIX, 1>::type (&raw)[NC], int, float (&X)[1][3],
+                                             uint32_t (&mask)[1]) {
+    using T = T_;
+    static_assert(NC <= TRI_RAY_TABLE_CAMS, "the mask table covers 8 cameras");
+    uint32_t m = 0;
+#pragma unroll
+    for (int c = 0; c < NC; c++) m |= (decode<float, PIX, 1>(raw[c]).v[0] ? 1u : 0u) << c;
+    T row[8];
+    if constexpr (sizeof(T) == 8) {
+      const double2* src = reinterpret_cast<const double2*>(rig.mask_table + 8 * m);
+#pragma unroll
+      for (int k = 0; k < (LM ? 4 : 2); k++) { const double2 t = __ldg(src + k); row[2 * k] = t.x; row[2 * k + 1] = t.y; }
+    } else {
+      const float4* src = reinterpret_cast<const float4*>(rig.mask_table + 8 * m);
+#pragma unroll
+      for (int k = 0; k < (LM ? 2 : 1); k++) { const float4 t = __ldg(src + k); row[4 * k] = t.x; row[4 * k + 1] = t.y; row[4 * k + 2] = t.z; row[4 * k + 3] = t.w; }
+    }
+    typename S::Acc acc;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const Views<T, PIX, 1> w = decode<T, PIX, 1>(raw[c]);
+      S::add_pixel(rig, c, w.x[0], w.y[0], w.v[0], acc);
+    }
+    acc.cn[0] = row[0]; acc.cn[1] = row[1]; acc.cn[2] = row[2]; acc.tr = row[3];
+    if constexpr (LM) { acc.so[0] = row[4]; acc.so[1] = row[5]; acc.so[2] = row[6]; acc.kn = row[7]; }
+    T P[3] = {0, 0, 0};
+    int it = 0;
+    if (__popc(m) >= 2) { S::solve(rig, acc, __popc(m), P, LM ? 1 : 0, it); S::to_world(rig, P); }
+    X[0][0] = (float)P[0]; X[0][1] = (float)P[1]; X[0][2] = (float)P[2];
+    mask[0] = m;
+  }
+};
+
 // ---- FP32 closed form, packed-pair SIMD (the ray counterpart of DltX2Tile) ----
 // Same operation order as RayPolicy<float> (which serves tails and optional outputs), so the points are
 // bit-identical; an absent view is masked by zeroing 1/|v|^2 and the constant terms' weight.
@@ -142,6 +193,7 @@ struct __align__(16) RayRigX2 {
   float2 ax[TRI_MAX_CAMS], bx[TRI_MAX_CAMS], ay[TRI_MAX_CAMS], by[TRI_MAX_CAMS], dd[TRI_MAX_CAMS], n4[TRI_MAX_CAMS];
   float2 ob[TRI_MAX_CAMS][3], n4ob[TRI_MAX_CAMS][3];
   float origin[3];
+  const float* mask_table;  // RayFold<float>::mask_table
 };
 
 struct RayX2Tile {
@@ -151,29 +203,34 @@ struct RayX2Tile {
   static __device__ __forceinline__ void run(const Rig& r, const typename RawPix<PIX, 2>::type (&raw)[NC], int, float (&X)[2][3],
                                              uint32_t (&mask)[2]) {
     const float2 z = make_float2(0.f, 0.f);
-    float2 uu[6] = {z, z, z, z, z, z}, cu[3] = {z, z, z}, cn[3] = {z, z, z}, tr = z;
+    float2 uu[6] = {z, z, z, z, z, z}, cu[3] = {z, z, z};
     uint32_t mask0 = 0, mask1 = 0;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
       const Views<float, PIX, 2> q = decode<float, PIX, 2>(raw[c]);
-      const float2 w = make_float2(q.v[0] ? 1.0f : 0.0f, q.v[1] ? 1.0f : 0.0f);
       mask0 |= (q.v[0] ? 1u : 0u) << c;
       mask1 |= (q.v[1] ? 1u : 0u) << c;
+    }
+    // sum of n4 ob and of n4 over the valid cameras: one table row per frame, used after the camera loop
+    const float4 k0 = __ldg(reinterpret_cast<const float4*>(r.mask_table + 8 * mask0));
+    const float4 k1 = __ldg(reinterpret_cast<const float4*>(r.mask_table + 8 * mask1));
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const Views<float, PIX, 2> q = decode<float, PIX, 2>(raw[c]);
       const float2 x = make_float2(q.x[0], q.x[1]), y = make_float2(q.y[0], q.y[1]);
       const float2 u0 = fma2(r.U0[c][0], x, fma2(r.U1[c][0], y, r.U2[c][0]));
       const float2 u1 = fma2(r.U0[c][1], x, fma2(r.U1[c][1], y, r.U2[c][1]));
       const float2 u2 = fma2(r.U0[c][2], x, fma2(r.U1[c][2], y, r.U2[c][2]));
       const float2 vx = fma2(r.ax[c], x, r.bx[c]), vy = fma2(r.ay[c], y, r.by[c]);
       const float2 vv = fma2(vx, vx, fma2(vy, vy, r.dd[c]));
-      const float2 inv = make_float2(q.v[0] ? 1.0f / vv.x : 0.f, q.v[1] ? 1.0f / vv.y : 0.f);
+      const float2 inv = make_float2(q.v[0] ? rcp_ray(vv.x) : 0.f, q.v[1] ? rcp_ray(vv.y) : 0.f);
       const float2 s0 = mul2(u0, inv), s1 = mul2(u1, inv), s2 = mul2(u2, inv);
       uu[0] = fma2(s0, u0, uu[0]); uu[1] = fma2(s0, u1, uu[1]); uu[2] = fma2(s0, u2, uu[2]);
       uu[3] = fma2(s1, u1, uu[3]); uu[4] = fma2(s1, u2, uu[4]); uu[5] = fma2(s2, u2, uu[5]);
       const float2 t = fma2(s0, r.ob[c][0], fma2(s1, r.ob[c][1], mul2(s2, r.ob[c][2])));
       cu[0] = fma2(u0, t, cu[0]); cu[1] = fma2(u1, t, cu[1]); cu[2] = fma2(u2, t, cu[2]);
-      cn[0] = fma2(w, r.n4ob[c][0], cn[0]); cn[1] = fma2(w, r.n4ob[c][1], cn[1]); cn[2] = fma2(w, r.n4ob[c][2], cn[2]);
-      tr = fma2(w, r.n4[c], tr);
     }
+    const float2 cn[3] = {make_float2(k0.x, k1.x), make_float2(k0.y, k1.y), make_float2(k0.z, k1.z)}, tr = make_float2(k0.w, k1.w);
     const float2 M[6] = {add2(tr, neg2(uu[0])), neg2(uu[1]), neg2(uu[2]), add2(tr, neg2(uu[3])), neg2(uu[4]), add2(tr, neg2(uu[5]))};
     const float2 cc[3] = {add2(cn[0], neg2(cu[0])), add2(cn[1], neg2(cu[1])), add2(cn[2], neg2(cu[2]))};
     float2 X0, X1, X2;
@@ -196,6 +253,7 @@ static RayRigX2 make_ray_x2(const RayFold<float>& f) {
     x.ax[c] = d(f.ax[c]); x.bx[c] = d(f.bx[c]); x.ay[c] = d(f.ay[c]); x.by[c] = d(f.by[c]); x.dd[c] = d(f.dd[c]); x.n4[c] = d(f.n4[c]);
   }
   for (int k = 0; k < 3; k++) x.origin[k] = f.origin[k];
+  x.mask_table = f.mask_table;
   return x;
 }
 
@@ -214,12 +272,17 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
       default: return launch_streamed<RayX2Tile, P32, PIX_U16, 2, 2, 3, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
     }
   }
-  using T64 = PolicyTile<P64, 1>;
+  // one frame per thread; the solver is a compile-time choice of the tile (the scalar policy serves the tails)
+  using LMT = RayTableTile<double, true>;
+  using CFT = RayTableTile<double, false>;
   switch (pixfmt) {
     case PIX_F32:
-      return launch_streamed<T64, P64, PIX_F32, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
-    case PIX_F64: return launch_streamed<T64, P64, PIX_F64, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
-    default: return launch_streamed<T64, P64, PIX_U16, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+      return lm ? launch_streamed<LMT, P64, PIX_F32, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
+                : launch_streamed<CFT, P64, PIX_F32, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+    case PIX_F64: return launch_streamed<LMT, P64, PIX_F64, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+    default:
+      return lm ? launch_streamed<LMT, P64, PIX_U16, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
+                : launch_streamed<CFT, P64, PIX_U16, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
   }
 }
 
