@@ -385,6 +385,153 @@ static cudaError_t launch_stream(const LaunchCtx& ctx, const typename TS::Rig& r
   return cudaGetLastError();
 }
 
+// ---- more than 8 cameras: the same barrier-free pipeline over (tile, camera chunk) units -----------
+// The generic batch_kernel indexes the rig with a runtime camera number, so every constant is an LDC (the ADU
+// pipe then bounds the ray kernels: 22 constants per view) and nothing is prefetched.  Here a tile's cameras are
+// walked in chunks of 8 with the accumulators carried in registers: one pipeline unit = 8 camera rows of one
+// tile, the chunk number selects one of four fully unrolled bodies, so every camera index is static again and
+// the constants come through uniform registers.
+constexpr int CHUNK_CAMS = 8;
+
+template <class S, int C0, int PIX, int FPT>
+__device__ __forceinline__ void chunk_accumulate(const typename S::Rig& rig, const typename RawPix<PIX, FPT>::type (&raw)[CHUNK_CAMS],
+                                                 int n_use, typename S::Acc (&acc)[FPT], uint32_t (&mask)[FPT]) {
+  using T = typename S::T;
+#pragma unroll
+  for (int c = 0; c < CHUNK_CAMS; c++) {
+    if (C0 + c < n_use) {  // uniform
+      const Views<T, PIX, FPT> w = decode<T, PIX, FPT>(raw[c]);
+#pragma unroll
+      for (int j = 0; j < FPT; j++) { S::add(rig, C0 + c, w.x[j], w.y[j], w.v[j], acc[j]); mask[j] |= (w.v[j] ? 1u : 0u) << (C0 + c); }
+    }
+  }
+}
+
+template <class S, int PIX, int FPT, int STAGES, int MINB>
+__global__ void __launch_bounds__(BATCH_THREADS, MINB)
+chunk_kernel(const __grid_constant__ typename S::Rig rig, const char* __restrict__ xy, int64_t row_bytes, int64_t n_tiles, int n_use,
+             BatchOut out, int opt, unsigned long long* first_bad, int64_t frame_base) {
+  using T = typename S::T;
+  using Raw = typename RawPix<PIX, FPT>::type;
+  constexpr int TILE = BATCH_THREADS * FPT;
+  constexpr int RB = (int)sizeof(Raw);
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: [STAGES][CHUNK_CAMS][BATCH_THREADS] Raw | [warps][32 * FPT * 3] float
+  Raw* slots = reinterpret_cast<Raw*>(smem);
+  float* outw = reinterpret_cast<float*>(smem + STAGES * CHUNK_CAMS * BATCH_THREADS * RB) + (threadIdx.x >> 5) * (32 * FPT * 3);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int n_chunks = (n_use + CHUNK_CAMS - 1) / CHUNK_CAMS;
+  // this CTA's units: tiles blockIdx.x, + gridDim.x, ...; each tile = n_chunks consecutive units
+  const int64_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t my_units = my_tiles * n_chunks;
+
+  auto prefetch = [&](int s, int64_t u) {
+    const int64_t t = blockIdx.x + (u / n_chunks) * gridDim.x;
+    const int ch = (int)(u % n_chunks);
+    const char* src = xy + (t * BATCH_THREADS + tid) * RB + (int64_t)ch * CHUNK_CAMS * row_bytes;
+#pragma unroll
+    for (int c = 0; c < CHUNK_CAMS; c++) {
+      if (ch * CHUNK_CAMS + c < n_use) {
+        Raw* dst = slots + (s * CHUNK_CAMS + c) * BATCH_THREADS + tid;
+        if constexpr (RB == 16) cp_async16(dst, src + c * row_bytes);
+        else if constexpr (RB == 8) cp_async8(dst, src + c * row_bytes);
+        else cp_async4(dst, src + c * row_bytes);
+      }
+    }
+  };
+#pragma unroll
+  for (int s = 0; s < STAGES; s++) {
+    if (s < my_units) prefetch(s, s);
+    cp_async_commit();
+  }
+
+  typename S::Acc acc[FPT];
+  uint32_t mask[FPT];
+  int ch = 0;
+  int64_t tile = blockIdx.x;
+  for (int64_t u = 0; u < my_units; u++) {
+    const int s = (int)(u % STAGES);
+    cp_async_wait<STAGES - 1>();
+    Raw raw[CHUNK_CAMS];
+#pragma unroll
+    for (int c = 0; c < CHUNK_CAMS; c++) raw[c] = slots[(s * CHUNK_CAMS + c) * BATCH_THREADS + tid];
+    if (u + STAGES < my_units) prefetch(s, u + STAGES);
+    cp_async_commit();
+
+    if (ch == 0) {
+#pragma unroll
+      for (int j = 0; j < FPT; j++) { acc[j] = typename S::Acc(); mask[j] = 0; }
+    }
+    switch (ch) {
+      case 0: chunk_accumulate<S, 0, PIX, FPT>(rig, raw, n_use, acc, mask); break;
+      case 1: chunk_accumulate<S, 8, PIX, FPT>(rig, raw, n_use, acc, mask); break;
+      case 2: chunk_accumulate<S, 16, PIX, FPT>(rig, raw, n_use, acc, mask); break;
+      default: chunk_accumulate<S, 24, PIX, FPT>(rig, raw, n_use, acc, mask); break;
+    }
+    if (++ch < n_chunks) continue;
+    ch = 0;
+
+    float X[FPT][3];
+#pragma unroll
+    for (int j = 0; j < FPT; j++) {
+      T P[3] = {0, 0, 0};
+      int it = 0;
+      if (__popc(mask[j]) >= 2) { S::solve(rig, acc[j], __popc(mask[j]), P, opt, it); S::to_world(rig, P); }
+      X[j][0] = (float)P[0]; X[j][1] = (float)P[1]; X[j][2] = (float)P[2];
+    }
+    const int64_t f0 = tile * TILE + (int64_t)tid * FPT;
+#pragma unroll
+    for (int j = 0; j < FPT; j++)
+      if (__popc(mask[j]) < 2) atomicMin(first_bad, (unsigned long long)(frame_base + f0 + j));
+    if (out.mask) {
+      if constexpr (FPT == 2) reinterpret_cast<uint2*>(out.mask)[f0 / 2] = make_uint2(mask[0], mask[1]);
+      else out.mask[f0] = mask[0];
+    }
+    __syncwarp();
+    if constexpr (FPT == 2) {
+      float2* o2 = reinterpret_cast<float2*>(outw) + 3 * lane;
+      o2[0] = make_float2(X[0][0], X[0][1]); o2[1] = make_float2(X[0][2], X[1][0]); o2[2] = make_float2(X[1][1], X[1][2]);
+    } else {
+      outw[3 * lane] = X[0][0]; outw[3 * lane + 1] = X[0][1]; outw[3 * lane + 2] = X[0][2];
+    }
+    __syncwarp();
+    float4* dst = reinterpret_cast<float4*>(out.xyz_f32 + 3 * (tile * TILE + (int64_t)(tid - lane) * FPT));
+    const float4* src4 = reinterpret_cast<const float4*>(outw);
+    constexpr int N4 = 32 * FPT * 3 / 4;
+#pragma unroll
+    for (int i = lane; i < N4; i += 32) __stcs(dst + i, src4[i]);
+    tile += gridDim.x;
+  }
+  cp_async_wait<0>();
+}
+
+template <class S, int PIX, int FPT, int STAGES, int MINB>
+static cudaError_t launch_chunk(const LaunchCtx& ctx, const typename S::Rig& rig, const void* d_xy, int n_use, int64_t n_frames,
+                                int64_t cam_stride, const BatchOut& out, int opt, int64_t* covered) {
+  *covered = 0;
+  constexpr int TILE = BATCH_THREADS * FPT;
+  using Raw = typename RawPix<PIX, FPT>::type;
+  const char* xy = static_cast<const char*>(d_xy);
+  const int64_t row_bytes = cam_stride * pix_bytes(PIX);
+  const int64_t n_tiles = n_frames / TILE;
+  if (n_tiles == 0 || n_use <= CHUNK_CAMS || n_use > 4 * CHUNK_CAMS) return cudaSuccess;
+  if (!out.xyz_f32 || out.xyz_f64 || out.err || out.iters) return cudaSuccess;
+  const int align = (int)sizeof(Raw);
+  if (((uintptr_t)xy % align) || (row_bytes % align) || ((uintptr_t)out.xyz_f32 & 15) || (out.mask && ((uintptr_t)out.mask & 7))) return cudaSuccess;
+  auto kern = chunk_kernel<S, PIX, FPT, STAGES, MINB>;
+  constexpr int bytes = STAGES * CHUNK_CAMS * BATCH_THREADS * (int)sizeof(Raw) + (BATCH_THREADS / 32) * 32 * FPT * 12;
+  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (err != cudaSuccess) return err;
+  int per_sm = 1;
+  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BATCH_THREADS, bytes);
+  if (err != cudaSuccess) return err;
+  const int64_t grid = std::min<int64_t>(n_tiles, (int64_t)ctx.sm_count * std::max(per_sm, 1));
+  kern<<<(unsigned)grid, BATCH_THREADS, bytes, ctx.stream>>>(rig, xy, row_bytes, n_tiles, n_use, out, opt, ctx.d_first_bad, ctx.frame_base);
+  ++*ctx.launches;
+  *covered = n_tiles * TILE;
+  return cudaGetLastError();
+}
+
 // Sub-range helper for the tail after the pipelined tiles.
 inline BatchOut advance(const BatchOut& o, int64_t frames) {
   BatchOut r = o;
@@ -404,7 +551,9 @@ static cudaError_t launch_streamed(const LaunchCtx& ctx, const typename TS::Rig&
   int64_t covered = 0;
   if constexpr (PIX != PIX_F64) {
     cudaError_t err;
-    if constexpr (OUTBUFS == 0)        // generation 3: barrier-free cp.async pipeline, rig from the parameter bank
+    if (S::CHUNKED && n_use > CHUNK_CAMS)  // 9..32 cameras: camera-chunked pipeline over the scalar policy
+      err = launch_chunk<S, PIX, (sizeof(typename S::T) == 4 ? 2 : 1), 3, (sizeof(typename S::T) == 4 ? 3 : 2)>(ctx, rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
+    else if constexpr (OUTBUFS == 0)   // generation 3: barrier-free cp.async pipeline, rig from the parameter bank
       err = launch_stream<TS, PIX, STAGES, MINB, false>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
     else if constexpr (OUTBUFS == -1)  // generation 3, rig staged in shared memory
       err = launch_stream<TS, PIX, STAGES, MINB, true>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
