@@ -281,7 +281,7 @@ def main():
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
             "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
             "kernel": ("stream_kernel<%s, 8 cams, float2>" % (("PolicyTile<DltPolicy<double>,2>" if a.precision == "f64" else "DltX2Tile (FFMA2)")
-                                                              if a.mode == "matrix" else "PolicyTile<RayPolicy>")),
+                                                              if a.mode == "matrix" else "RayTableTile<RayPolicy>")),
             "algorithmic_bytes_per_frame": 8 * N_CAMS + 12, "kernel_ms": kernel_ms}
 
     if a.precision == "f64" and a.mode == "matrix":
@@ -317,6 +317,31 @@ def main():
                        "frac": algo_bytes / (k * 1e-3) / 1e9 / peak}
         eng.device_status()
     res["other_kernels"] = other
+
+    # BASELINE config 5's batch half: the 32-camera two-ring rig, ray-LM and DLT on 20 M frames per GPU (the classifier
+    # half of that config is exponential in the camera count and not runnable with reference semantics)
+    try:
+        F32C = max(512, min(20_000_000, F // 5))
+        cams32 = S.ring_rig(32, rings=((6000.0, 3000.0), (9000.0, 5000.0)))
+        eng32 = T.Engine(cams32, local)
+        xy32 = S.generate_frames(cams32, F32C, frame0=frame0, device=dev)
+        out32 = {"xyz_f32": torch.empty((F32C, 3), dtype=torch.float32, device=dev)}
+        bytes32 = (8 * 32 + 12) * F32C
+        c5 = {"cameras": 32, "frames_per_gpu": F32C, "algorithmic_bytes_per_frame": 8 * 32 + 12}
+        for name, md, fl in (("ray_lm_f64", T.RAY, T.ALLOW_TOO_FEW), ("ray_closed_f32", T.RAY, T.ALLOW_TOO_FEW | T.F32),
+                             ("dlt_f64", T.MATRIX, T.ALLOW_TOO_FEW), ("dlt_f32", T.MATRIX, T.ALLOW_TOO_FEW | T.F32)):
+            def fn32(md=md, fl=fl):
+                eng32.triangulate_points_device(md, xy32, fl, out=out32)
+            tms, _, _ = timed(fn32, 3, 2)
+            k = tms / 3
+            c5[name] = {"ms_per_step": k, "frames_per_s": world * F32C / (k * 1e-3), "hbm_gbs": bytes32 / (k * 1e-3) / 1e9,
+                        "frac": bytes32 / (k * 1e-3) / 1e9 / peak}
+            eng32.device_status()
+        res["config5_batch_32cam"] = c5
+        del xy32, out32, eng32
+        torch.cuda.empty_cache()
+    except Exception as exc:  # noqa: BLE001
+        res["config5_batch_32cam"] = {"error": repr(exc)}
 
     # final gather of the points over NVLink (north star): one all-gather per step
     if world > 1:
