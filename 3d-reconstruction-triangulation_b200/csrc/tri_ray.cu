@@ -274,9 +274,13 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
   if (f32) {  // FP32: closed form only (the gain ratio of the LM loop needs S to ~1e-9 relative)
     const RayRigX2 x2 = make_ray_x2(r32);
     switch (pixfmt) {
-      case PIX_F32: return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 2, 3, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case PIX_F64: return launch_streamed<RayX2Tile, P32, PIX_F64, 2, 2, 3, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-      default: return launch_streamed<RayX2Tile, P32, PIX_U16, 2, 2, 3, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case PIX_F32:
+        // 3 stages x 2 CTAs per SM: 1.32 ms per 100 M frames; 2 stages x 3 CTAs (the DLT's choice): 1.47 ms -- with the
+        // lighter solve the kernel waits on memory (ncu r1f: long_scoreboard on top), so depth beats occupancy
+        if (ctx.variant == 1) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 2, 3, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 2, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case PIX_F64: return launch_streamed<RayX2Tile, P32, PIX_F64, 2, 3, 2, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      default: return launch_streamed<RayX2Tile, P32, PIX_U16, 2, 3, 2, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
     }
   }
   // one frame per thread; the solver is a compile-time choice of the tile (the scalar policy serves the tails)
@@ -284,6 +288,7 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
   using CFT = RayTableTile<double, false>;
   switch (pixfmt) {
     case PIX_F32:
+      // (4- and 6-stage rings measured the same: these two are FP64-pipe-bound)
       return lm ? launch_streamed<LMT, P64, PIX_F32, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
                 : launch_streamed<CFT, P64, PIX_F32, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
     case PIX_F64: return launch_streamed<LMT, P64, PIX_F64, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
