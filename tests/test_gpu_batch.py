@@ -334,6 +334,13 @@ def test_other_camera_counts(torch, n_cams):
         sub = [k for k in range(n_cams) if ref["mask"][f] >> k & 1]
         Xc = O.ray_closed_form(oc, sub, host[sub, f].astype(np.float64))
         assert np.abs(c["xyz_f64"][f].cpu().numpy() - Xc).max() < 1e-6
+    # the float3-only outputs take the streaming kernels (<= 8 cameras: table tiles; more: the camera-chunked
+    # pipeline) -- same points as the generic kernel's FP64 output, same masks
+    for fl, tol in ((0, 1e-3), (T.RAY_CLOSED_FORM, 1e-3), (T.F32, 0.2)):
+        q = eng.triangulate_points_device(T.RAY, xy, T.ALLOW_TOO_FEW | fl, want=("xyz_f32", "mask"))
+        eng.device_status()
+        assert np.array_equal(q["mask"].cpu().numpy().view(np.uint32), ref["mask"])
+        assert float((q["xyz_f32"].double() - c["xyz_f64"]).abs().max()) < tol
 
 
 def test_host_path_multi_chunk_pipeline(torch):
