@@ -51,8 +51,9 @@ struct DltPolicy {
   using T = T_;
   using Rig = DltRig<T>;
   // more than 8 cameras stay on the generic batch_kernel: the chunked pipeline measured slower for the DLT
-  // (32 cameras x 20 M frames: FP64 2.40 vs 1.84 ms, FP32 1.29 vs 0.99 ms)
+  // (32 cameras x 20 M frames: FP64 2.40 ms at one frame per thread, 2.03 ms at two, vs 1.84 ms; FP32 1.29 vs 0.99 ms)
   static constexpr bool CHUNKED = false;
+  static constexpr int CHUNK_FPT = 2;
   struct Acc {
     T M[6] = {0, 0, 0, 0, 0, 0};
     T v[3] = {0, 0, 0};

@@ -552,7 +552,7 @@ static cudaError_t launch_streamed(const LaunchCtx& ctx, const typename TS::Rig&
   if constexpr (PIX != PIX_F64) {
     cudaError_t err;
     if (S::CHUNKED && n_use > CHUNK_CAMS)  // 9..32 cameras: camera-chunked pipeline over the scalar policy
-      err = launch_chunk<S, PIX, (sizeof(typename S::T) == 4 ? 2 : 1), 3, (sizeof(typename S::T) == 4 ? 3 : 2)>(ctx, rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
+      err = launch_chunk<S, PIX, S::CHUNK_FPT, 3, (sizeof(typename S::T) == 4 ? 3 : 2)>(ctx, rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
     else if constexpr (OUTBUFS == 0)   // generation 3: barrier-free cp.async pipeline, rig from the parameter bank
       err = launch_stream<TS, PIX, STAGES, MINB, false>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
     else if constexpr (OUTBUFS == -1)  // generation 3, rig staged in shared memory

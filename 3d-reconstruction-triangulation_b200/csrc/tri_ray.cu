@@ -27,6 +27,7 @@ struct RayPolicy {
   // more than 8 cameras: chunk_kernel (tri_pipe.cuh) -- 32 cameras x 20 M frames: LM FP64 5.37 -> 3.30 ms, closed
   // form FP64 5.01 -> 2.81 ms, FP32 3.69 -> 1.81 ms against the generic kernel (profiles/r1_32cams.log)
   static constexpr bool CHUNKED = true;
+  static constexpr int CHUNK_FPT = sizeof(T_) == 4 ? 2 : 1;
   struct Acc {
     T uu[6] = {0, 0, 0, 0, 0, 0};  // sum u u^T / |v|^2        (M = tr I - uu)
     T cu[3] = {0, 0, 0};           // sum u (s . ob)           (c = cn - cu)
