@@ -68,6 +68,7 @@ struct DltPolicy {
     acc_row(valid, fma_(-x, P[8], P[0]), fma_(-x, P[9], P[1]), fma_(-x, P[10], P[2]), fma_(x, P[11], -P[3]), a.M, a.v);
     acc_row(valid, fma_(-y, P[8], P[4]), fma_(-y, P[9], P[5]), fma_(-y, P[10], P[6]), fma_(y, P[11], -P[7]), a.M, a.v);
   }
+  static __device__ __forceinline__ void add_chunk(const Rig& rig, int c, T x, T y, bool valid, Acc& a) { add(rig, c, x, y, valid, a); }
   static __device__ __forceinline__ void solve(const Rig&, const Acc& a, int, T (&X)[3], int, int&) {
     solve_sym3<T>(a.M, a.v, X);
   }

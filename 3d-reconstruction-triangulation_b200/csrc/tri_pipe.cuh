@@ -397,12 +397,21 @@ template <class S, int C0, int PIX, int FPT>
 __device__ __forceinline__ void chunk_accumulate(const typename S::Rig& rig, const typename RawPix<PIX, FPT>::type (&raw)[CHUNK_CAMS],
                                                  int n_use, typename S::Acc (&acc)[FPT], uint32_t (&mask)[FPT]) {
   using T = typename S::T;
+  if (C0 + CHUNK_CAMS <= n_use) {  // a full chunk: no per-camera test, so the views of the chunk can overlap
 #pragma unroll
-  for (int c = 0; c < CHUNK_CAMS; c++) {
-    if (C0 + c < n_use) {  // uniform
+    for (int c = 0; c < CHUNK_CAMS; c++) {
       const Views<T, PIX, FPT> w = decode<T, PIX, FPT>(raw[c]);
 #pragma unroll
-      for (int j = 0; j < FPT; j++) { S::add(rig, C0 + c, w.x[j], w.y[j], w.v[j], acc[j]); mask[j] |= (w.v[j] ? 1u : 0u) << (C0 + c); }
+      for (int j = 0; j < FPT; j++) { S::add_chunk(rig, C0 + c, w.x[j], w.y[j], w.v[j], acc[j]); mask[j] |= (w.v[j] ? 1u : 0u) << (C0 + c); }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < CHUNK_CAMS; c++) {
+      if (C0 + c < n_use) {  // uniform
+        const Views<T, PIX, FPT> w = decode<T, PIX, FPT>(raw[c]);
+#pragma unroll
+        for (int j = 0; j < FPT; j++) { S::add_chunk(rig, C0 + c, w.x[j], w.y[j], w.v[j], acc[j]); mask[j] |= (w.v[j] ? 1u : 0u) << (C0 + c); }
+      }
     }
   }
 }
@@ -552,7 +561,7 @@ static cudaError_t launch_streamed(const LaunchCtx& ctx, const typename TS::Rig&
   if constexpr (PIX != PIX_F64) {
     cudaError_t err;
     if (S::CHUNKED && n_use > CHUNK_CAMS)  // 9..32 cameras: camera-chunked pipeline over the scalar policy
-      err = launch_chunk<S, PIX, S::CHUNK_FPT, 3, (sizeof(typename S::T) == 4 ? 3 : 2)>(ctx, rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
+      err = launch_chunk<S, PIX, S::CHUNK_FPT, 3, 2>(ctx, rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
     else if constexpr (OUTBUFS == 0)   // generation 3: barrier-free cp.async pipeline, rig from the parameter bank
       err = launch_stream<TS, PIX, STAGES, MINB, false>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
     else if constexpr (OUTBUFS == -1)  // generation 3, rig staged in shared memory

@@ -70,6 +70,11 @@ struct RayPolicy {
     add_pixel(r, c, x, y, valid, a);
     add_const(r, c, valid, a);
   }
+  // chunk_kernel: the pixel terms branch-free (views of a chunk can then overlap), the cheap presence terms skipped
+  static __device__ __forceinline__ void add_chunk(const Rig& r, int c, T x, T y, bool valid, Acc& a) {
+    add_pixel<false>(r, c, x, y, valid, a);
+    add_const(r, c, valid, a);
+  }
   static __device__ __forceinline__ T quad(const T (&M)[6], const T (&c)[3], T k, const T (&p)[3]) {
     const T Mp0 = fma_(M[0], p[0], fma_(M[1], p[1], mul_(M[2], p[2])));
     const T Mp1 = fma_(M[1], p[0], fma_(M[3], p[1], mul_(M[4], p[2])));
