@@ -137,8 +137,10 @@ def cpu_baseline(cams, mode, seconds, make_sample):
     n2 = int(min(max(rate * seconds, n), 40_000_000))
     xy = make_sample(n2)
     valid, dt = cpu_run(O, ocams, xy, mode, threads)
+    v1, dt1 = cpu_run(O, ocams, xy[:, :min(n2, 2_000_000)], mode, 1)  # the reference itself is single-threaded
     return {"value": valid / dt, "unit": UNIT, "cores": threads, "kind": "port",
-            "sample": "first %d frames of the workload, %d valid points, %.2f s, OpenMP over frames" % (n2, valid, dt)}
+            "sample": "first %d frames of the workload, %d valid points, %.2f s, OpenMP over frames" % (n2, valid, dt),
+            "single_thread": v1 / dt1}
 
 
 def reference_arm(a, emit):
@@ -278,7 +280,7 @@ def main():
         traffic = float(t) * (F / 100_000_000) if t else None
     except Exception:
         pass
-    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8tbs": achieved / 8000.0,
             "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
             "kernel": ("stream_kernel<%s, 8 cams, float2>" % (("PolicyTile<DltPolicy<double>,2>" if a.precision == "f64" else "DltX2Tile (FFMA2)")
                                                               if a.mode == "matrix" else "RayTableTile<RayPolicy>")),
