@@ -67,7 +67,8 @@ EXPORTS = ["tri_version", "tri_last_error", "tri_device_count", "tri_create", "t
            "tri_engine_cameras", "tri_kernel_launches", "tri_triangulate_points", "tri_triangulate_points_multi",
            "tri_triangulate_points_device",
            "tri_device_status", "tri_enable_peer_access", "tri_ipc_export", "tri_ipc_open", "tri_ipc_close",
-           "tri_copy_device", "tri_triangulate_subsets", "tri_dist_from_ray", "tri_classify", "tri_host_alloc",
+           "tri_copy_device", "tri_triangulate_subsets", "tri_dist_from_ray", "tri_classify", "tri_classify_state_bytes",
+           "tri_classify_begin", "tri_classify_finish", "tri_host_alloc",
            "tri_host_free", "tri_device_alloc", "tri_device_free", "tri_copy_to_device", "tri_copy_to_host"]
 
 _lib = None
@@ -109,6 +110,9 @@ def lib():
         L.tri_dist_from_ray.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.tri_classify.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.POINTER(ClassifyStats)]
+        L.tri_classify_begin.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.tri_classify_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.POINTER(ClassifyStats)]
         L.tri_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
         L.tri_host_free.argtypes = [C.c_void_p]
         _lib = L
@@ -412,6 +416,33 @@ class Engine:
         _check(lib().tri_classify(self._h, mode, flags, n_drones, _np_ptr(offs), _np_ptr(xy), n_frames, _np_ptr(paths),
                                   _np_ptr(assign), _np_ptr(phase), C.byref(st)), mode)
         return dict(paths=paths, assign=assign, phase=phase, stats=st.as_dict())
+
+
+    # ---- frame-sharded classification: enumerate now, link when the previous shard's state has arrived ----
+    def classify_begin(self, mode, n_drones, det_offsets, dets_xy, n_frames, flags=0):
+        offs = np.ascontiguousarray(det_offsets, np.int32)
+        xy = np.ascontiguousarray(dets_xy, np.float64)
+        self._cls_job = (mode, n_drones, n_frames)
+        _check(lib().tri_classify_begin(self._h, mode, flags, n_drones, _np_ptr(offs), _np_ptr(xy), n_frames), mode)
+
+    def classify_finish(self, state=None):
+        """state: the bytes the previous shard's classify_finish returned (None at the start of the sequence).
+        Returns the same dict as classify() for this shard's frames, plus 'state' for the next shard."""
+        mode, n_drones, n_frames = self._cls_job
+        n_cams = len(self.cameras)
+        paths = np.zeros((n_drones, n_frames, 3))
+        assign = np.zeros((n_drones, n_frames, n_cams), np.int8)
+        phase = np.zeros((n_drones, n_frames), np.uint8)
+        st = ClassifyStats()
+        nb = lib().tri_classify_state_bytes()
+        s_in = None
+        if state is not None:
+            s_in = np.frombuffer(bytes(state), np.uint8).copy()
+            assert s_in.size == nb
+        s_out = np.zeros(nb, np.uint8)
+        _check(lib().tri_classify_finish(self._h, _np_ptr(s_in) if s_in is not None else None, _np_ptr(s_out), _np_ptr(paths),
+                                         _np_ptr(assign), _np_ptr(phase), C.byref(st)), mode)
+        return dict(paths=paths, assign=assign, phase=phase, stats=st.as_dict(), state=s_out.tobytes())
 
 
 def triangulate_points_multi(engines, mode, xy, flags=0, want=("xyz_f64",)):

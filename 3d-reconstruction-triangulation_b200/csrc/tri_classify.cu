@@ -559,6 +559,10 @@ struct DevBuf {
 
 struct ClsWork {
   DevBuf offs, dets, paths, assign, phase, state, ctr, front, txyz, terr, lcomb, lerr, lxyz, loff, lcnt;
+  // tri_classify_begin / tri_classify_finish: the enumerated shard waiting for its linking pass
+  bool pending = false;
+  ClsParams job;
+  int job_max_frontier = 0;
 };
 static void free_cls_work(void* w) { delete static_cast<ClsWork*>(w); }
 
@@ -699,6 +703,137 @@ extern "C" int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drone
     stats->nodes = (int64_t)h.nodes; stats->solves = (int64_t)h.solves; stats->leaves = (int64_t)h.leaves;
     stats->lm_iters = (int64_t)h.lm_iters; stats->phase1 = (int64_t)h.phase1; stats->phase2 = (int64_t)h.phase2;
     stats->ties = (int64_t)h.ties; stats->max_frontier = max_frontier;
+  }
+  return TRI_OK;
+}
+
+// ---- frame-sharded classification: candidate generation is independent per frame, linking is a
+// chain.  tri_classify_begin enumerates a contiguous shard of the sequence and keeps every frame's candidate
+// list on the device; tri_classify_finish links the shard starting from the tracking state the previous shard
+// ended with (n_drones x (last point + 3-point tail) + counters, an opaque tri_classify_state_bytes() blob) and
+// returns the state for the next one.  All ranks enumerate at once; only the small state travels along the chain.
+extern "C" int tri_classify_state_bytes(void) { return (int)sizeof(LinkState); }
+
+extern "C" int tri_classify_begin(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t* det_offsets,
+                                  const double* dets_xy, int n_frames) {
+  if (!e) return fail(TRI_ERR_ARG, "null engine");
+  if (mode != TRI_MATRIX && mode != TRI_RAY) return fail(TRI_ERR_ARG, "mode must be TRI_MATRIX or TRI_RAY");
+  const int C = e->n_cams;
+  if (C > CLS_MAX_CAMS) return fail(TRI_ERR_ARG, "the classifier handles at most 16 cameras (the search is exponential in the camera count)");
+  if (n_drones < 1 || n_drones > TRI_MAX_DRONES) return fail(TRI_ERR_ARG, "n_drones must be in [1, TRI_MAX_DRONES]");
+  if (n_frames < 0) return fail(TRI_ERR_ARG, "bad frame count");
+  if (n_frames > 0 && !det_offsets) return fail(TRI_ERR_ARG, "null detection offsets");
+  const size_t n_offs = (size_t)C * (n_frames + 1);
+  int64_t n_det = 0;
+  for (int c = 0; c < C && n_frames > 0; c++) {
+    const int32_t* o = det_offsets + (size_t)c * (n_frames + 1);
+    for (int f = 0; f < n_frames; f++) {
+      if (o[f + 1] < o[f]) return fail(TRI_ERR_ARG, "detection offsets must be non-decreasing");
+      if (o[f + 1] - o[f] > TRI_MAX_DETS) return fail(TRI_ERR_CAPACITY, "more than TRI_MAX_DETS detections on one camera in one frame");
+    }
+    n_det = std::max<int64_t>(n_det, o[n_frames]);
+  }
+  if (n_det > 0 && !dets_xy) return fail(TRI_ERR_ARG, "null detections");
+  DeviceGuard g(e->device);
+  cudaStream_t s = e->stream;
+  if (!e->cls_work) { e->cls_work = new ClsWork(); e->cls_work_free = free_cls_work; }
+  ClsWork& W = *static_cast<ClsWork*>(e->cls_work);
+  W.pending = false;
+  ClsParams p;
+  p.n_cams = C; p.n_drones = n_drones; p.n_frames = n_frames;
+  p.solver = mode == TRI_MATRIX ? 0 : (flags & TRI_RAY_REFERENCE_LM) ? 1 : 2;
+  p.error_ = mode == TRI_MATRIX ? MAX_ERROR_MATRIX : MAX_ERROR_RAY;
+  p.f0 = 0; p.f1 = n_frames;
+  W.job = p;
+  W.job_max_frontier = 0;
+  if (n_frames == 0) { W.pending = true; return TRI_OK; }
+  TRI_CUDA(W.offs.alloc(sizeof(int32_t) * n_offs));
+  TRI_CUDA(W.dets.alloc(sizeof(double) * 2 * n_det));
+  TRI_CUDA(W.ctr.alloc(sizeof(ClsCounters)));
+  TRI_CUDA(W.loff.alloc(sizeof(long long) * n_frames));
+  TRI_CUDA(W.lcnt.alloc(sizeof(int) * n_frames));
+  TRI_CUDA(cudaMemcpyAsync(W.offs.p, det_offsets, sizeof(int32_t) * n_offs, cudaMemcpyHostToDevice, s));
+  if (n_det) TRI_CUDA(cudaMemcpyAsync(W.dets.p, dets_xy, sizeof(double) * 2 * n_det, cudaMemcpyHostToDevice, s));
+  int per_sm = 2;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, enumerate_kernel, CLS_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  int cap = 1 << 14;
+  long long leaf_cap = std::max<long long>(4ll << 20, 1024ll * n_frames);
+  for (;;) {  // the whole shard's candidates stay resident: on overflow grow the buffers and enumerate again
+    const int grid = std::max(1, std::min(n_frames, per_sm * e->sm_count));
+    TRI_CUDA(W.front.alloc(sizeof(u64) * 2 * (size_t)cap * grid));
+    TRI_CUDA(W.txyz.alloc(sizeof(double) * 3 * (size_t)cap * grid));
+    TRI_CUDA(W.terr.alloc(sizeof(double) * (size_t)cap * grid));
+    TRI_CUDA(W.lcomb.alloc(sizeof(u64) * leaf_cap));
+    TRI_CUDA(W.lerr.alloc(sizeof(double) * leaf_cap));
+    TRI_CUDA(W.lxyz.alloc(sizeof(double) * 3 * leaf_cap));
+    TRI_CUDA(cudaMemsetAsync(W.ctr.p, 0, sizeof(ClsCounters), s));
+    p.cap = cap; p.leaf_cap = leaf_cap;
+    enumerate_kernel<<<grid, CLS_THREADS, 0, s>>>(e->rig64, e->ray, p, W.offs.as<int32_t>(), W.dets.as<double>(), W.front.as<u64>(),
+                                                   W.txyz.as<double>(), W.terr.as<double>(), W.lcomb.as<u64>(), W.lerr.as<double>(),
+                                                   W.lxyz.as<double>(), W.loff.as<long long>(), W.lcnt.as<int>(), W.ctr.as<ClsCounters>());
+    e->launches++;
+    TRI_CUDA(cudaGetLastError());
+    ClsCounters h{};
+    TRI_CUDA(cudaMemcpyAsync(&h, W.ctr.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    TRI_CUDA(cudaStreamSynchronize(s));
+    if (h.bad_input == 2) return fail(TRI_ERR_CAPACITY, "more than 16384 candidate combinations in one frame");
+    if (h.bad_input) return fail(TRI_ERR_ARG, "malformed detection offsets");
+    if (h.overflow_frontier) { if (cap >= (1 << 22)) return fail(TRI_ERR_CAPACITY, "combination frontier exceeds 4M nodes in one frame"); cap *= 4; continue; }
+    if (h.overflow_leaves) { if (leaf_cap >= (256ll << 20)) return fail(TRI_ERR_CAPACITY, "candidate list exceeds device buffer"); leaf_cap *= 4; continue; }
+    W.job_max_frontier = h.max_frontier;
+    break;
+  }
+  W.job = p;
+  W.pending = true;
+  return TRI_OK;
+}
+
+extern "C" int tri_classify_finish(tri_engine* e, const void* state_in, void* state_out, double* out_paths, int8_t* out_assign,
+                                   uint8_t* out_phase, tri_classify_stats* stats) {
+  if (!e || !e->cls_work) return fail(TRI_ERR_ARG, "tri_classify_finish without tri_classify_begin");
+  ClsWork& W = *static_cast<ClsWork*>(e->cls_work);
+  if (!W.pending) return fail(TRI_ERR_ARG, "tri_classify_finish without tri_classify_begin");
+  W.pending = false;
+  const ClsParams p = W.job;
+  const int C = p.n_cams, n_frames = p.n_frames, n_drones = p.n_drones;
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n_frames == 0) {
+    if (state_out) { if (state_in) memcpy(state_out, state_in, sizeof(LinkState)); else memset(state_out, 0, sizeof(LinkState)); }
+    return TRI_OK;
+  }
+  if (!out_paths) return fail(TRI_ERR_ARG, "bad output arguments");
+  DeviceGuard g(e->device);
+  cudaStream_t s = e->stream;
+  const size_t sz_paths = sizeof(double) * 3 * n_drones * (size_t)n_frames, sz_assign = (size_t)n_drones * n_frames * C,
+               sz_phase = (size_t)n_drones * n_frames;
+  TRI_CUDA(W.paths.alloc(sz_paths));
+  TRI_CUDA(W.assign.alloc(sz_assign));
+  TRI_CUDA(W.phase.alloc(sz_phase));
+  TRI_CUDA(W.state.alloc(sizeof(LinkState)));
+  TRI_CUDA(cudaMemsetAsync(W.paths.p, 0, sz_paths, s));
+  TRI_CUDA(cudaMemsetAsync(W.assign.p, 0xff, sz_assign, s));
+  TRI_CUDA(cudaMemsetAsync(W.phase.p, 0, sz_phase, s));
+  if (state_in) TRI_CUDA(cudaMemcpyAsync(W.state.p, state_in, sizeof(LinkState), cudaMemcpyHostToDevice, s));
+  else TRI_CUDA(cudaMemsetAsync(W.state.p, 0, sizeof(LinkState), s));
+  constexpr int LINK_DYN_BYTES = 2 * (int)((sizeof(u64) + 4 * sizeof(double)) * LINK_STAGE_LEAVES);
+  TRI_CUDA(cudaFuncSetAttribute(link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LINK_DYN_BYTES));
+  link_kernel<<<1, LINK_THREADS, LINK_DYN_BYTES, s>>>(e->ray, p, W.offs.as<int32_t>(), W.dets.as<double>(), W.lcomb.as<u64>(), W.lerr.as<double>(),
+                                                      W.lxyz.as<double>(), W.loff.as<long long>(), W.lcnt.as<int>(), W.state.as<LinkState>(),
+                                                      W.paths.as<double>(), out_assign ? W.assign.as<int8_t>() : nullptr,
+                                                      out_phase ? W.phase.as<uint8_t>() : nullptr, W.ctr.as<ClsCounters>());
+  e->launches++;
+  TRI_CUDA(cudaGetLastError());
+  ClsCounters h{};
+  TRI_CUDA(cudaMemcpyAsync(out_paths, W.paths.p, sz_paths, cudaMemcpyDeviceToHost, s));
+  if (out_assign) TRI_CUDA(cudaMemcpyAsync(out_assign, W.assign.p, sz_assign, cudaMemcpyDeviceToHost, s));
+  if (out_phase) TRI_CUDA(cudaMemcpyAsync(out_phase, W.phase.p, sz_phase, cudaMemcpyDeviceToHost, s));
+  if (state_out) TRI_CUDA(cudaMemcpyAsync(state_out, W.state.p, sizeof(LinkState), cudaMemcpyDeviceToHost, s));
+  TRI_CUDA(cudaMemcpyAsync(&h, W.ctr.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  TRI_CUDA(cudaStreamSynchronize(s));
+  if (stats) {
+    stats->nodes = (int64_t)h.nodes; stats->solves = (int64_t)h.solves; stats->leaves = (int64_t)h.leaves;
+    stats->lm_iters = (int64_t)h.lm_iters; stats->phase1 = (int64_t)h.phase1; stats->phase2 = (int64_t)h.phase2;
+    stats->ties = (int64_t)h.ties; stats->max_frontier = W.job_max_frontier;
   }
   return TRI_OK;
 }

@@ -155,6 +155,20 @@ int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drones, const in
                  const double* dets_xy, int n_frames, double* out_paths, int8_t* out_assign,
                  uint8_t* out_phase, tri_classify_stats* stats);
 
+/* The same over a frame-sharded sequence (one engine per GPU): candidate generation is independent
+ * per frame (fillCombinationQueue, DroneClassifier.cpp:156-198), linking is sequential (classifyDrones' path
+ * state, :119-135, :269-297).  tri_classify_begin enumerates this engine's contiguous shard of the sequence and
+ * keeps the candidates on the device; tri_classify_finish links the shard starting from `state_in` -- the opaque
+ * tri_classify_state_bytes() blob tri_classify_finish returned for the PREVIOUS shard (NULL = start of the
+ * sequence) -- and writes the state after the shard's last frame to `state_out` (may be NULL).  Outputs as in
+ * tri_classify, for the shard's frames; concatenated over the shards they equal tri_classify on the whole
+ * sequence bit for bit. */
+int tri_classify_state_bytes(void);
+int tri_classify_begin(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t* det_offsets,
+                       const double* dets_xy, int n_frames);
+int tri_classify_finish(tri_engine* e, const void* state_in, void* state_out, double* out_paths, int8_t* out_assign,
+                        uint8_t* out_phase, tri_classify_stats* stats);
+
 /* Memory helpers so a host without CUDA headers can own pinned / device buffers. */
 int tri_host_alloc(void** p, uint64_t bytes);   /* page-locked */
 int tri_host_free(void* p);

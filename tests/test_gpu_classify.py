@@ -242,3 +242,54 @@ def test_long_sequence_crosses_frame_batches(s09):
     r = eng.classify(T.MATRIX, 6, big_offs, big_xy, n)
     assert np.array_equal(r["assign"], ref["assign"]) and np.array_equal(r["phase"], ref["phase"])
     np.testing.assert_allclose(r["paths"], ref["paths"], rtol=1e-9, atol=1e-5)
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_frame_sharded_chain_equals_whole_sequence(s09, world):
+    """every shard's candidates are enumerated independently (tri_classify_begin), the shards are linked
+    in order with only the tracking state handed along (tri_classify_finish) -- bit for bit the unsharded result.
+    One engine per shard; on a one-GPU box they share the device, with more GPUs they are spread over them."""
+    import torch
+    from tri_b200 import sharding as SH
+    cams, eng, (offs, xy, nc, nf) = s09
+    whole = eng.classify(T.MATRIX, 6, offs, xy, nf)
+    n_dev = torch.cuda.device_count()
+    engines = [T.Engine(cams, g % n_dev) for g in range(world)]
+    r = SH.classify_chain(engines, T.MATRIX, 6, offs, xy, nf)
+    assert np.array_equal(r["assign"], whole["assign"]) and np.array_equal(r["phase"], whole["phase"])
+    assert np.array_equal(r["paths"], whole["paths"])
+    for k in ("nodes", "solves", "leaves", "phase1", "phase2", "ties"):
+        assert r["stats"][k] == whole["stats"][k], k
+    # the fast ray solver and a single-drone sequence through the same chain
+    w2 = eng.classify(T.RAY, 6, offs, xy, nf)
+    r2 = SH.classify_chain(engines, T.RAY, 6, offs, xy, nf)
+    assert np.array_equal(r2["assign"], w2["assign"]) and np.array_equal(r2["paths"], w2["paths"])
+
+
+def test_frame_sharded_edge_cases(r02):
+    """Shards shorter than the tail, an empty shard, finish without begin."""
+    from tri_b200 import sharding as SH
+    cams, eng, (offs, xy, nc, nf) = r02
+    o, x, _, n = O.slice_frames(offs, xy, nc, nf, 0, 7)
+    whole = eng.classify(T.MATRIX, 1, o, x, n)
+    engines = [T.Engine(cams, 0) for _ in range(9)]  # 9 shards over 7 frames: some are empty
+    r = SH.classify_chain(engines, T.MATRIX, 1, o, x, n)
+    assert np.array_equal(r["assign"], whole["assign"]) and np.array_equal(r["paths"], whole["paths"])
+    fresh = T.Engine(cams, 0)
+    fresh._cls_job = (T.MATRIX, 1, 7)
+    with pytest.raises(T.TriError):
+        fresh.classify_finish(None)  # tri_classify_finish without tri_classify_begin
+
+
+def test_frame_sharded_two_processes_nccl(s09, tmp_path):
+    """One process per GPU, the tracking state sent rank to rank over NCCL (needs 2 GPUs)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "_dist_classify_worker.py")],
+                         capture_output=True, text=True, timeout=600)
+    assert "DIST_CLASSIFY_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]

@@ -28,3 +28,21 @@ def test_gather_world_size_2_gloo():
                         "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "_dist_worker.py")],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_slice_csr_matches_the_oracle_slicer():
+    """Frame ranges of the classifier's CSR detections (what each rank of the sharded classifier enumerates):
+    same offsets / pixels as the oracle's own slicer, on a real multi-drone fixture with ragged detection counts."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    offs, xy, nc, nf = O.load_dets(os.path.join(ROOT, "tests", "golden", "S09_D6_dets.npz"))
+    for f0, f1 in ((0, nf), (0, 1), (17, 18), (100, 1600), (nf - 3, nf), (5, 5)):
+        o, x = SH.slice_csr(offs, xy, nc, nf, f0, f1)
+        wo, wx, wnc, wnf = O.slice_frames(offs, xy, nc, nf, f0, f1)
+        assert wnf == f1 - f0 and np.array_equal(o, np.asarray(wo).reshape(-1))
+        assert np.array_equal(np.asarray(x).reshape(-1, 2), np.asarray(wx).reshape(-1, 2))
+    # the ranges classify_chain / classify_sharded use partition the sequence
+    for world in (1, 2, 3, 8):
+        cuts = [(nf * g // world, nf * (g + 1) // world) for g in range(world)]
+        assert cuts[0][0] == 0 and cuts[-1][1] == nf and all(cuts[g][1] == cuts[g + 1][0] for g in range(world - 1))
