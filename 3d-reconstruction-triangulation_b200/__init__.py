@@ -68,7 +68,7 @@ EXPORTS = ["tri_version", "tri_last_error", "tri_device_count", "tri_create", "t
            "tri_triangulate_points_device",
            "tri_device_status", "tri_enable_peer_access", "tri_ipc_export", "tri_ipc_open", "tri_ipc_close",
            "tri_copy_device", "tri_triangulate_subsets", "tri_dist_from_ray", "tri_classify", "tri_classify_state_bytes",
-           "tri_classify_begin", "tri_classify_finish", "tri_host_alloc",
+           "tri_classify_begin", "tri_classify_finish", "tri_classify_multi", "tri_host_alloc",
            "tri_host_free", "tri_device_alloc", "tri_device_free", "tri_copy_to_device", "tri_copy_to_host"]
 
 _lib = None
@@ -113,6 +113,8 @@ def lib():
         L.tri_classify_begin.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.tri_classify_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(ClassifyStats)]
+        L.tri_classify_multi.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ClassifyStats)]
         L.tri_host_alloc.argtypes = [C.POINTER(C.c_void_p), C.c_uint64]
         L.tri_host_free.argtypes = [C.c_void_p]
         _lib = L
@@ -443,6 +445,21 @@ class Engine:
         _check(lib().tri_classify_finish(self._h, _np_ptr(s_in) if s_in is not None else None, _np_ptr(s_out), _np_ptr(paths),
                                          _np_ptr(assign), _np_ptr(phase), C.byref(st)), mode)
         return dict(paths=paths, assign=assign, phase=phase, stats=st.as_dict(), state=s_out.tobytes())
+
+
+def classify_multi(engines, mode, n_drones, det_offsets, dets_xy, n_frames, flags=0):
+    """tri_classify_multi: one sequence, frame-sharded over several engines (one per GPU) from one process."""
+    n_cams = len(engines[0].cameras)
+    offs = np.ascontiguousarray(det_offsets, np.int32)
+    xy = np.ascontiguousarray(dets_xy, np.float64)
+    paths = np.zeros((n_drones, n_frames, 3))
+    assign = np.zeros((n_drones, n_frames, n_cams), np.int8)
+    phase = np.zeros((n_drones, n_frames), np.uint8)
+    st = ClassifyStats()
+    hs = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    _check(lib().tri_classify_multi(hs, len(engines), mode, flags, n_drones, _np_ptr(offs), _np_ptr(xy), n_frames, _np_ptr(paths),
+                                    _np_ptr(assign), _np_ptr(phase), C.byref(st)), mode)
+    return dict(paths=paths, assign=assign, phase=phase, stats=st.as_dict())
 
 
 def triangulate_points_multi(engines, mode, xy, flags=0, want=("xyz_f64",)):

@@ -24,6 +24,8 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "tri_engine.cuh"
@@ -834,6 +836,75 @@ extern "C" int tri_classify_finish(tri_engine* e, const void* state_in, void* st
     stats->nodes = (int64_t)h.nodes; stats->solves = (int64_t)h.solves; stats->leaves = (int64_t)h.leaves;
     stats->lm_iters = (int64_t)h.lm_iters; stats->phase1 = (int64_t)h.phase1; stats->phase2 = (int64_t)h.phase2;
     stats->ties = (int64_t)h.ties; stats->max_frontier = W.job_max_frontier;
+  }
+  return TRI_OK;
+}
+
+// One C++ process driving several GPUs: every engine enumerates its contiguous frame range on its own host thread,
+// then the shards are linked in order on the caller's thread with the state handed along.  Same outputs as
+// tri_classify on the whole sequence.
+extern "C" int tri_classify_multi(tri_engine* const* engines, int n_engines, int mode, unsigned flags, int n_drones,
+                                  const int32_t* det_offsets, const double* dets_xy, int n_frames, double* out_paths,
+                                  int8_t* out_assign, uint8_t* out_phase, tri_classify_stats* stats) {
+  if (!engines || n_engines < 1) return fail(TRI_ERR_ARG, "no engines");
+  for (int g = 0; g < n_engines; g++)
+    if (!engines[g] || engines[g]->n_cams != engines[0]->n_cams) return fail(TRI_ERR_ARG, "engines must hold the same rig");
+  if (n_engines == 1) return tri_classify(engines[0], mode, flags, n_drones, det_offsets, dets_xy, n_frames, out_paths, out_assign, out_phase, stats);
+  if (n_frames < 0 || !out_paths || (n_frames > 0 && !det_offsets)) return fail(TRI_ERR_ARG, "bad arguments");
+  if (n_drones < 1 || n_drones > TRI_MAX_DRONES) return fail(TRI_ERR_ARG, "n_drones must be in [1, TRI_MAX_DRONES]");
+  const int C = engines[0]->n_cams;
+  auto cut = [&](int g) { return (int)((int64_t)n_frames * g / n_engines); };
+  // per-shard CSR: offsets rebased to the shard, detections gathered camera by camera
+  std::vector<std::vector<int32_t>> offs(n_engines);
+  std::vector<std::vector<double>> dets(n_engines);
+  for (int g = 0; g < n_engines; g++) {
+    const int f0 = cut(g), f1 = cut(g + 1);
+    offs[g].assign((size_t)C * (f1 - f0 + 1), 0);
+    int32_t base = 0;
+    for (int c = 0; c < C; c++) {
+      const int32_t* o = det_offsets + (size_t)c * (n_frames + 1);
+      const int32_t a = o[f0], b = o[f1];
+      if (b < a) return fail(TRI_ERR_ARG, "detection offsets must be non-decreasing");
+      for (int f = f0; f <= f1; f++) offs[g][(size_t)c * (f1 - f0 + 1) + (f - f0)] = o[f] - a + base;
+      if (b > a) {
+        if (!dets_xy) return fail(TRI_ERR_ARG, "null detections");
+        dets[g].insert(dets[g].end(), dets_xy + 2 * (size_t)a, dets_xy + 2 * (size_t)b);
+      }
+      base += b - a;
+    }
+  }
+  std::vector<int> status(n_engines, TRI_OK);
+  std::vector<std::string> msg(n_engines);
+  std::vector<std::thread> workers;
+  for (int g = 0; g < n_engines; g++)
+    workers.emplace_back([&, g]() {
+      status[g] = tri_classify_begin(engines[g], mode, flags, n_drones, offs[g].data(), dets[g].empty() ? nullptr : dets[g].data(), cut(g + 1) - cut(g));
+      if (status[g] != TRI_OK) msg[g] = tri_last_error();
+    });
+  for (std::thread& t : workers) t.join();
+  for (int g = 0; g < n_engines; g++)
+    if (status[g] != TRI_OK) return fail(status[g], msg[g]);
+  if (stats) memset(stats, 0, sizeof(*stats));
+  std::vector<unsigned char> state(sizeof(LinkState), 0);
+  for (int g = 0; g < n_engines; g++) {
+    const int f0 = cut(g), nf = cut(g + 1) - f0;
+    std::vector<double> paths((size_t)3 * n_drones * nf);
+    std::vector<int8_t> assign(out_assign ? (size_t)n_drones * nf * C : 0);
+    std::vector<uint8_t> phase(out_phase ? (size_t)n_drones * nf : 0);
+    tri_classify_stats st{};
+    const int rc = tri_classify_finish(engines[g], g == 0 ? nullptr : state.data(), state.data(), nf ? paths.data() : out_paths,
+                                       out_assign ? assign.data() : nullptr, out_phase ? phase.data() : nullptr, &st);
+    if (rc != TRI_OK) return rc;
+    for (int d = 0; d < n_drones; d++) {  // [drone][frame] rows of the shard into the whole sequence's rows
+      if (nf) memcpy(out_paths + ((size_t)d * n_frames + f0) * 3, paths.data() + (size_t)d * nf * 3, sizeof(double) * 3 * nf);
+      if (out_assign && nf) memcpy(out_assign + ((size_t)d * n_frames + f0) * C, assign.data() + (size_t)d * nf * C, (size_t)nf * C);
+      if (out_phase && nf) memcpy(out_phase + (size_t)d * n_frames + f0, phase.data() + (size_t)d * nf, nf);
+    }
+    if (stats) {
+      stats->nodes += st.nodes; stats->solves += st.solves; stats->leaves += st.leaves; stats->lm_iters += st.lm_iters;
+      stats->phase1 += st.phase1; stats->phase2 += st.phase2; stats->ties += st.ties;
+      stats->max_frontier = std::max(stats->max_frontier, st.max_frontier);
+    }
   }
   return TRI_OK;
 }

@@ -168,6 +168,11 @@ int tri_classify_begin(tri_engine* e, int mode, unsigned flags, int n_drones, co
                        const double* dets_xy, int n_frames);
 int tri_classify_finish(tri_engine* e, const void* state_in, void* state_out, double* out_paths, int8_t* out_assign,
                         uint8_t* out_phase, tri_classify_stats* stats);
+/* One host process, one engine per GPU: begin on every engine concurrently, finish in order.  Arguments and
+ * results as tri_classify. */
+int tri_classify_multi(tri_engine* const* engines, int n_engines, int mode, unsigned flags, int n_drones,
+                       const int32_t* det_offsets, const double* dets_xy, int n_frames, double* out_paths,
+                       int8_t* out_assign, uint8_t* out_phase, tri_classify_stats* stats);
 
 /* Memory helpers so a host without CUDA headers can own pinned / device buffers. */
 int tri_host_alloc(void** p, uint64_t bytes);   /* page-locked */

@@ -260,6 +260,10 @@ def test_frame_sharded_chain_equals_whole_sequence(s09, world):
     assert np.array_equal(r["paths"], whole["paths"])
     for k in ("nodes", "solves", "leaves", "phase1", "phase2", "ties"):
         assert r["stats"][k] == whole["stats"][k], k
+    # the C entry point that does the same from one process (a host thread per engine for the enumeration)
+    m = T.classify_multi(engines, T.MATRIX, 6, offs, xy, nf)
+    assert np.array_equal(m["assign"], whole["assign"]) and np.array_equal(m["phase"], whole["phase"]) and np.array_equal(m["paths"], whole["paths"])
+    assert m["stats"]["leaves"] == whole["stats"]["leaves"] and m["stats"]["phase1"] == whole["stats"]["phase1"]
     # the fast ray solver and a single-drone sequence through the same chain
     w2 = eng.classify(T.RAY, 6, offs, xy, nf)
     r2 = SH.classify_chain(engines, T.RAY, 6, offs, xy, nf)
