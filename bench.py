@@ -345,6 +345,30 @@ def main():
     except Exception as exc:  # noqa: BLE001
         res["config5_batch_32cam"] = {"error": repr(exc)}
 
+    # BASELINE config 3 (S09_D6, 8 cameras, 6 drones, 3000 frames): the batched DroneClassifier through tri_classify,
+    # wall clock of the whole call from host CSR detections to host paths (the fixture ships with the tests)
+    if rank == 0:
+        try:
+            import numpy as np
+            gdir = os.path.join(ROOT, "tests", "golden")
+            z = np.load(os.path.join(gdir, "S09_D6_dets.npz"))
+            ceng = T.Engine(T.load_cameras_xml(os.path.join(gdir, "S09_D6_cameras.xml")), local)
+            counts = z["counts"].astype(np.int64)  # [cam][frame] detection counts -> CSR offsets, cameras back to back
+            c_nf = counts.shape[1]
+            c_offs = np.zeros((counts.shape[0], c_nf + 1), np.int64)
+            c_offs[:, 1:] = np.cumsum(counts, axis=1)
+            c_offs += np.concatenate([[0], np.cumsum(counts.sum(1))[:-1]])[:, None]
+            c_offs, c_xy = c_offs.astype(np.int32).reshape(-1), z["xy"].astype(np.float64)
+            ceng.classify(T.MATRIX, 6, c_offs, c_xy, c_nf)
+            t0 = time.perf_counter()
+            cr = ceng.classify(T.MATRIX, 6, c_offs, c_xy, c_nf)
+            cdt = time.perf_counter() - t0
+            res["config3_classifier"] = {"dataset": "S09_D6", "mode": "matrix", "n_drones": 6, "frames": c_nf, "seconds": cdt,
+                                         "frames_per_s": c_nf / cdt, "candidate_solves": cr["stats"]["solves"],
+                                         "points": int(cr["stats"]["phase1"] + cr["stats"]["phase2"])}
+        except Exception as exc:  # noqa: BLE001
+            res["config3_classifier"] = {"error": repr(exc)}
+
     # final gather of the points over NVLink (north star): one all-gather per step
     if world > 1:
         allp = torch.empty((world * F, 3), dtype=torch.float32, device=dev)
