@@ -297,7 +297,18 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __re
     if (n < 0x3fffffff) S.n[path] = n + 1;
     double* o = out_paths + ((size_t)path * p.n_frames + f) * 3;
     o[0] = pt[0]; o[1] = pt[1]; o[2] = pt[2];
-    if (out_assign) for (int c = 0; c < C; c++) out_assign[((size_t)path * p.n_frames + f) * C + c] = (int8_t)((comb >> (4 * c)) & 15);
+    if (out_assign) {
+      int8_t* dst = out_assign + ((size_t)path * p.n_frames + f) * C;
+      if (C == 8) {  // the 8 nibbles spread to 8 bytes, one store (rows of 8 bytes are 8-byte aligned)
+        u64 x = comb & 0xffffffffull;
+        x = (x | (x << 16)) & 0x0000ffff0000ffffull;
+        x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
+        x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
+        *reinterpret_cast<u64*>(dst) = x;
+      } else {
+        for (int c = 0; c < C; c++) dst[c] = (int8_t)((comb >> (4 * c)) & 15);
+      }
+    }
     if (out_phase) out_phase[(size_t)path * p.n_frames + f] = (uint8_t)phase;
   };
 
