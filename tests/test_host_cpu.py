@@ -57,6 +57,16 @@ def test_create_argument_checks():
     assert T.lib().tri_create(T.MAX_CAMS + 1, None, 0, ctypes.byref(h)) == T.ERR_ARG
 
 
+def test_sharded_classifier_entry_points_reject_missing_engines():
+    """tri_classify_begin / _finish / _multi fail with TRI_ERR_ARG (and a message) before touching a device."""
+    L = T.lib()
+    assert L.tri_classify_state_bytes() == 16 * 3 * 3 * 8 + 16 * 4  # TRI_MAX_DRONES x (3-point tail) + counters
+    assert L.tri_classify_begin(None, T.MATRIX, 0, 1, None, None, 0) == T.ERR_ARG
+    assert L.tri_classify_finish(None, None, None, None, None, None, None) == T.ERR_ARG
+    assert L.tri_classify_multi(None, 0, T.MATRIX, 0, 1, None, None, 0, None, None, None, None) == T.ERR_ARG
+    assert b"engine" in L.tri_last_error()
+
+
 def test_synthetic_frames_are_keyed_by_global_frame_index():
     cams = S.ring_rig(8)
     whole = S.generate_frames(cams, 3000)
