@@ -157,44 +157,55 @@ struct RayPolicy {
 // ---- streaming tile of the scalar policy, one frame per thread: the validity mask first, its table row
 // requested at once (it is needed only after the camera loop, so the load hides behind it), the solver a
 // compile-time choice (the closed form then drops the terms only the LM loop reads) ----
-template <typename T_, bool LM>
+template <typename T_, bool LM, int FPT_ = 1>
 struct RayTableTile {
-  static constexpr int FPT = 1;
+  static constexpr int FPT = FPT_;
   using S = RayPolicy<T_>;
   using Rig = typename S::Rig;
   template <int NC, int PIX>
-  static __device__ __forceinline__ void run(const Rig& rig, const typename RawPix<PIX, 1>::type (&raw)[NC], int, float (&X)[1][3],
-                                             uint32_t (&mask)[1]) {
+  static __device__ __forceinline__ void run(const Rig& rig, const typename RawPix<PIX, FPT>::type (&raw)[NC], int, float (&X)[FPT][3],
+                                             uint32_t (&mask)[FPT]) {
     using T = T_;
     static_assert(NC <= TRI_RAY_TABLE_CAMS, "the mask table covers 8 cameras");
-    uint32_t m = 0;
 #pragma unroll
-    for (int c = 0; c < NC; c++) m |= (decode<float, PIX, 1>(raw[c]).v[0] ? 1u : 0u) << c;
-    T row[8];
-    if constexpr (sizeof(T) == 8) {
-      const double2* src = reinterpret_cast<const double2*>(rig.mask_table + 8 * m);
-#pragma unroll
-      for (int k = 0; k < (LM ? 4 : 2); k++) { const double2 t = __ldg(src + k); row[2 * k] = t.x; row[2 * k + 1] = t.y; }
-    } else {
-      const float4* src = reinterpret_cast<const float4*>(rig.mask_table + 8 * m);
-#pragma unroll
-      for (int k = 0; k < (LM ? 2 : 1); k++) { const float4 t = __ldg(src + k); row[4 * k] = t.x; row[4 * k + 1] = t.y; row[4 * k + 2] = t.z; row[4 * k + 3] = t.w; }
-    }
-    typename S::Acc acc;
+    for (int j = 0; j < FPT; j++) mask[j] = 0;
 #pragma unroll
     for (int c = 0; c < NC; c++) {
-      const Views<T, PIX, 1> w = decode<T, PIX, 1>(raw[c]);
+      const Views<float, PIX, FPT> v = decode<float, PIX, FPT>(raw[c]);
+#pragma unroll
+      for (int j = 0; j < FPT; j++) mask[j] |= (v.v[j] ? 1u : 0u) << c;
+    }
+    T row[FPT][8];
+#pragma unroll
+    for (int j = 0; j < FPT; j++) {
+      if constexpr (sizeof(T) == 8) {
+        const double2* src = reinterpret_cast<const double2*>(rig.mask_table + 8 * mask[j]);
+#pragma unroll
+        for (int k = 0; k < (LM ? 4 : 2); k++) { const double2 t = __ldg(src + k); row[j][2 * k] = t.x; row[j][2 * k + 1] = t.y; }
+      } else {
+        const float4* src = reinterpret_cast<const float4*>(rig.mask_table + 8 * mask[j]);
+#pragma unroll
+        for (int k = 0; k < (LM ? 2 : 1); k++) { const float4 t = __ldg(src + k); row[j][4 * k] = t.x; row[j][4 * k + 1] = t.y; row[j][4 * k + 2] = t.z; row[j][4 * k + 3] = t.w; }
+      }
+    }
+    typename S::Acc acc[FPT];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const Views<T, PIX, FPT> w = decode<T, PIX, FPT>(raw[c]);
       // absent views: skipped by a branch in the closed form, masked branch-free under the LM loop (measured:
       // 2.54 vs 3.04 ms and 4.75 vs 4.98 ms per 100 M frames -- the branch-free closed form spills at 128 registers)
-      S::template add_pixel<!LM>(rig, c, w.x[0], w.y[0], w.v[0], acc);
+#pragma unroll
+      for (int j = 0; j < FPT; j++) S::template add_pixel<!LM>(rig, c, w.x[j], w.y[j], w.v[j], acc[j]);
     }
-    acc.cn[0] = row[0]; acc.cn[1] = row[1]; acc.cn[2] = row[2]; acc.tr = row[3];
-    if constexpr (LM) { acc.so[0] = row[4]; acc.so[1] = row[5]; acc.so[2] = row[6]; acc.kn = row[7]; }
-    T P[3] = {0, 0, 0};
-    int it = 0;
-    if (__popc(m) >= 2) { S::solve(rig, acc, __popc(m), P, LM ? 1 : 0, it); S::to_world(rig, P); }
-    X[0][0] = (float)P[0]; X[0][1] = (float)P[1]; X[0][2] = (float)P[2];
-    mask[0] = m;
+#pragma unroll
+    for (int j = 0; j < FPT; j++) {
+      acc[j].cn[0] = row[j][0]; acc[j].cn[1] = row[j][1]; acc[j].cn[2] = row[j][2]; acc[j].tr = row[j][3];
+      if constexpr (LM) { acc[j].so[0] = row[j][4]; acc[j].so[1] = row[j][5]; acc[j].so[2] = row[j][6]; acc[j].kn = row[j][7]; }
+      T P[3] = {0, 0, 0};
+      int it = 0;
+      if (__popc(mask[j]) >= 2) { S::solve(rig, acc[j], __popc(mask[j]), P, LM ? 1 : 0, it); S::to_world(rig, P); }
+      X[j][0] = (float)P[0]; X[j][1] = (float)P[1]; X[j][2] = (float)P[2];
+    }
   }
 };
 
@@ -291,16 +302,16 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
   }
   // one frame per thread; the solver is a compile-time choice of the tile (the scalar policy serves the tails)
   using LMT = RayTableTile<double, true>;
-  using CFT = RayTableTile<double, false>;
+  using CFT = RayTableTile<double, false, 2>;  // closed form: two frames per thread (2.41 vs 2.50 ms per 100 M frames)
   switch (pixfmt) {
     case PIX_F32:
       // (4- and 6-stage rings measured the same: these two are FP64-pipe-bound)
       return lm ? launch_streamed<LMT, P64, PIX_F32, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
-                : launch_streamed<CFT, P64, PIX_F32, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+                : launch_streamed<CFT, P64, PIX_F32, 2, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
     case PIX_F64: return launch_streamed<LMT, P64, PIX_F64, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
     default:
       return lm ? launch_streamed<LMT, P64, PIX_U16, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
-                : launch_streamed<CFT, P64, PIX_U16, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+                : launch_streamed<CFT, P64, PIX_U16, 2, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
   }
 }
 
