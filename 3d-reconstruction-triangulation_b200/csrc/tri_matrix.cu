@@ -217,7 +217,9 @@ cudaError_t launch_dlt(const LaunchCtx& ctx, bool f32, int pixfmt, const DltRig<
       case 1: return launch_streamed<T64, P64, PIX_F32, 1, 4, 3, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);  // gen 2
       case 2: return launch_batch_policy<P64, PIX_F32, 1, 3>(ctx, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);                // gen 1
       case 3: return launch_streamed<T64, P64, PIX_F32, 1, 3, 4, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);  // gen 3, one frame per thread
-      default: return launch_streamed<PolicyTile<P64, 2>, P64, PIX_F32, 2, 3, 2, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 4: return launch_streamed<PolicyTile<P64, 2>, P64, PIX_F32, 2, 3, 2, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);  // 3-stage ring: 1.955 ms
+      // two frames per thread, 2-stage ring, 2 CTAs per SM: 1.934 ms (3 CTAs at 80 registers spill: 2.196 ms)
+      default: return launch_streamed<PolicyTile<P64, 2>, P64, PIX_F32, 2, 2, 2, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
     }
   }
   if (pixfmt == PIX_F64) return launch_streamed<T64, P64, PIX_F64, 1, 4, 3, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);

@@ -282,7 +282,7 @@ def main():
         pass
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8tbs": achieved / 8000.0,
             "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
-            "kernel": ("stream_kernel<%s, 8 cams, float2>" % (("PolicyTile<DltPolicy<double>,2>" if a.precision == "f64" else "DltX2Tile (FFMA2)")
+            "kernel": ("stream_kernel<%s, 8 cams, float2>" % (("PolicyTile<DltPolicy<double>,2>, 2-stage ring" if a.precision == "f64" else "DltX2Tile (FFMA2)")
                                                               if a.mode == "matrix" else "RayTableTile<RayPolicy>")),
             "algorithmic_bytes_per_frame": 8 * N_CAMS + 12, "kernel_ms": kernel_ms}
 
