@@ -301,16 +301,18 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
     }
   }
   // one frame per thread; the solver is a compile-time choice of the tile (the scalar policy serves the tails)
-  using LMT = RayTableTile<double, true>;
-  using CFT = RayTableTile<double, false, 2>;  // closed form: two frames per thread (2.41 vs 2.50 ms per 100 M frames)
+  // two frames per thread in both solvers (independent chains for the FP64 pipe): LM 4.70 -> 4.44 ms, closed form
+  // 2.50 -> 2.41 ms per 100 M frames
+  using LMT = RayTableTile<double, true, 2>;
+  using CFT = RayTableTile<double, false, 2>;
   switch (pixfmt) {
     case PIX_F32:
       // (4- and 6-stage rings measured the same: these two are FP64-pipe-bound)
-      return lm ? launch_streamed<LMT, P64, PIX_F32, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
+      return lm ? launch_streamed<LMT, P64, PIX_F32, 2, 2, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
                 : launch_streamed<CFT, P64, PIX_F32, 2, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
     case PIX_F64: return launch_streamed<LMT, P64, PIX_F64, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
     default:
-      return lm ? launch_streamed<LMT, P64, PIX_U16, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
+      return lm ? launch_streamed<LMT, P64, PIX_U16, 2, 2, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
                 : launch_streamed<CFT, P64, PIX_U16, 2, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
   }
 }
