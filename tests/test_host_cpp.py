@@ -126,6 +126,23 @@ def test_cli_end_to_end(host_bins, tmp_path, kind, golden, frames, drones, data)
 
 
 @pytest.mark.gpu
+def test_cli_frame_sharded_classifier(host_bins, tmp_path):
+    """TRI_B200_GPUS=3 ./main ...: the C++ DroneClassifier adapter shards the sequence over three engines
+    (tri_classify_multi) -- same dump as the golden vectors."""
+    csv_dir = tmp_path / "data"
+    csv_dir.mkdir()
+    nc, nf = write_csvs(str(csv_dir), G + "/S09_D6_dets.npz", 120)
+    env = dict(os.environ, TRI_B200_GPUS="3")
+    r = subprocess.run([host_bins[1], G + "/S09_D6_cameras.xml", str(csv_dir), "--n_drones", "6", "--triangulator", "matrix",
+                        "--dump", str(tmp_path / "dump.bin")], capture_output=True, text=True, cwd=str(tmp_path), env=env)
+    assert r.returncode == 0, r.stderr
+    g = np.load(G + "/golden_S09_D6_classify_matrix.npz")
+    p, a, ph = read_dump(str(tmp_path / "dump.bin"))
+    assert np.array_equal(a, g["assign"]) and np.array_equal(ph, g["phase"])
+    np.testing.assert_allclose(p, g["paths"], rtol=1e-9, atol=1e-5)
+
+
+@pytest.mark.gpu
 def test_cli_rejects_unknown_triangulator(host_bins, tmp_path):
     csv_dir = tmp_path / "data"
     csv_dir.mkdir()
