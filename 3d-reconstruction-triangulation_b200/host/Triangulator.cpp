@@ -68,12 +68,7 @@ std::pair<cv::Point3d, double> Triangulator::triangulatePoint(std::vector<CamPoi
   return triangulatePointsOfSubsets({images})[0];
 }
 
-std::vector<cv::Point3d> Triangulator::triangulatePoints(std::vector<std::vector<cv::Point2d>> points) {
-  // MatrixTriangulator.cpp:72-76 / RayTriangulator.cpp:54-58
-  for (size_t i = 1; i < points.size(); i++)
-    if (points[i - 1].size() != points[i].size()) throw std::runtime_error("Every camera should have the same number of points");
-  const int64_t n_frames = points.empty() ? 0 : (int64_t)points[0].size();
-  const int n_rows = (int)points.size();
+unsigned Triangulator::pixelFormatFor(const std::vector<std::vector<cv::Point2d>>& points) {
   // pack [cam][frame] pixel pairs in the narrowest format that holds every value exactly: ushort2 (integer pixels
   // below 65535 -- what DetectionsContainer::readFiles produces, DetectionsContainer.cpp:36 -- with 0xFFFF,0xFFFF
   // for a pair the reference would skip, MatrixTriangulator.cpp:86), float2, else double2
@@ -88,6 +83,17 @@ std::vector<cv::Point3d> Triangulator::triangulatePoints(std::vector<std::vector
     if (!exact32) break;
   }
   exact16 = exact16 && exact32;
+  return exact16 ? (unsigned)TRI_PIX_U16 : exact32 ? 0u : (unsigned)TRI_PIX_F64;
+}
+
+std::vector<cv::Point3d> Triangulator::triangulatePoints(std::vector<std::vector<cv::Point2d>> points) {
+  // MatrixTriangulator.cpp:72-76 / RayTriangulator.cpp:54-58
+  for (size_t i = 1; i < points.size(); i++)
+    if (points[i - 1].size() != points[i].size()) throw std::runtime_error("Every camera should have the same number of points");
+  const int64_t n_frames = points.empty() ? 0 : (int64_t)points[0].size();
+  const int n_rows = (int)points.size();
+  const unsigned fmt = pixelFormatFor(points);
+  const bool exact16 = fmt == TRI_PIX_U16, exact32 = fmt != TRI_PIX_F64;
   std::vector<double> xyz(3 * (size_t)n_frames);
   tri_batch_out out{};
   out.xyz_f64 = xyz.data();

@@ -34,6 +34,10 @@ class Triangulator {
   // many subsets in one launch (what a batched caller of triangulatePoint should use)
   std::vector<std::pair<cv::Point3d, double>> triangulatePointsOfSubsets(const std::vector<std::vector<CamPointPair>>& items);
 
+  // narrowest pixel format of the C ABI that holds every value of `points` exactly: TRI_PIX_U16 (integer pixels
+  // below 65535; a pair with x == -1 or y == -1 becomes the missing marker), 0 (float2) or TRI_PIX_F64
+  static unsigned pixelFormatFor(const std::vector<std::vector<cv::Point2d>>& points);
+
   // :58 -- distance of `point` to the pixel ray of `pair`
   static double getDistFromRay(CamPointPair pair, cv::Point3d point);
 

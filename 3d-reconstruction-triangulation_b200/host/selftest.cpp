@@ -3,6 +3,7 @@
 #include <cstdio>
 
 #include "DetectionsContainer.h"
+#include "Triangulator.h"
 #include "utils.h"
 
 int main(int argc, const char** argv) {
@@ -26,6 +27,15 @@ int main(int argc, const char** argv) {
   std::vector<double> xy;
   box.toCSR(offs, xy);
   std::printf("csr %zu %zu %d\n", offs.size(), xy.size() / 2, offs.back());
+  // the pixel format the batch adapter packs (no engine call): ushort2 for integer detections incl. the sentinel,
+  // float2 off the integer grid or out of the 16-bit range, double2 when a value is not a float
+  using Pts = std::vector<std::vector<cv::Point2d>>;
+  const Pts ints = {{{12, 7}, {-1, -1}, {1919, 1079}}, {{0, 0}, {-1, 5}, {65534, 3}}};
+  Pts big = ints, frac = ints, neg = ints, dbl = ints;
+  big[1][2].x = 65535; frac[0][0].x = 12.25; neg[0][0].y = -2; dbl[0][0].x = 12.000000001;
+  std::printf("pixfmt %u %u %u %u %u %u\n", Triangulator::pixelFormatFor(ints), Triangulator::pixelFormatFor(big),
+              Triangulator::pixelFormatFor(frac), Triangulator::pixelFormatFor(neg), Triangulator::pixelFormatFor(dbl),
+              Triangulator::pixelFormatFor(Pts()));
   for (const auto& cam : cams) delete cam;
   return 0;
 }

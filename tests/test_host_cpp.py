@@ -43,6 +43,8 @@ def test_cpp_loaders_match_python_host_and_twin(host_bins):
     assert len({len(want[c][f]) for c in range(n_cam) for f in range(n_frames)}) > 1  # ragged detection counts
     n_det = sum(len(want[c][f]) for c in range(n_cam) for f in range(n_frames))
     assert [l for l in out if l.startswith("csr")][0] == "csr %d %d %d" % (n_cam * (n_frames + 1), n_det, n_det)
+    # the batch adapter's packing decision: ushort2 (TRI_PIX_U16) / float2 (0) / double2 (TRI_PIX_F64)
+    assert [l for l in out if l.startswith("pixfmt")][0] == "pixfmt %d 0 0 0 %d %d" % (T.PIX_U16, T.PIX_F64, T.PIX_U16)
 
 
 def test_cpp_csv_reader_gaps_and_truncation(host_bins, tmp_path):
