@@ -863,6 +863,7 @@ extern "C" int tri_classify_multi(tri_engine* const* engines, int n_engines, int
   if (n_engines == 1) return tri_classify(engines[0], mode, flags, n_drones, det_offsets, dets_xy, n_frames, out_paths, out_assign, out_phase, stats);
   if (n_frames < 0 || !out_paths || (n_frames > 0 && !det_offsets)) return fail(TRI_ERR_ARG, "bad arguments");
   if (n_drones < 1 || n_drones > TRI_MAX_DRONES) return fail(TRI_ERR_ARG, "n_drones must be in [1, TRI_MAX_DRONES]");
+  if (n_frames == 0) { if (stats) memset(stats, 0, sizeof(*stats)); return TRI_OK; }
   const int C = engines[0]->n_cams;
   auto cut = [&](int g) { return (int)((int64_t)n_frames * g / n_engines); };
   // per-shard CSR: offsets rebased to the shard, detections gathered camera by camera
