@@ -132,6 +132,44 @@ static cudaError_t upload_ray_table(RayFold<T>& f, int n_cams) {
   return err;
 }
 
+// DltRig<T>::absent (host copy): per group of 8 cameras and per 8-bit set m, what the cameras of m add to the normal
+// equations at the canonical pixel (x = y = 0 relative to the rig's pixel origin: rows P[r,0:3], rhs -P[r,3]), accumulated
+// in camera order with the kernels' own fma sequence (acc_row, tri_matrix.cu).
+static inline double fma_h(double a, double b, double c) { return fma(a, b, c); }
+static inline float fma_h(float a, float b, float c) { return fmaf(a, b, c); }
+template <typename T>
+static std::vector<T> dlt_absent_table(const DltRig<T>& r, int n_cams) {
+  const int groups = (n_cams + 7) / 8;
+  std::vector<T> tab((size_t)groups * 256 * DLT_TABLE_ROW, (T)0);
+  for (int g = 0; g < groups; g++)
+    for (int m = 0; m < 256; m++) {
+      T M[6] = {0, 0, 0, 0, 0, 0}, v[3] = {0, 0, 0};
+      for (int k = 0; k < 8 && 8 * g + k < n_cams; k++) {
+        if (!(m >> k & 1)) continue;
+        const T* P = r.P[8 * g + k];
+        for (int row = 0; row < 2; row++) {
+          const T a0 = P[4 * row], a1 = P[4 * row + 1], a2 = P[4 * row + 2], b = -P[4 * row + 3];
+          M[0] = fma_h(a0, a0, M[0]); M[1] = fma_h(a0, a1, M[1]); M[2] = fma_h(a0, a2, M[2]); v[0] = fma_h(a0, b, v[0]);
+          M[3] = fma_h(a1, a1, M[3]); M[4] = fma_h(a1, a2, M[4]); v[1] = fma_h(a1, b, v[1]);
+          M[5] = fma_h(a2, a2, M[5]); v[2] = fma_h(a2, b, v[2]);
+        }
+      }
+      T* row = &tab[((size_t)g * 256 + m) * DLT_TABLE_ROW];
+      for (int k = 0; k < 6; k++) row[k] = M[k];
+      for (int k = 0; k < 3; k++) row[6 + k] = v[k];
+    }
+  return tab;
+}
+template <typename T>
+static cudaError_t upload_dlt_table(DltRig<T>& r, int n_cams) {
+  const std::vector<T> tab = dlt_absent_table(r, n_cams);
+  T* d = nullptr;
+  cudaError_t err = cudaMalloc((void**)&d, tab.size() * sizeof(T));
+  if (err == cudaSuccess) err = cudaMemcpy(d, tab.data(), tab.size() * sizeof(T), cudaMemcpyHostToDevice);
+  r.absent = d;
+  return err;
+}
+
 static void build_rigs(tri_engine* e) {
   memset(&e->fold64, 0, sizeof(e->fold64));
   memset(&e->fold32, 0, sizeof(e->fold32));
@@ -196,14 +234,18 @@ static int check_batch_args(tri_engine* e, int mode, unsigned flags, const void*
       return fail(TRI_ERR_DIM, "ray mode: more pixel rows than cameras");
     *n_use = n_point_cams;
   }
-  (void)flags;
+#ifndef TRI_TUNING
+  if (flags & TRI_DEBUG_STREAM) return fail(TRI_ERR_ARG, "TRI_DEBUG_STREAM is a measurement aid of the tuning build (make -C csrc tuning)");
+#endif
   return TRI_OK;
 }
 
 static int launch_batch(tri_engine* e, LaunchCtx ctx, int mode, unsigned flags, int fmt, const void* d_xy, int n_use,
                         int64_t n_frames, int64_t cam_stride, const BatchOut& out) {
   cudaError_t err;
+#ifdef TRI_TUNING
   ctx.debug_stream = (flags & TRI_DEBUG_STREAM) != 0;
+#endif
   if (mode == TRI_MATRIX) {
     err = launch_dlt(ctx, (flags & TRI_F32) != 0, fmt, e->rig64, e->rig32, d_xy, n_use, n_frames, cam_stride, out);
   } else {
@@ -264,11 +306,15 @@ int tri_create(int n_cams, const tri_camera* cams, int device, tri_engine** out)
   e->device = device;
   e->n_cams = n_cams;
   e->sm_count = prop.multiProcessorCount;
+#ifdef TRI_TUNING
   if (const char* v = getenv("TRI_VARIANT")) e->variant = atoi(v);
+#endif
   memcpy(e->cams, cams, sizeof(tri_camera) * n_cams);
   build_rigs(e);
-  cudaError_t err = cudaMalloc((void**)&e->d_first_bad, sizeof(unsigned long long));
-  if (err == cudaSuccess) err = cudaMemset(e->d_first_bad, 0xff, sizeof(unsigned long long));
+  cudaError_t err = cudaMalloc((void**)&e->d_first_bad, 2 * sizeof(unsigned long long));
+  if (err == cudaSuccess) err = cudaMemset(e->d_first_bad, 0xff, 2 * sizeof(unsigned long long));
+  if (err == cudaSuccess) err = upload_dlt_table(e->rig64, n_cams);
+  if (err == cudaSuccess) err = upload_dlt_table(e->rig32, n_cams);
   if (err == cudaSuccess) err = upload_ray_table(e->fold64, n_cams);
   if (err == cudaSuccess) err = upload_ray_table(e->fold32, n_cams);
   if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
@@ -295,6 +341,8 @@ void tri_destroy(tri_engine* e) {
   if (e->d_scratch) cudaFree(e->d_scratch);
   if (e->stream) cudaStreamDestroy(e->stream);
   if (e->d_first_bad) cudaFree(e->d_first_bad);
+  if (e->rig64.absent) cudaFree(const_cast<double*>(e->rig64.absent));
+  if (e->rig32.absent) cudaFree(const_cast<float*>(e->rig32.absent));
   if (e->fold64.mask_table) cudaFree(const_cast<double*>(e->fold64.mask_table));
   if (e->fold32.mask_table) cudaFree(const_cast<float*>(e->fold32.mask_table));
   delete e;
@@ -401,7 +449,9 @@ int tri_triangulate_points(tri_engine* e, int mode, unsigned flags, const void* 
   // chunk: large enough to run the copy engines at full rate, small enough to pipeline
   int64_t chunk = n_frames >= (16 << 20) ? (4 << 20) : (1 << 20);  // measured: 4 Mi-frame chunks run PCIe at 63 GB/s, 1 Mi at 60.6
   if (mode == TRI_RAY && (flags & TRI_RAY_REFERENCE_LM)) chunk = 1 << 18;
-  if (const char* v = getenv("TRI_CHUNK_FRAMES")) chunk = std::max<int64_t>(2, atoll(v) / 2 * 2);  // tuning override
+#ifdef TRI_TUNING
+  if (const char* v = getenv("TRI_CHUNK_FRAMES")) chunk = std::max<int64_t>(2, atoll(v) / 2 * 2);
+#endif
   if (n_frames <= chunk) chunk = (n_frames + 1) / 2 * 2;  // one chunk
   const size_t in_row = align_up((size_t)chunk * pb, 256);
   const size_t o_xyz32 = 0;
@@ -415,37 +465,50 @@ int tri_triangulate_points(tri_engine* e, int mode, unsigned flags, const void* 
     if ((st = ensure(&e->slots[i].d_in, &e->slots[i].in_cap, in_row * std::max(n_use, 1))) != TRI_OK) return st;
     if ((st = ensure(&e->slots[i].d_out, &e->slots[i].out_cap, out_bytes)) != TRI_OK) return st;
   }
-  TRI_CUDA(cudaMemsetAsync(e->d_first_bad, 0xff, sizeof(unsigned long long), e->slots[0].stream));
+  unsigned long long* latch = e->d_first_bad + 1;  // the host path's own latch: a pending one of the device entry point stays
+  TRI_CUDA(cudaMemsetAsync(latch, 0xff, sizeof(unsigned long long), e->slots[0].stream));
   TRI_CUDA(cudaStreamSynchronize(e->slots[0].stream));
   const char* src = static_cast<const char*>(xy);
-  int k = 0;
-  for (int64_t f0 = 0; f0 < n_frames; f0 += chunk, k++) {
-    Slot& s = e->slots[k % n_slots];
-    const int64_t n = std::min(chunk, n_frames - f0);
-    TRI_CUDA(cudaStreamSynchronize(s.stream));  // slot free (its previous D2H has landed)
-    for (int c = 0; c < n_use; c++)
-      TRI_CUDA(cudaMemcpyAsync(s.d_in + (size_t)c * in_row, src + ((size_t)c * cam_stride + f0) * pb, (size_t)n * pb,
-                               cudaMemcpyHostToDevice, s.stream));
-    BatchOut o{out->xyz_f32 ? (float*)(s.d_out + o_xyz32) : nullptr, out->xyz_f64 ? (double*)(s.d_out + o_xyz64) : nullptr,
-               out->mask ? (uint32_t*)(s.d_out + o_mask) : nullptr, out->err ? (double*)(s.d_out + o_err) : nullptr,
-               out->iters ? (int32_t*)(s.d_out + o_iters) : nullptr};
-    if (n_use == 0) {
-      TRI_CUDA(cudaMemsetAsync(s.d_out, 0, out_bytes, s.stream));
-      TRI_CUDA(cudaMemsetAsync(e->d_first_bad, 0, sizeof(unsigned long long), s.stream));
-    } else if ((st = launch_batch(e, e->ctx(s.stream, f0), mode, flags, fmt, s.d_in, n_use, n, (int64_t)(in_row / pb), o)) != TRI_OK) {
-      return st;
+  // the chunk loop; on any failure the copies already queued into the caller's buffers are drained before returning
+  auto run = [&]() -> int {
+    int k = 0;
+    for (int64_t f0 = 0; f0 < n_frames; f0 += chunk, k++) {
+      Slot& s = e->slots[k % n_slots];
+      const int64_t n = std::min(chunk, n_frames - f0);
+      TRI_CUDA(cudaStreamSynchronize(s.stream));  // slot free (its previous D2H has landed)
+      for (int c = 0; c < n_use; c++)
+        TRI_CUDA(cudaMemcpyAsync(s.d_in + (size_t)c * in_row, src + ((size_t)c * cam_stride + f0) * pb, (size_t)n * pb,
+                                 cudaMemcpyHostToDevice, s.stream));
+      BatchOut o{out->xyz_f32 ? (float*)(s.d_out + o_xyz32) : nullptr, out->xyz_f64 ? (double*)(s.d_out + o_xyz64) : nullptr,
+                 out->mask ? (uint32_t*)(s.d_out + o_mask) : nullptr, out->err ? (double*)(s.d_out + o_err) : nullptr,
+                 out->iters ? (int32_t*)(s.d_out + o_iters) : nullptr};
+      if (n_use == 0) {
+        TRI_CUDA(cudaMemsetAsync(s.d_out, 0, out_bytes, s.stream));
+        TRI_CUDA(cudaMemsetAsync(latch, 0, sizeof(unsigned long long), s.stream));
+      } else {
+        const int st2 = launch_batch(e, e->ctx(s.stream, f0, true), mode, flags, fmt, s.d_in, n_use, n, (int64_t)(in_row / pb), o);
+        if (st2 != TRI_OK) return st2;
+      }
+      if (out->xyz_f32) TRI_CUDA(cudaMemcpyAsync(out->xyz_f32 + 3 * f0, o.xyz_f32, (size_t)n * 12, cudaMemcpyDeviceToHost, s.stream));
+      if (out->xyz_f64) TRI_CUDA(cudaMemcpyAsync(out->xyz_f64 + 3 * f0, o.xyz_f64, (size_t)n * 24, cudaMemcpyDeviceToHost, s.stream));
+      if (out->mask) TRI_CUDA(cudaMemcpyAsync(out->mask + f0, o.mask, (size_t)n * 4, cudaMemcpyDeviceToHost, s.stream));
+      if (out->err) TRI_CUDA(cudaMemcpyAsync(out->err + f0, o.err, (size_t)n * 8, cudaMemcpyDeviceToHost, s.stream));
+      if (out->iters) TRI_CUDA(cudaMemcpyAsync(out->iters + f0, o.iters, (size_t)n * 4, cudaMemcpyDeviceToHost, s.stream));
     }
-    if (out->xyz_f32) TRI_CUDA(cudaMemcpyAsync(out->xyz_f32 + 3 * f0, o.xyz_f32, (size_t)n * 12, cudaMemcpyDeviceToHost, s.stream));
-    if (out->xyz_f64) TRI_CUDA(cudaMemcpyAsync(out->xyz_f64 + 3 * f0, o.xyz_f64, (size_t)n * 24, cudaMemcpyDeviceToHost, s.stream));
-    if (out->mask) TRI_CUDA(cudaMemcpyAsync(out->mask + f0, o.mask, (size_t)n * 4, cudaMemcpyDeviceToHost, s.stream));
-    if (out->err) TRI_CUDA(cudaMemcpyAsync(out->err + f0, o.err, (size_t)n * 8, cudaMemcpyDeviceToHost, s.stream));
-    if (out->iters) TRI_CUDA(cudaMemcpyAsync(out->iters + f0, o.iters, (size_t)n * 4, cudaMemcpyDeviceToHost, s.stream));
+    for (int i = 0; i < n_slots; i++) TRI_CUDA(cudaStreamSynchronize(e->slots[i].stream));
+    return TRI_OK;
+  };
+  if ((st = run()) != TRI_OK) {
+    const std::string why = g_error;
+    for (int i = 0; i < n_slots; i++) cudaStreamSynchronize(e->slots[i].stream);  // nothing is left in flight into the caller's memory
+    cudaMemset(latch, 0xff, sizeof(unsigned long long));
+    cudaGetLastError();
+    return fail(st, why);
   }
-  for (int i = 0; i < n_slots; i++) TRI_CUDA(cudaStreamSynchronize(e->slots[i].stream));
   unsigned long long v = 0;
-  TRI_CUDA(cudaMemcpy(&v, e->d_first_bad, sizeof(v), cudaMemcpyDeviceToHost));
+  TRI_CUDA(cudaMemcpy(&v, latch, sizeof(v), cudaMemcpyDeviceToHost));
   if (v != ~0ull) {
-    TRI_CUDA(cudaMemset(e->d_first_bad, 0xff, sizeof(v)));
+    TRI_CUDA(cudaMemset(latch, 0xff, sizeof(v)));
     if (first_bad_frame) *first_bad_frame = (int64_t)v;
     if (!(flags & TRI_ALLOW_TOO_FEW))
       return fail(TRI_ERR_TOO_FEW, mode == TRI_MATRIX ? "Too few rays are found" : "Too few detections are found");

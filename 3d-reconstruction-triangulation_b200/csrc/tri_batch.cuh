@@ -9,7 +9,8 @@
 // per-frame solve is a policy class S:
 //     S::T, S::Rig (a __grid_constant__ parameter: operands come from the constant bank), S::Acc,
 //     S::add(rig, c, x, y, valid, acc)     one view into the accumulator (a no-op when !valid)
-//     S::solve(rig, acc, n, X, opt, iters) the per-frame solve, X in rig coordinates
+//     S::solve(rig, acc, mask, n, X, opt, iters) the per-frame solve, X in rig coordinates (mask = validity bits:
+//                                          the FP64 DLT takes its absent-view correction from a table row)
 //     S::residual(rig, c, x, y, X)         that view's contribution to the reported error
 //     S::error(sum, n)                     the reported error from the summed contributions
 //     S::to_world(rig, X)
@@ -125,7 +126,7 @@ batch_kernel(const __grid_constant__ typename S::Rig rig, const char* __restrict
 #pragma unroll
       for (int j = 0; j < FPT; j++) {
         n[j] = __popc(mask[j]);
-        if (n[j] >= 2) S::solve(rig, acc[j], n[j], X[j], opt, it[j]);
+        if (n[j] >= 2) S::solve(rig, acc[j], mask[j], n[j], X[j], opt, it[j]);
       }
       if (out.err) {
 #pragma unroll
@@ -145,7 +146,7 @@ batch_kernel(const __grid_constant__ typename S::Rig rig, const char* __restrict
 #pragma unroll
       for (int j = 0; j < FPT; j++) {
         n[j] = __popc(mask[j]);
-        if (n[j] >= 2) S::solve(rig, acc[j], n[j], X[j], opt, it[j]);
+        if (n[j] >= 2) S::solve(rig, acc[j], mask[j], n[j], X[j], opt, it[j]);
       }
       if (out.err) {
         for (int c = 0; c < nc; c++) {
@@ -207,7 +208,7 @@ batch_single_kernel(const __grid_constant__ typename S::Rig rig, const char* __r
   }
   const int n = __popc(mask);
   if (n >= 2) {
-    S::solve(rig, acc, n, X, opt, it);
+    S::solve(rig, acc, mask, n, X, opt, it);
     if (out.err)
       for (int c = 0; c < n_use; c++) {
         T x, y; bool ok;

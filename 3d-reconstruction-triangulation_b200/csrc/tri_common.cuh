@@ -11,12 +11,18 @@ namespace tri {
 // instruction can take its camera operand straight from the constant bank (no loads, no registers).
 
 // MatrixTriangulator rows (MatrixTriangulator.cpp:16-49): a = P[r,0:3] - u*P[2,0:3], b = u*P[2,3] - P[r,3]
+constexpr int DLT_TABLE_ROW = 12;  // M00 M01 M02 M11 M12 M22 v0 v1 v2 + padding (16-byte vector loads)
 template <typename T>
 struct __align__(16) DltRig {
   T P[TRI_MAX_CAMS][12];  // FP64: cameraPerspectiveMatrix as is.  FP32: world origin moved to the
                           // rig centre and pixel origin to (cx,cy) (algebraically the same rows)
   T pix0[TRI_MAX_CAMS][2];  // pixel origin subtracted before use (0 for FP64)
   T origin[3];              // world origin added back to the solution (0 for FP64)
+  // device, [TRI_MAX_CAMS / 8][256][DLT_TABLE_ROW]: row (g, m) = what the cameras 8g + {bits of m} add to the normal
+  // equations at the canonical pixel (the rig's pixel origin) -- absent views are accumulated there and this row is
+  // subtracted afterwards (tri_matrix.cu); built by the host with the kernels' own fma sequence
+  const T* absent;
+  int n_use;  // pixel rows of this launch (set per launch)
 };
 
 // Ray constants (Triangulator.cpp:15-55).  depth = 1/tan(fovy*0.0174533/2) is evaluated on the
@@ -63,16 +69,6 @@ __host__ __device__ inline int pix_bytes(int fmt) { return fmt == PIX_F32 ? 8 : 
 // The sentinel test of MatrixTriangulator.cpp:86 / RayTriangulator.cpp:66 on the stored type.
 __device__ __forceinline__ bool pix_valid(float x, float y) { return x != -1.0f && y != -1.0f; }
 __device__ __forceinline__ bool pix_valid(double x, double y) { return x != -1.0 && y != -1.0; }
-
-// Exact float -> double widening on the integer pipe (F2F.F64.F32 runs at a quarter of the DFMA
-// rate; this keeps the FP64 pipe for the solve).  Zero/denormal/inf/nan take the slow path.
-__device__ __forceinline__ double widen(float f) {
-  unsigned u = __float_as_uint(f);
-  unsigned e = (u >> 23) & 0xffu;
-  if (e == 0u || e == 255u) return (double)f;
-  unsigned hi = (u & 0x80000000u) | (((u & 0x7fffffffu) >> 3) + 0x38000000u);
-  return __hiloint2double((int)hi, (int)(u << 29));
-}
 
 template <typename T> __device__ __forceinline__ T to_real(float v);
 template <> __device__ __forceinline__ float to_real<float>(float v) { return v; }
@@ -143,8 +139,10 @@ struct LaunchCtx {
   unsigned long long* d_first_bad;  // latched index of the first frame with < 2 views
   int64_t frame_base;               // global index of frame 0 of this launch (chunked host path)
   int64_t* launches;
-  bool debug_stream = false;
-  int variant = 0;  // TRI_VARIANT (tuning experiments)  // TRI_DEBUG_STREAM: memory-roofline probe instead of the solve
+#ifdef TRI_TUNING  // tuning builds only (make tuning): never compiled into libtri_b200.so
+  bool debug_stream = false;  // TRI_DEBUG_STREAM: memory-roofline probe instead of the solve
+  int variant = 0;            // TRI_VARIANT environment variable: kernel shape under A/B measurement
+#endif
 };
 
 enum RaySolver { RAY_ANALYTIC_LM = 0, RAY_REFERENCE_LM = 1, RAY_CLOSED_FORM = 2 };

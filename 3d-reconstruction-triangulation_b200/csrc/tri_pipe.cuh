@@ -1,19 +1,14 @@
-// tri_pipe.cuh -- persistent, TMA-fed streaming kernel for the batched triangulatePoints hot path.
+// tri_pipe.cuh -- persistent streaming kernels of the batched triangulatePoints hot path.
 //
-// The first generation (tri_batch.cuh: load 8 rows -> compute -> store, one tile per CTA) left the
-// memory system idle while a warp computed: ncu (profiles/r1_*) showed 59-61 % DRAM throughput with
-// `long_scoreboard` the top stall and only ~5.6 warps per scheduler to cover it.  Here the loads are
-// decoupled from the math, the Blackwell way:
-//   * grid = SMs x resident CTAs, each CTA walks tiles  t = blockIdx.x, += gridDim.x;
-//   * one elected thread streams a tile's camera rows (contiguous, TILE x 8 B each) into a
-//     STAGES-deep shared-memory ring with 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP), each
-//     stage completing on an mbarrier (expect_tx = bytes of the stage);
-//   * all threads wait on the stage's mbarrier, pull their pixels into registers with conflict-free
-//     LDS.128, release the stage (the producer re-arms it for tile t + STAGES*grid at once) and only
-//     then start the solve -- so STAGES tiles are always in flight per CTA, whatever the math costs;
-//   * the 12-byte points are staged in a double-buffered shared tile and leave as ONE bulk store
-//     (cp.async.bulk.global.shared::cta) per tile.
-// Algorithmic traffic is unchanged: 8 B x cameras in, 12 B out per frame; nothing is re-read.
+// grid = SMs x resident CTAs, each CTA walks tiles t = blockIdx.x, += gridDim.x of BATCH_THREADS x FPT frames; the
+// pixels of the next STAGES tiles are always in flight into a shared-memory ring while the current tile is solved;
+// the 12-byte points leave through a per-warp transpose as 16-byte streaming stores.  Two feeders for the ring:
+//   * stream_kernel: every thread prefetches its own pixels with cp.async (LDGSTS) and waits on its own copy group --
+//     no cross-warp synchronisation at all;
+//   * tma_kernel: a producer warp streams each camera's row segment with 1-D bulk async copies (cp.async.bulk, SASS
+//     UBLKCP) that complete on a per-stage `full` mbarrier; the eight consumer warps wait on it, pull their pixels
+//     into registers and release the stage through an `empty` mbarrier (one arrival per warp) -- no CTA barrier.
+// Algorithmic traffic: 8 B x cameras in, 12 B out per frame; nothing is re-read (profiles/: 7.59 GB per 100 M frames).
 #pragma once
 #include "tri_batch.cuh"
 
@@ -28,6 +23,9 @@ __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarr
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
@@ -96,14 +94,26 @@ __device__ __forceinline__ void solve_sym3_x2(const float2 (&M)[6], const float2
   X2 = mul2(fma2(c02, v[0], fma2(c12, v[1], mul2(c22, v[2]))), inv);
 }
 
+// ---- tile interface of the streaming kernels ------------------------------------------------------
+// A tile solver TS turns the raw pixels of FPT consecutive frames (one RawPix per camera) into points:
+//     TS::FPT, TS::Rig (a __grid_constant__ parameter), TS::Real (the arithmetic type of the result)
+//     TS::CONST_BYTES, TS::stage_consts(rig, dst, tid)   optional: rig constants the tile wants in shared memory
+//     TS::run<NC, PIX, WIDE>(rig, sc, raw, opt, X, mask, err, iters)     (sc = that shared copy)
+// WIDE is a compile-time switch for the optional outputs of tri_batch_out (double3 points, the `error` of
+// triangulatePoint, LM iterations): the lean instantiation (float3 + mask) is what the throughput metric runs,
+// the wide one serves the C++ adapter, whose interface returns cv::Point3d (Triangulator.h:51-52).
+
 // Tile solver built from a scalar policy (tri_batch.cuh): FPT frames per thread, one after the other.
 template <class S, int FPT_>
 struct PolicyTile {
   static constexpr int FPT = FPT_;
   using Rig = typename S::Rig;
-  template <int NC, int PIX>
-  static __device__ __forceinline__ void run(const Rig& rig, const typename RawPix<PIX, FPT>::type (&raw)[NC], int opt,
-                                             float (&X)[FPT][3], uint32_t (&mask)[FPT]) {
+  using Real = typename S::T;
+  static constexpr int CONST_BYTES = 0;
+  static __device__ __forceinline__ void stage_consts(const Rig&, unsigned char*, int) {}
+  template <int NC, int PIX, bool WIDE>
+  static __device__ __forceinline__ void run(const Rig& rig, const unsigned char*, const typename RawPix<PIX, FPT>::type (&raw)[NC], int opt,
+                                             Real (&X)[FPT][3], uint32_t (&mask)[FPT], double (&err)[FPT], int (&iters)[FPT]) {
     using T = typename S::T;
     typename S::Acc acc[FPT];
 #pragma unroll
@@ -117,147 +127,34 @@ struct PolicyTile {
     }
 #pragma unroll
     for (int j = 0; j < FPT; j++) {
-      T P[3] = {0, 0, 0};
-      int it = 0;
-      if (__popc(mask[j]) >= 2) { S::solve(rig, acc[j], __popc(mask[j]), P, opt, it); S::to_world(rig, P); }
-      X[j][0] = (float)P[0]; X[j][1] = (float)P[1]; X[j][2] = (float)P[2];
+      X[j][0] = X[j][1] = X[j][2] = 0;
+      iters[j] = 0;
+      err[j] = 0;
+      const int n = __popc(mask[j]);
+      if (n >= 2) {
+        S::solve(rig, acc[j], mask[j], n, X[j], opt, iters[j]);
+        if constexpr (WIDE) {
+          T e = 0;
+#pragma unroll
+          for (int c = 0; c < NC; c++) {
+            const Views<T, PIX, FPT> w = decode<T, PIX, FPT>(raw[c]);
+            if (w.v[j]) e += S::residual(rig, c, w.x[j], w.y[j], X[j]);
+          }
+          err[j] = S::error(e, n);
+        }
+        S::to_world(rig, X[j]);
+      }
     }
   }
 };
 
-template <int NC, int PIX, int FPT, int STAGES, int OUTBUFS = 2>
-struct PipeLayout {
-  static constexpr int TILE = BATCH_THREADS * FPT;
-  static constexpr int PB = PIX == PIX_F32 ? 8 : 4;
-  static constexpr int ROW = TILE * PB;
-  static constexpr int STAGE = NC * ROW;
-  static constexpr int OUT = TILE * 12;
-  static constexpr int BYTES = STAGES * STAGE + OUTBUFS * OUT + STAGES * 8;
-};
-
-template <class TS, int NC, int PIX, int STAGES, int MINB, int OUTBUFS>
-__global__ void __launch_bounds__(BATCH_THREADS, MINB)
-pipe_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restrict__ xy, int64_t row_bytes, int64_t n_tiles,
-            BatchOut out, int opt, unsigned long long* first_bad, int64_t frame_base) {
-  constexpr int FPT = TS::FPT;
-  using L = PipeLayout<NC, PIX, FPT, STAGES, OUTBUFS>;
-  using Raw = typename RawPix<PIX, FPT>::type;
-  extern __shared__ __align__(128) unsigned char smem[];
-  unsigned char* in = smem;
-  float* outb = reinterpret_cast<float*>(smem + STAGES * L::STAGE);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * L::STAGE + OUTBUFS * L::OUT);
-  const int tid = threadIdx.x;
-  const int64_t stride = gridDim.x;
-  int64_t tile = blockIdx.x;
-  // Rig constants live in shared memory: operands arrive by broadcast LDS.128 on the (idle) LSU pipe.
-  // Read straight from the parameter bank every FMA row needs a second constant in a register, and
-  // those LDCs saturated the ADU pipe (ncu r1c: adu 53-68 %, the top pipe).
-  __shared__ __align__(16) typename TS::Rig srig;
-  for (int i = tid; i < (int)(sizeof(typename TS::Rig) / 4); i += BATCH_THREADS)
-    reinterpret_cast<int*>(&srig)[i] = reinterpret_cast<const int*>(&rig)[i];
-
-  auto issue = [&](int s, int64_t t) {  // producer (thread 0): one stage = NC contiguous row segments
-    mbar_expect_tx(&full[s], L::STAGE);
-    const char* src = xy + t * L::ROW;
-#pragma unroll
-    for (int c = 0; c < NC; c++) bulk_load(in + s * L::STAGE + c * L::ROW, src + c * row_bytes, L::ROW, &full[s]);
-  };
-
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; s++) mbar_init(&full[s], 1);
-    fence_barrier_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-#pragma unroll
-    for (int s = 0; s < STAGES; s++)
-      if (tile + s * stride < n_tiles) issue(s, tile + s * stride);
-  }
-
-  for (int k = 0; tile < n_tiles; k++, tile += stride) {
-    const int s = k % STAGES;
-    mbar_wait(&full[s], (uint32_t)((k / STAGES) & 1));
-    Raw raw[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) raw[c] = reinterpret_cast<const Raw*>(in + s * L::STAGE + c * L::ROW)[tid];
-    if (tid == 0) bulk_wait_read<OUTBUFS - 1>();  // the store that last used this tile's out buffer has drained
-    __syncthreads();                    // every thread holds its pixels: stage s is free again
-    if (tid == 0 && tile + STAGES * stride < n_tiles) issue(s, tile + STAGES * stride);
-
-    float X[FPT][3];
-    uint32_t mask[FPT];
-    TS::template run<NC, PIX>(srig, raw, opt, X, mask);
-
-    const int64_t f0 = tile * L::TILE + (int64_t)tid * FPT;
-#pragma unroll
-    for (int j = 0; j < FPT; j++)
-      if (__popc(mask[j]) < 2) atomicMin(first_bad, (unsigned long long)(frame_base + f0 + j));
-    if (out.mask) {
-      if constexpr (FPT == 2) reinterpret_cast<uint2*>(out.mask)[f0 / 2] = make_uint2(mask[0], mask[1]);
-      else out.mask[f0] = mask[0];
-    }
-    float* ob = outb + (k % OUTBUFS) * (L::OUT / 4) + 3 * FPT * tid;
-    if constexpr (FPT == 2) {
-      float2* o2 = reinterpret_cast<float2*>(ob);
-      o2[0] = make_float2(X[0][0], X[0][1]); o2[1] = make_float2(X[0][2], X[1][0]); o2[2] = make_float2(X[1][1], X[1][2]);
-    } else {
-      ob[0] = X[0][0]; ob[1] = X[0][1]; ob[2] = X[0][2];
-    }
-    fence_proxy_async();  // generic-proxy writes -> visible to the bulk (async-proxy) store
-    __syncthreads();
-    if (tid == 0) {
-      bulk_store(out.xyz_f32 + 3 * tile * L::TILE, outb + (k % OUTBUFS) * (L::OUT / 4), L::OUT);
-      bulk_commit();
-    }
-  }
-  if (tid == 0) bulk_wait_read<0>();
-}
-
-// Launch the pipelined kernel on the full tiles of [0, n_frames); returns the number of frames covered
-// (0 if the layout does not qualify: unaligned rows, optional outputs the lean kernel does not write).
-template <class TS, int PIX, int STAGES, int MINB, int OUTBUFS = 2>
-static cudaError_t launch_pipe(const LaunchCtx& ctx, const typename TS::Rig& rig, const void* d_xy, int n_use, int64_t n_frames,
-                               int64_t cam_stride, const BatchOut& out, int opt, int64_t* covered) {
-  *covered = 0;
-  constexpr int FPT = TS::FPT;
-  constexpr int TILE = BATCH_THREADS * FPT;
-  const char* xy = static_cast<const char*>(d_xy);
-  const int64_t row_bytes = cam_stride * pix_bytes(PIX);
-  const int64_t n_tiles = n_frames / TILE;
-  if (n_tiles == 0 || n_use < 2 || n_use > 8) return cudaSuccess;
-  if (!out.xyz_f32 || out.xyz_f64 || out.err || out.iters) return cudaSuccess;
-  if (((uintptr_t)xy & 15) || (row_bytes & 15) || ((uintptr_t)out.xyz_f32 & 15) || (out.mask && ((uintptr_t)out.mask & 7))) return cudaSuccess;
-  cudaError_t err = cudaSuccess;
-#define TRI_CASE(N)                                                                                                     \
-  case N: {                                                                                                             \
-    auto kern = pipe_kernel<TS, N, PIX, STAGES, MINB, OUTBUFS>;                                                                  \
-    constexpr int bytes = PipeLayout<N, PIX, FPT, STAGES, OUTBUFS>::BYTES;                                                       \
-    err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);                               \
-    if (err != cudaSuccess) return err;                                                                                 \
-    int per_sm = 1;                                                                                                     \
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BATCH_THREADS, bytes);                           \
-    if (err != cudaSuccess) return err;                                                                                 \
-    const int64_t grid = std::min<int64_t>(n_tiles, (int64_t)ctx.sm_count * std::max(per_sm, 1));                       \
-    kern<<<(unsigned)grid, BATCH_THREADS, bytes, ctx.stream>>>(rig, xy, row_bytes, n_tiles, out, opt, ctx.d_first_bad,  \
-                                                               ctx.frame_base);                                         \
-  } break;
-  switch (n_use) { TRI_CASE(2) TRI_CASE(3) TRI_CASE(4) TRI_CASE(5) TRI_CASE(6) TRI_CASE(7) TRI_CASE(8) }
-#undef TRI_CASE
-  ++*ctx.launches;
-  *covered = n_tiles * TILE;
-  return cudaGetLastError();
-}
-
-// ---- generation 3: barrier-free per-thread async pipeline -----------------------------------------
-// ncu on pipe_kernel (profiles/r1c) showed the CTA-wide phases as the limiter: all warps of a CTA hit
-// the math pipe together (stall_math / not_selected) and then idle together at the barriers (16 % of
-// stall samples), so FMA/FP64 pipes and DRAM each sat near 58-61 %.  Here nothing synchronises across
-// warps: every thread prefetches ITS OWN pixels of the next STAGES tiles with cp.async (LDGSTS, 16 B per
-// camera row, fully coalesced per warp) into a private shared-memory slot, waits only on its own
-// cp.async group, pulls the slot into registers, re-arms it, and solves.  Warps drift apart freely, so
+// ---- barrier-free per-thread async pipeline ---------------------------------------------------------
+// Nothing synchronises across warps: every thread prefetches ITS OWN pixels of the next STAGES tiles with
+// cp.async (LDGSTS, 16 B per camera row, fully coalesced per warp) into a private shared-memory slot, waits only
+// on its own cp.async group, pulls the slot into registers, re-arms it, and solves.  Warps drift apart freely, so
 // one warp's memory wait hides under another warp's FMAs.  The 12-byte points are transposed through a
-// per-warp shared tile (__syncwarp only) into coalesced 16-byte streaming stores.
+// per-warp shared tile (__syncwarp only) into coalesced 16-byte streaming stores.  (Measured against it in round
+// 1 and dropped: one tile per CTA with up-front vector loads, and a CTA-synchronous TMA ring -- profiles/r1_*.)
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -271,12 +168,38 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <class TS, int NC, int PIX, int STAGES, int MINB, bool SMEM_RIG>
-__global__ void __launch_bounds__(BATCH_THREADS, MINB)
+// the optional per-frame outputs of FPT consecutive frames starting at f0 (per-thread stores; a warp covers a
+// contiguous range, so every sector is fully written)
+template <int FPT, typename Real>
+__device__ __forceinline__ void store_wide(const BatchOut& out, int64_t f0, const Real (&X)[FPT][3], const double (&err)[FPT],
+                                           const int (&iters)[FPT]) {
+  if (out.xyz_f64) {
+    double* o = out.xyz_f64 + 3 * f0;
+    if constexpr (FPT == 2) {  // 48 B, 16-byte aligned (f0 is even)
+      double2* o2 = reinterpret_cast<double2*>(o);
+      o2[0] = make_double2((double)X[0][0], (double)X[0][1]); o2[1] = make_double2((double)X[0][2], (double)X[1][0]);
+      o2[2] = make_double2((double)X[1][1], (double)X[1][2]);
+    } else {
+      o[0] = (double)X[0][0]; o[1] = (double)X[0][1]; o[2] = (double)X[0][2];
+    }
+  }
+  if (out.err) {
+    if constexpr (FPT == 2) reinterpret_cast<double2*>(out.err)[f0 / 2] = make_double2(err[0], err[1]);
+    else out.err[f0] = err[0];
+  }
+  if (out.iters) {
+    if constexpr (FPT == 2) reinterpret_cast<int2*>(out.iters)[f0 / 2] = make_int2(iters[0], iters[1]);
+    else out.iters[f0] = iters[0];
+  }
+}
+
+template <class TS, int NC, int PIX, int STAGES, int MINB, bool WIDE>
+__global__ void __launch_bounds__(BATCH_THREADS, WIDE ? 1 : MINB)  // the wide instantiation keeps the pixels live for the error pass
 stream_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restrict__ xy, int64_t row_bytes, int64_t n_tiles,
               BatchOut out, int opt, unsigned long long* first_bad, int64_t frame_base) {
   constexpr int FPT = TS::FPT;
   using Raw = typename RawPix<PIX, FPT>::type;
+  using Real = typename TS::Real;
   constexpr int TILE = BATCH_THREADS * FPT;
   constexpr int RB = (int)sizeof(Raw);  // bytes per thread per camera per tile
   extern __shared__ __align__(128) unsigned char smem[];
@@ -286,14 +209,11 @@ stream_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restri
   const int tid = threadIdx.x, lane = tid & 31;
   const int64_t stride = gridDim.x;
   int64_t tile = blockIdx.x;
-
-  __shared__ __align__(16) typename TS::Rig srig_store[1];
-  if constexpr (SMEM_RIG) {
-    for (int i = tid; i < (int)(sizeof(typename TS::Rig) / 4); i += BATCH_THREADS)
-      reinterpret_cast<int*>(&srig_store[0])[i] = reinterpret_cast<const int*>(&rig)[i];
+  unsigned char* sc = smem + STAGES * NC * BATCH_THREADS * RB + (BATCH_THREADS / 32) * (32 * FPT * 12);
+  if constexpr (TS::CONST_BYTES > 0) {  // the only CTA-wide barrier of the kernel, before the first tile
+    TS::stage_consts(rig, sc, tid);
     __syncthreads();
   }
-  const typename TS::Rig& R = SMEM_RIG ? srig_store[0] : rig;
 
   auto prefetch = [&](int s, int64_t t) {
     const char* src = xy + (t * BATCH_THREADS + tid) * RB;
@@ -320,9 +240,11 @@ stream_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restri
     if (tile + STAGES * stride < n_tiles) prefetch(s, tile + STAGES * stride);
     cp_async_commit();
 
-    float X[FPT][3];
+    Real X[FPT][3];
     uint32_t mask[FPT];
-    TS::template run<NC, PIX>(R, raw, opt, X, mask);
+    double err[FPT];
+    int iters[FPT];
+    TS::template run<NC, PIX, WIDE>(rig, sc, raw, opt, X, mask, err, iters);
 
     const int64_t f0 = tile * TILE + (int64_t)tid * FPT;
 #pragma unroll
@@ -332,13 +254,18 @@ stream_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restri
       if constexpr (FPT == 2) reinterpret_cast<uint2*>(out.mask)[f0 / 2] = make_uint2(mask[0], mask[1]);
       else out.mask[f0] = mask[0];
     }
+    if constexpr (WIDE) {
+      store_wide<FPT, Real>(out, f0, X, err, iters);
+      if (!out.xyz_f32) continue;  // uniform
+    }
     // warp-level transpose: 32 x FPT x 12 B contiguous in global memory
     __syncwarp();  // the previous tile's reads of this warp's tile are done
     if constexpr (FPT == 2) {
       float2* o2 = reinterpret_cast<float2*>(outw) + 3 * lane;
-      o2[0] = make_float2(X[0][0], X[0][1]); o2[1] = make_float2(X[0][2], X[1][0]); o2[2] = make_float2(X[1][1], X[1][2]);
+      o2[0] = make_float2((float)X[0][0], (float)X[0][1]); o2[1] = make_float2((float)X[0][2], (float)X[1][0]);
+      o2[2] = make_float2((float)X[1][1], (float)X[1][2]);
     } else {
-      outw[3 * lane] = X[0][0]; outw[3 * lane + 1] = X[0][1]; outw[3 * lane + 2] = X[0][2];
+      outw[3 * lane] = (float)X[0][0]; outw[3 * lane + 1] = (float)X[0][1]; outw[3 * lane + 2] = (float)X[0][2];
     }
     __syncwarp();
     float4* dst = reinterpret_cast<float4*>(out.xyz_f32 + 3 * (tile * TILE + (int64_t)(tid - lane) * FPT));
@@ -350,39 +277,148 @@ stream_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restri
   cp_async_wait<0>();
 }
 
-template <class TS, int PIX, int STAGES, int MINB, bool SMEM_RIG>
-static cudaError_t launch_stream(const LaunchCtx& ctx, const typename TS::Rig& rig, const void* d_xy, int n_use, int64_t n_frames,
-                                 int64_t cam_stride, const BatchOut& out, int opt, int64_t* covered) {
-  *covered = 0;
+
+// ---- warp-specialised TMA feeder ---------------------------------------------------------------------
+constexpr int TMA_THREADS = BATCH_THREADS + 32;  // eight consumer warps + one producer warp
+
+template <class TS, int NC, int PIX, int STAGES, int MINB, bool WIDE>
+__global__ void __launch_bounds__(TMA_THREADS, WIDE ? 1 : MINB)
+tma_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restrict__ xy, int64_t row_bytes, int64_t n_tiles,
+           BatchOut out, int opt, unsigned long long* first_bad, int64_t frame_base) {
   constexpr int FPT = TS::FPT;
-  constexpr int TILE = BATCH_THREADS * FPT;
   using Raw = typename RawPix<PIX, FPT>::type;
-  const char* xy = static_cast<const char*>(d_xy);
-  const int64_t row_bytes = cam_stride * pix_bytes(PIX);
-  const int64_t n_tiles = n_frames / TILE;
-  if (n_tiles == 0 || n_use < 2 || n_use > 8) return cudaSuccess;
-  if (!out.xyz_f32 || out.xyz_f64 || out.err || out.iters) return cudaSuccess;
-  const int align = (int)sizeof(Raw);
-  if (((uintptr_t)xy % align) || (row_bytes % align) || ((uintptr_t)out.xyz_f32 & 15) || (out.mask && ((uintptr_t)out.mask & 7))) return cudaSuccess;
+  using Real = typename TS::Real;
+  constexpr int TILE = BATCH_THREADS * FPT;
+  constexpr int ROW = BATCH_THREADS * (int)sizeof(Raw);  // bytes of one camera's segment of a tile
+  constexpr int STAGE = NC * ROW;
+  extern __shared__ __align__(128) unsigned char smem[];
+  // layout: [STAGES][NC][BATCH_THREADS] Raw | [warps][32 * FPT * 3] float | tile constants | full[STAGES] empty[STAGES]
+  unsigned char* sc = smem + STAGES * STAGE + (BATCH_THREADS / 32) * (32 * FPT * 12);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sc + ((TS::CONST_BYTES + 15) & ~15));
+  uint64_t* empty = full + STAGES;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int64_t stride = gridDim.x;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], BATCH_THREADS / 32); }
+    fence_barrier_init();
+  }
+  if constexpr (TS::CONST_BYTES > 0) if (tid < BATCH_THREADS) TS::stage_consts(rig, sc, tid);
+  __syncthreads();  // the only CTA-wide barrier: before the first tile
+
+  if (tid >= BATCH_THREADS) {  // ---- producer warp: one elected lane keeps the ring full ----
+    if (lane == 0) {
+      int k = 0;
+      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += stride, k++) {
+        const int s = k % STAGES;
+        if (k >= STAGES) mbar_wait(&empty[s], (uint32_t)((k / STAGES - 1) & 1));  // every consumer warp has pulled tile k - STAGES
+        mbar_expect_tx(&full[s], STAGE);
+        const char* src = xy + tile * ROW;
+#pragma unroll
+        for (int c = 0; c < NC; c++) bulk_load(smem + s * STAGE + c * ROW, src + c * row_bytes, ROW, &full[s]);
+      }
+    }
+    return;
+  }
+
+  float* outw = reinterpret_cast<float*>(smem + STAGES * STAGE) + (tid >> 5) * (32 * FPT * 3);
+  int k = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += stride, k++) {
+    const int s = k % STAGES;
+    mbar_wait(&full[s], (uint32_t)((k / STAGES) & 1));
+    Raw raw[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) raw[c] = reinterpret_cast<const Raw*>(smem + s * STAGE + c * ROW)[tid];
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);  // this warp holds its pixels: one of the eight arrivals that free the stage
+
+    Real X[FPT][3];
+    uint32_t mask[FPT];
+    double err[FPT];
+    int iters[FPT];
+    TS::template run<NC, PIX, WIDE>(rig, sc, raw, opt, X, mask, err, iters);
+
+    const int64_t f0 = tile * TILE + (int64_t)tid * FPT;
+#pragma unroll
+    for (int j = 0; j < FPT; j++)
+      if (__popc(mask[j]) < 2) atomicMin(first_bad, (unsigned long long)(frame_base + f0 + j));
+    if (out.mask) {
+      if constexpr (FPT == 2) reinterpret_cast<uint2*>(out.mask)[f0 / 2] = make_uint2(mask[0], mask[1]);
+      else out.mask[f0] = mask[0];
+    }
+    if constexpr (WIDE) {
+      store_wide<FPT, Real>(out, f0, X, err, iters);
+      if (!out.xyz_f32) continue;
+    }
+    __syncwarp();
+    if constexpr (FPT == 2) {
+      float2* o2 = reinterpret_cast<float2*>(outw) + 3 * lane;
+      o2[0] = make_float2((float)X[0][0], (float)X[0][1]); o2[1] = make_float2((float)X[0][2], (float)X[1][0]);
+      o2[2] = make_float2((float)X[1][1], (float)X[1][2]);
+    } else {
+      outw[3 * lane] = (float)X[0][0]; outw[3 * lane + 1] = (float)X[0][1]; outw[3 * lane + 2] = (float)X[0][2];
+    }
+    __syncwarp();
+    float4* dst = reinterpret_cast<float4*>(out.xyz_f32 + 3 * (tile * TILE + (int64_t)(tid - lane) * FPT));
+    const float4* src4 = reinterpret_cast<const float4*>(outw);
+    constexpr int N4 = 32 * FPT * 3 / 4;
+#pragma unroll
+    for (int i = lane; i < N4; i += 32) __stcs(dst + i, src4[i]);
+  }
+}
+
+// which optional outputs the caller wants -> the WIDE instantiation; alignment of whatever is written
+static inline bool wants_wide(const BatchOut& out) { return out.xyz_f64 || out.err || out.iters; }
+static inline bool stream_aligned(const void* xy, int64_t row_bytes, int align, const BatchOut& out) {
+  return !(((uintptr_t)xy % align) || (row_bytes % align) || ((uintptr_t)out.xyz_f32 & 15) || ((uintptr_t)out.xyz_f64 & 15) ||
+           ((uintptr_t)out.mask & 7) || ((uintptr_t)out.err & 15) || ((uintptr_t)out.iters & 7));
+}
+
+template <class TS, int PIX, int STAGES, int MINB, bool WIDE, bool TMA>
+static cudaError_t launch_stream_w(const LaunchCtx& ctx, const typename TS::Rig& rig, const char* xy, int n_use, int64_t n_tiles,
+                                   int64_t row_bytes, const BatchOut& out, int opt) {
+  constexpr int FPT = TS::FPT;
+  using Raw = typename RawPix<PIX, FPT>::type;
   cudaError_t err = cudaSuccess;
 #define TRI_CASE(N)                                                                                                     \
   case N: {                                                                                                             \
-    auto kern = stream_kernel<TS, N, PIX, STAGES, MINB, SMEM_RIG>;                                                      \
-    constexpr int bytes = STAGES * N * BATCH_THREADS * (int)sizeof(Raw) + (BATCH_THREADS / 32) * 32 * FPT * 12;         \
+    auto kern = TMA ? tma_kernel<TS, N, PIX, STAGES, MINB, WIDE> : stream_kernel<TS, N, PIX, STAGES, MINB, WIDE>;        \
+    constexpr int threads = TMA ? TMA_THREADS : BATCH_THREADS;                                                          \
+    constexpr int bytes = STAGES * N * BATCH_THREADS * (int)sizeof(Raw) + (BATCH_THREADS / 32) * 32 * FPT * 12 +         \
+                          ((TS::CONST_BYTES + 15) & ~15) + (TMA ? 2 * STAGES * 8 : 0);                                  \
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);                               \
     if (err != cudaSuccess) return err;                                                                                 \
     int per_sm = 1;                                                                                                     \
-    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BATCH_THREADS, bytes);                           \
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, bytes);                                 \
     if (err != cudaSuccess) return err;                                                                                 \
     const int64_t grid = std::min<int64_t>(n_tiles, (int64_t)ctx.sm_count * std::max(per_sm, 1));                       \
-    kern<<<(unsigned)grid, BATCH_THREADS, bytes, ctx.stream>>>(rig, xy, row_bytes, n_tiles, out, opt, ctx.d_first_bad,  \
-                                                               ctx.frame_base);                                         \
+    kern<<<(unsigned)grid, threads, bytes, ctx.stream>>>(rig, xy, row_bytes, n_tiles, out, opt, ctx.d_first_bad,        \
+                                                         ctx.frame_base);                                               \
   } break;
   switch (n_use) { TRI_CASE(2) TRI_CASE(3) TRI_CASE(4) TRI_CASE(5) TRI_CASE(6) TRI_CASE(7) TRI_CASE(8) }
 #undef TRI_CASE
   ++*ctx.launches;
-  *covered = n_tiles * TILE;
   return cudaGetLastError();
+}
+
+// Launch the streaming kernel on the full tiles of [0, n_frames); *covered = the number of frames it took
+// (0 if the layout does not qualify: unaligned rows or outputs, fewer frames than a tile).
+template <class TS, int PIX, int STAGES, int MINB, bool TMA = false>
+static cudaError_t launch_stream(const LaunchCtx& ctx, const typename TS::Rig& rig, const void* d_xy, int n_use, int64_t n_frames,
+                                 int64_t cam_stride, const BatchOut& out, int opt, int64_t* covered) {
+  *covered = 0;
+  constexpr int TILE = BATCH_THREADS * TS::FPT;
+  using Raw = typename RawPix<PIX, TS::FPT>::type;
+  const char* xy = static_cast<const char*>(d_xy);
+  const int64_t row_bytes = cam_stride * pix_bytes(PIX);
+  const int64_t n_tiles = n_frames / TILE;
+  if (n_tiles == 0 || n_use < 2 || n_use > 8) return cudaSuccess;
+  if (!stream_aligned(xy, row_bytes, TMA ? 16 : (int)sizeof(Raw), out)) return cudaSuccess;
+  const cudaError_t err = wants_wide(out) ? launch_stream_w<TS, PIX, STAGES, MINB, true, TMA>(ctx, rig, xy, n_use, n_tiles, row_bytes, out, opt)
+                                          : launch_stream_w<TS, PIX, STAGES, MINB, false, TMA>(ctx, rig, xy, n_use, n_tiles, row_bytes, out, opt);
+  if (err == cudaSuccess) *covered = n_tiles * TILE;
+  return err;
 }
 
 // ---- more than 8 cameras: the same barrier-free pipeline over (tile, camera chunk) units -----------
@@ -416,7 +452,7 @@ __device__ __forceinline__ void chunk_accumulate(const typename S::Rig& rig, con
   }
 }
 
-template <class S, int PIX, int FPT, int STAGES, int MINB>
+template <class S, int PIX, int FPT, int STAGES, int MINB, bool WIDE>
 __global__ void __launch_bounds__(BATCH_THREADS, MINB)
 chunk_kernel(const __grid_constant__ typename S::Rig rig, const char* __restrict__ xy, int64_t row_bytes, int64_t n_tiles, int n_use,
              BatchOut out, int opt, unsigned long long* first_bad, int64_t frame_base) {
@@ -480,15 +516,19 @@ chunk_kernel(const __grid_constant__ typename S::Rig rig, const char* __restrict
     if (++ch < n_chunks) continue;
     ch = 0;
 
-    float X[FPT][3];
+    T X[FPT][3];
+    double err[FPT];
+    int iters[FPT];
 #pragma unroll
     for (int j = 0; j < FPT; j++) {
-      T P[3] = {0, 0, 0};
-      int it = 0;
-      if (__popc(mask[j]) >= 2) { S::solve(rig, acc[j], __popc(mask[j]), P, opt, it); S::to_world(rig, P); }
-      X[j][0] = (float)P[0]; X[j][1] = (float)P[1]; X[j][2] = (float)P[2];
+      X[j][0] = X[j][1] = X[j][2] = 0;
+      err[j] = 0;
+      iters[j] = 0;
+      if (__popc(mask[j]) >= 2) { S::solve(rig, acc[j], mask[j], __popc(mask[j]), X[j], opt, iters[j]); S::to_world(rig, X[j]); }
     }
     const int64_t f0 = tile * TILE + (int64_t)tid * FPT;
+    const int64_t warp_f0 = tile * TILE + (int64_t)(tid - lane) * FPT;
+    tile += gridDim.x;
 #pragma unroll
     for (int j = 0; j < FPT; j++)
       if (__popc(mask[j]) < 2) atomicMin(first_bad, (unsigned long long)(frame_base + f0 + j));
@@ -496,20 +536,24 @@ chunk_kernel(const __grid_constant__ typename S::Rig rig, const char* __restrict
       if constexpr (FPT == 2) reinterpret_cast<uint2*>(out.mask)[f0 / 2] = make_uint2(mask[0], mask[1]);
       else out.mask[f0] = mask[0];
     }
+    if constexpr (WIDE) {  // double3 points / iterations (the `error` output needs the pixels again: generic kernel)
+      store_wide<FPT, T>(out, f0, X, err, iters);
+      if (!out.xyz_f32) continue;
+    }
     __syncwarp();
     if constexpr (FPT == 2) {
       float2* o2 = reinterpret_cast<float2*>(outw) + 3 * lane;
-      o2[0] = make_float2(X[0][0], X[0][1]); o2[1] = make_float2(X[0][2], X[1][0]); o2[2] = make_float2(X[1][1], X[1][2]);
+      o2[0] = make_float2((float)X[0][0], (float)X[0][1]); o2[1] = make_float2((float)X[0][2], (float)X[1][0]);
+      o2[2] = make_float2((float)X[1][1], (float)X[1][2]);
     } else {
-      outw[3 * lane] = X[0][0]; outw[3 * lane + 1] = X[0][1]; outw[3 * lane + 2] = X[0][2];
+      outw[3 * lane] = (float)X[0][0]; outw[3 * lane + 1] = (float)X[0][1]; outw[3 * lane + 2] = (float)X[0][2];
     }
     __syncwarp();
-    float4* dst = reinterpret_cast<float4*>(out.xyz_f32 + 3 * (tile * TILE + (int64_t)(tid - lane) * FPT));
+    float4* dst = reinterpret_cast<float4*>(out.xyz_f32 + 3 * warp_f0);
     const float4* src4 = reinterpret_cast<const float4*>(outw);
     constexpr int N4 = 32 * FPT * 3 / 4;
 #pragma unroll
     for (int i = lane; i < N4; i += 32) __stcs(dst + i, src4[i]);
-    tile += gridDim.x;
   }
   cp_async_wait<0>();
 }
@@ -524,21 +568,24 @@ static cudaError_t launch_chunk(const LaunchCtx& ctx, const typename S::Rig& rig
   const int64_t row_bytes = cam_stride * pix_bytes(PIX);
   const int64_t n_tiles = n_frames / TILE;
   if (n_tiles == 0 || n_use <= CHUNK_CAMS || n_use > 4 * CHUNK_CAMS) return cudaSuccess;
-  if (!out.xyz_f32 || out.xyz_f64 || out.err || out.iters) return cudaSuccess;
-  const int align = (int)sizeof(Raw);
-  if (((uintptr_t)xy % align) || (row_bytes % align) || ((uintptr_t)out.xyz_f32 & 15) || (out.mask && ((uintptr_t)out.mask & 7))) return cudaSuccess;
-  auto kern = chunk_kernel<S, PIX, FPT, STAGES, MINB>;
+  if (out.err) return cudaSuccess;
+  if (!stream_aligned(xy, row_bytes, (int)sizeof(Raw), out)) return cudaSuccess;
   constexpr int bytes = STAGES * CHUNK_CAMS * BATCH_THREADS * (int)sizeof(Raw) + (BATCH_THREADS / 32) * 32 * FPT * 12;
-  cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  auto go = [&](auto kern) -> cudaError_t {
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (err != cudaSuccess) return err;
+    int per_sm = 1;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BATCH_THREADS, bytes);
+    if (err != cudaSuccess) return err;
+    const int64_t grid = std::min<int64_t>(n_tiles, (int64_t)ctx.sm_count * std::max(per_sm, 1));
+    kern<<<(unsigned)grid, BATCH_THREADS, bytes, ctx.stream>>>(rig, xy, row_bytes, n_tiles, n_use, out, opt, ctx.d_first_bad, ctx.frame_base);
+    return cudaGetLastError();
+  };
+  const cudaError_t err = wants_wide(out) ? go(chunk_kernel<S, PIX, FPT, STAGES, MINB, true>) : go(chunk_kernel<S, PIX, FPT, STAGES, MINB, false>);
   if (err != cudaSuccess) return err;
-  int per_sm = 1;
-  err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BATCH_THREADS, bytes);
-  if (err != cudaSuccess) return err;
-  const int64_t grid = std::min<int64_t>(n_tiles, (int64_t)ctx.sm_count * std::max(per_sm, 1));
-  kern<<<(unsigned)grid, BATCH_THREADS, bytes, ctx.stream>>>(rig, xy, row_bytes, n_tiles, n_use, out, opt, ctx.d_first_bad, ctx.frame_base);
   ++*ctx.launches;
   *covered = n_tiles * TILE;
-  return cudaGetLastError();
+  return cudaSuccess;
 }
 
 // Sub-range helper for the tail after the pipelined tiles.
@@ -553,8 +600,8 @@ inline BatchOut advance(const BatchOut& o, int64_t frames) {
 }
 
 
-// pipelined kernel on the full tiles, the scalar policy kernel on whatever is left
-template <class TS, class S, int PIX, int FPT, int STAGES, int MINB, int OUTBUFS>
+// streaming kernel on the full tiles, the scalar policy kernel on whatever is left (tails, unaligned rows)
+template <class TS, class S, int PIX, int FPT, int STAGES, int MINB, bool TMA = false>
 static cudaError_t launch_streamed(const LaunchCtx& ctx, const typename TS::Rig& tile_rig, const typename S::Rig& rig,
                                    const void* d_xy, int n_use, int64_t n_frames, int64_t cam_stride, const BatchOut& out, int opt) {
   int64_t covered = 0;
@@ -562,12 +609,8 @@ static cudaError_t launch_streamed(const LaunchCtx& ctx, const typename TS::Rig&
     cudaError_t err;
     if (S::CHUNKED && n_use > CHUNK_CAMS)  // 9..32 cameras: camera-chunked pipeline over the scalar policy
       err = launch_chunk<S, PIX, S::CHUNK_FPT, 3, 2>(ctx, rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
-    else if constexpr (OUTBUFS == 0)   // generation 3: barrier-free cp.async pipeline, rig from the parameter bank
-      err = launch_stream<TS, PIX, STAGES, MINB, false>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
-    else if constexpr (OUTBUFS == -1)  // generation 3, rig staged in shared memory
-      err = launch_stream<TS, PIX, STAGES, MINB, true>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
     else
-      err = launch_pipe<TS, PIX, STAGES, MINB, OUTBUFS>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
+      err = launch_stream<TS, PIX, STAGES, MINB, TMA>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
     if (err != cudaSuccess || covered == n_frames) return err;
   }
   LaunchCtx rest = ctx;

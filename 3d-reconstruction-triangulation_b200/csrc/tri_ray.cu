@@ -81,7 +81,7 @@ struct RayPolicy {
     const T Mp2 = fma_(M[2], p[0], fma_(M[4], p[1], mul_(M[5], p[2])));
     return fma_(p[0], fma_(T(-2), c[0], Mp0), fma_(p[1], fma_(T(-2), c[1], Mp1), fma_(p[2], fma_(T(-2), c[2], Mp2), k)));
   }
-  static __device__ __forceinline__ void solve(const Rig&, const Acc& a, int n, T (&X)[3], int opt, int& iters) {
+  static __device__ __forceinline__ void solve(const Rig&, const Acc& a, uint32_t, int n, T (&X)[3], int opt, int& iters) {
     const T M[6] = {a.tr - a.uu[0], -a.uu[1], -a.uu[2], a.tr - a.uu[3], -a.uu[4], a.tr - a.uu[5]};
     const T c[3] = {a.cn[0] - a.cu[0], a.cn[1] - a.cu[1], a.cn[2] - a.cu[2]};
     if (!(opt & 1)) {
@@ -162,9 +162,12 @@ struct RayTableTile {
   static constexpr int FPT = FPT_;
   using S = RayPolicy<T_>;
   using Rig = typename S::Rig;
-  template <int NC, int PIX>
-  static __device__ __forceinline__ void run(const Rig& rig, const typename RawPix<PIX, FPT>::type (&raw)[NC], int, float (&X)[FPT][3],
-                                             uint32_t (&mask)[FPT]) {
+  using Real = T_;
+  static constexpr int CONST_BYTES = 0;
+  static __device__ __forceinline__ void stage_consts(const Rig&, unsigned char*, int) {}
+  template <int NC, int PIX, bool WIDE>
+  static __device__ __forceinline__ void run(const Rig& rig, const unsigned char*, const typename RawPix<PIX, FPT>::type (&raw)[NC], int, T_ (&X)[FPT][3],
+                                             uint32_t (&mask)[FPT], double (&err)[FPT], int (&iters)[FPT]) {
     using T = T_;
     static_assert(NC <= TRI_RAY_TABLE_CAMS, "the mask table covers 8 cameras");
 #pragma unroll
@@ -201,10 +204,23 @@ struct RayTableTile {
     for (int j = 0; j < FPT; j++) {
       acc[j].cn[0] = row[j][0]; acc[j].cn[1] = row[j][1]; acc[j].cn[2] = row[j][2]; acc[j].tr = row[j][3];
       if constexpr (LM) { acc[j].so[0] = row[j][4]; acc[j].so[1] = row[j][5]; acc[j].so[2] = row[j][6]; acc[j].kn = row[j][7]; }
-      T P[3] = {0, 0, 0};
-      int it = 0;
-      if (__popc(mask[j]) >= 2) { S::solve(rig, acc[j], __popc(mask[j]), P, LM ? 1 : 0, it); S::to_world(rig, P); }
-      X[j][0] = (float)P[0]; X[j][1] = (float)P[1]; X[j][2] = (float)P[2];
+      X[j][0] = X[j][1] = X[j][2] = 0;
+      err[j] = 0;
+      iters[j] = 0;
+      const int n = __popc(mask[j]);
+      if (n >= 2) {
+        S::solve(rig, acc[j], mask[j], n, X[j], LM ? 1 : 0, iters[j]);
+        if constexpr (WIDE) {  // mean distance to the rays at the solution (RayTriangulator.cpp:26)
+          T e = 0;
+#pragma unroll
+          for (int c = 0; c < NC; c++) {
+            const Views<T, PIX, FPT> w = decode<T, PIX, FPT>(raw[c]);
+            if (w.v[j]) e += S::residual(rig, c, w.x[j], w.y[j], X[j]);
+          }
+          err[j] = S::error(e, n);
+        }
+        S::to_world(rig, X[j]);
+      }
     }
   }
 };
@@ -223,9 +239,12 @@ struct __align__(16) RayRigX2 {
 struct RayX2Tile {
   static constexpr int FPT = 2;
   using Rig = RayRigX2;
-  template <int NC, int PIX>
-  static __device__ __forceinline__ void run(const Rig& r, const typename RawPix<PIX, 2>::type (&raw)[NC], int, float (&X)[2][3],
-                                             uint32_t (&mask)[2]) {
+  using Real = float;
+  static constexpr int CONST_BYTES = 0;
+  static __device__ __forceinline__ void stage_consts(const Rig&, unsigned char*, int) {}
+  template <int NC, int PIX, bool WIDE>
+  static __device__ __forceinline__ void run(const Rig& r, const unsigned char*, const typename RawPix<PIX, 2>::type (&raw)[NC], int, float (&X)[2][3],
+                                             uint32_t (&mask)[2], double (&err)[2], int (&iters)[2]) {
     const float2 z = make_float2(0.f, 0.f);
     float2 uu[6] = {z, z, z, z, z, z}, cu[3] = {z, z, z};
     uint32_t mask0 = 0, mask1 = 0;
@@ -260,9 +279,35 @@ struct RayX2Tile {
     float2 X0, X1, X2;
     solve_sym3_x2(M, cc, X0, X1, X2);
     const bool ok0 = __popc(mask0) >= 2, ok1 = __popc(mask1) >= 2;
-    X[0][0] = ok0 ? X0.x + r.origin[0] : 0.f; X[0][1] = ok0 ? X1.x + r.origin[1] : 0.f; X[0][2] = ok0 ? X2.x + r.origin[2] : 0.f;
-    X[1][0] = ok1 ? X0.y + r.origin[0] : 0.f; X[1][1] = ok1 ? X1.y + r.origin[1] : 0.f; X[1][2] = ok1 ? X2.y + r.origin[2] : 0.f;
     mask[0] = mask0; mask[1] = mask1;
+    const float Xr[2][3] = {{X0.x, X1.x, X2.x}, {X0.y, X1.y, X2.y}};
+#pragma unroll
+    for (int j = 0; j < 2; j++) {
+      const bool ok = j == 0 ? ok0 : ok1;
+      err[j] = 0;
+      iters[j] = ok ? 1 : 0;
+      if constexpr (WIDE) {
+        if (ok) {  // mean distance to the rays, the arithmetic of RayPolicy<float>::residual
+          float e = 0;
+#pragma unroll
+          for (int c = 0; c < NC; c++) {
+            const Views<float, PIX, 2> q = decode<float, PIX, 2>(raw[c]);
+            if (q.v[j]) {
+              const float x = q.x[j], y = q.y[j];
+              const float u0 = fmaf(r.U0[c][0].x, x, fmaf(r.U1[c][0].x, y, r.U2[c][0].x)), u1 = fmaf(r.U0[c][1].x, x, fmaf(r.U1[c][1].x, y, r.U2[c][1].x)),
+                          u2 = fmaf(r.U0[c][2].x, x, fmaf(r.U1[c][2].x, y, r.U2[c][2].x));
+              const float vx = fmaf(r.ax[c].x, x, r.bx[c].x), vy = fmaf(r.ay[c].x, y, r.by[c].x);
+              const float inv = rcp_ray(fmaf(vx, vx, fmaf(vy, vy, r.dd[c].x)));
+              const float w0 = Xr[j][0] - r.ob[c][0].x, w1 = Xr[j][1] - r.ob[c][1].x, w2 = Xr[j][2] - r.ob[c][2].x;
+              const float c0 = fmaf(u1, w2, -__fmul_rn(u2, w1)), c1 = fmaf(u2, w0, -__fmul_rn(u0, w2)), c2 = fmaf(u0, w1, -__fmul_rn(u1, w0));
+              e += sqrtf(__fmul_rn(fmaf(c0, c0, fmaf(c1, c1, __fmul_rn(c2, c2))), inv));
+            }
+          }
+          err[j] = (double)e / (double)__popc(j == 0 ? mask0 : mask1);
+        }
+      }
+      X[j][0] = ok ? Xr[j][0] + r.origin[0] : 0.f; X[j][1] = ok ? Xr[j][1] + r.origin[1] : 0.f; X[j][2] = ok ? Xr[j][2] + r.origin[2] : 0.f;
+    }
   }
 };
 
@@ -294,10 +339,14 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
       case PIX_F32:
         // 3 stages x 2 CTAs per SM: 1.32 ms per 100 M frames; 2 stages x 3 CTAs (the DLT's choice): 1.47 ms -- with the
         // lighter solve the kernel waits on memory (ncu r1f: long_scoreboard on top), so depth beats occupancy
-        if (ctx.variant == 1) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 2, 3, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 2, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case PIX_F64: return launch_streamed<RayX2Tile, P32, PIX_F64, 2, 3, 2, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-      default: return launch_streamed<RayX2Tile, P32, PIX_U16, 2, 3, 2, 0>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+#ifdef TRI_TUNING
+        if (ctx.variant == 1) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 2, true>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        if (ctx.variant == 2) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 4, 2, true>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        if (ctx.variant == 3) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 3, true>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+#endif
+        return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 2>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case PIX_F64: return launch_streamed<RayX2Tile, P32, PIX_F64, 2, 3, 2>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      default: return launch_streamed<RayX2Tile, P32, PIX_U16, 2, 3, 2>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
     }
   }
   // one frame per thread; the solver is a compile-time choice of the tile (the scalar policy serves the tails)
@@ -307,13 +356,17 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
   using CFT = RayTableTile<double, false, 2>;
   switch (pixfmt) {
     case PIX_F32:
+#ifdef TRI_TUNING
+      if (ctx.variant == 1) return lm ? launch_streamed<LMT, P64, PIX_F32, 2, 2, 2, true>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
+                                      : launch_streamed<CFT, P64, PIX_F32, 2, 3, 2, true>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+#endif
       // (4- and 6-stage rings measured the same: these two are FP64-pipe-bound)
-      return lm ? launch_streamed<LMT, P64, PIX_F32, 2, 2, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
-                : launch_streamed<CFT, P64, PIX_F32, 2, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
-    case PIX_F64: return launch_streamed<LMT, P64, PIX_F64, 1, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+      return lm ? launch_streamed<LMT, P64, PIX_F32, 2, 2, 2>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
+                : launch_streamed<CFT, P64, PIX_F32, 2, 3, 2>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+    case PIX_F64: return launch_streamed<LMT, P64, PIX_F64, 1, 3, 2>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
     default:
-      return lm ? launch_streamed<LMT, P64, PIX_U16, 2, 2, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
-                : launch_streamed<CFT, P64, PIX_U16, 2, 3, 2, 0>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+      return lm ? launch_streamed<LMT, P64, PIX_U16, 2, 2, 2>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
+                : launch_streamed<CFT, P64, PIX_U16, 2, 3, 2>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
   }
 }
 

@@ -282,7 +282,7 @@ def main():
         pass
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8tbs": achieved / 8000.0,
             "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
-            "kernel": ("stream_kernel<%s, 8 cams, float2>" % (("PolicyTile<DltPolicy<double>,2>, 2-stage ring" if a.precision == "f64" else "DltX2Tile (FFMA2)")
+            "kernel": ("stream_kernel<%s, 8 cams, float2>" % (("DltTile64 (absent-view table), 2-stage ring" if a.precision == "f64" else "DltX2Tile (FFMA2)")
                                                               if a.mode == "matrix" else "RayTableTile<RayPolicy>")),
             "algorithmic_bytes_per_frame": 8 * N_CAMS + 12, "kernel_ms": kernel_ms}
 
@@ -309,8 +309,7 @@ def main():
     other = {}
     for name, md, fl in (("dlt_f32" if a.precision == "f64" else "dlt_f64", T.MATRIX, flags ^ T.F32),
                          ("ray_lm_f64", T.RAY, T.ALLOW_TOO_FEW), ("ray_closed_f64", T.RAY, T.ALLOW_TOO_FEW | T.RAY_CLOSED_FORM),
-                         ("ray_closed_f32", T.RAY, T.ALLOW_TOO_FEW | T.F32),
-                         ("stream_probe", T.MATRIX, T.ALLOW_TOO_FEW | T.F32 | T.DEBUG_STREAM)):
+                         ("ray_closed_f32", T.RAY, T.ALLOW_TOO_FEW | T.F32)):
         def fn(md=md, fl=fl):
             eng.triangulate_points_device(md, xy, fl, out=out)
         tms, _, _ = timed(fn, max(3, a.steps // 2), 2)

@@ -198,7 +198,10 @@ def classify(cams, mode, n_drones, offs, xy, n_cam, n_frames):
                             _p(assign, C.c_int8), _p(phase, C.c_uint8), C.byref(st))
     if rc != OK:
         raise RuntimeError("orc_classify status %d" % rc)
-    return dict(paths=paths, assign=assign, phase=phase, stats=st.as_dict())
+    m = np.zeros(5)
+    lib().orc_last_margins(_p(m))
+    return dict(paths=paths, assign=assign, phase=phase, stats=st.as_dict(),
+                margins=dict(error=m[0], step=m[1], gate=m[2], order=m[3], tail=m[4]))
 
 
 def enumerate_frame(cams, mode, offs, xy, n_cam, n_frames, frame, max_leaves=1 << 16):

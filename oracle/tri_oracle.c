@@ -54,6 +54,9 @@ static int inv3(const double S[9], double T[9]) {
   return 1;
 }
 
+/* exported for oracle/shim (cv::Mat::inv of a 3x3) */
+int orc_inv3(const double S[9], double T[9]) { return inv3(S, T); }
+
 int orc_camera_make(orc_camera* c, int id, int width, int height, double focal, const double pos[3],
                     const double quat[4]) {
   /* createCamera, src/utils.cpp:94-107, then Camera::compCamParams, src/Camera.h:177-187 */
@@ -644,6 +647,20 @@ static void pq_pop(comb_vec* q) {
   q->n--;
 }
 
+/* Margin audit: the smallest |lhs - rhs| of every floating-point compare that decides an index --
+ * a flip needs an arithmetic difference of at least that much.  [0] error vs error_ (DroneClassifier.cpp:185,209,243),
+ * [1] |c.point - pos| vs MAX_STEP (:244), [2] getDistFromRay vs MAX_STEP (:231-233), [3] error vs error between
+ * queue entries with the same number of unused cameras (Combination::operator<, :12-20), [4] the tail distances
+ * compared in classifyPaths (:291, :299-300). */
+static _Thread_local double g_margin[5];
+static void margin(int k, double lhs, double rhs) { double d = fabs(lhs - rhs); if (d < g_margin[k]) g_margin[k] = d; }
+void orc_last_margins(double out[5]) { memcpy(out, g_margin, sizeof(g_margin)); }
+static int cmp_zero_err(const void* a, const void* b) {
+  const double* x = (const double*)a; const double* y = (const double*)b;
+  if (x[0] != y[0]) return x[0] < y[0] ? -1 : 1;
+  return x[1] < y[1] ? -1 : x[1] > y[1] ? 1 : 0;
+}
+
 typedef struct {
   const orc_camera* cams; int n_cams, mode, n_drones; double error_;
   orc_stats st;
@@ -696,6 +713,7 @@ static void fill_queue(clf_t* cl, const frame_dets* fd, comb_vec* q, int heap) {
     c.err = cl->mode == ORC_MATRIX ? orc_matrix_point(cl->cams, n, idx, pix, c.p)
                                    : orc_ray_point(cl->cams, n, idx, pix, c.p, &iters);
     cl->st.lm_iters += iters;
+    margin(0, c.err, cl->error_);
     if (c.err > cl->error_) {
       if (!it_cut(&it)) break;
     } else if (!has_unset && count >= MIN_CAMERAS) {
@@ -723,6 +741,14 @@ static int comb_unique(const comb_t* c, const comb_t* list, int n, int n_cams) {
 static void tie_audit(clf_t* cl, const comb_vec* q) {
   /* count (zeros, error) keys that occur more than once: there the pop order is an artefact of
    * the heap algorithm, and the CUDA engine's documented tie rule (DFS order) may differ */
+  if (q->n > 1) { /* ordering margin: smallest error gap between entries of equal priority class */
+    double* key = (double*)malloc(sizeof(double) * 2 * (size_t)q->n);
+    for (int i = 0; i < q->n; i++) { key[2 * i] = q->v[i].zeros; key[2 * i + 1] = q->v[i].err; }
+    qsort(key, (size_t)q->n, 2 * sizeof(double), cmp_zero_err);
+    for (int i = 1; i < q->n; i++)
+      if (key[2 * i] == key[2 * i - 2] && key[2 * i + 1] != key[2 * i - 1]) margin(3, key[2 * i + 1], key[2 * i - 1]);
+    free(key);
+  }
   for (int i = 0; i < q->n; i++)
     for (int j = i + 1; j < q->n; j++)
       if (q->v[i].zeros == q->v[j].zeros && q->v[i].err == q->v[j].err) { cl->st.ties++; break; }
@@ -768,6 +794,7 @@ int orc_classify(const orc_camera* cams, int n_cams, int mode, int n_drones, con
                  orc_stats* stats) {
   if (n_cams > ORC_MAX_CAMS || n_drones > 64) return ORC_ERR_DIM;
   clf_t cl; memset(&cl, 0, sizeof(cl));
+  for (int k = 0; k < 5; k++) g_margin[k] = HUGE_VAL;
   cl.cams = cams; cl.n_cams = n_cams; cl.mode = mode; cl.n_drones = n_drones;
   cl.error_ = mode == ORC_MATRIX ? MAX_ERROR_MATRIX : MAX_ERROR_RAY; /* DroneClassifier.cpp:3-10 */
   path_t* paths = (path_t*)calloc((size_t)n_drones, sizeof(path_t));
@@ -799,7 +826,9 @@ int orc_classify(const orc_camera* cams, int n_cams, int mode, int n_drones, con
         gd->n[c] = 0; gd->xy[c] = gd->gated_xy[c]; gd->remap[c][0] = 0;
         for (int d = 0; d < fd->n[c]; d++) {
           double x = fd->xy[c][2 * d], y = fd->xy[c][2 * d + 1];
-          if (orc_dist_from_ray(&cams[c], x, y, last) < MAX_STEP) {
+          const double gate = orc_dist_from_ray(&cams[c], x, y, last);
+          margin(2, gate, MAX_STEP);
+          if (gate < MAX_STEP) {
             gd->gated_xy[c][2 * gd->n[c]] = x; gd->gated_xy[c][2 * gd->n[c] + 1] = y;
             gd->n[c]++;
             gd->remap[c][gd->n[c]] = d + 1;
@@ -813,7 +842,11 @@ int orc_classify(const orc_camera* cams, int n_cams, int mode, int n_drones, con
       comb_t best;
       while (q.n > 0) {
         comb_t c = q.v[0];
-        if (comb_unique(&c, used, n_used, n_cams) && c.err < cl.error_ && dist3(c.p, last) < MAX_STEP) { best = c; found = 1; break; }
+        if (comb_unique(&c, used, n_used, n_cams) && c.err < cl.error_) {
+          const double step = dist3(c.p, last);
+          margin(1, step, MAX_STEP);
+          if (step < MAX_STEP) { best = c; found = 1; break; }
+        }
         pq_pop(&q);
       }
       if (found) {
@@ -849,6 +882,7 @@ int orc_classify(const orc_camera* cams, int n_cams, int mode, int n_drones, con
         double dist = 0;
         for (int t = paths[j].n - npc; t < paths[j].n; t++) dist += dist3(paths[j].p[t], fin.v[i].p);
         dist /= (double)npc;
+        if (bestDist != -1) margin(4, dist, bestDist);
         if (dist < bestDist || bestDist == -1) { bestDist = dist; bestPath = j; }
       }
       cp_comb[i] = i; cp_path[i] = bestPath; cp_err[i] = bestDist;
@@ -857,6 +891,7 @@ int orc_classify(const orc_camera* cams, int n_cams, int mode, int n_drones, con
      * uses insertion sort for <= 16 elements (stable); restated as a stable insertion sort. */
     for (int i = 1; i < nf; i++) {
       int c0 = cp_comb[i], p0 = cp_path[i]; double e0 = cp_err[i]; int j = i - 1;
+      for (int k = 0; k < i; k++) if (e0 != -1 && cp_err[k] != -1) margin(4, e0, cp_err[k]);
       while (j >= 0 && e0 < cp_err[j]) { cp_comb[j + 1] = cp_comb[j]; cp_path[j + 1] = cp_path[j]; cp_err[j + 1] = cp_err[j]; j--; }
       cp_comb[j + 1] = c0; cp_path[j + 1] = p0; cp_err[j + 1] = e0;
     }

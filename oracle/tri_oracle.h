@@ -38,6 +38,8 @@ int orc_camera_make(orc_camera* c, int id, int width, int height, double focal, 
 
 /* cv::invert(A, DECOMP_SVD) for an m x n (n<=4, m>=n) row-major A; pinv is n x m row-major. */
 void orc_pinv_svd(const double* A, int m, int n, double* pinv);
+/* cv::Mat::inv() of a 3x3 (closed-form branch of cv::invert); returns 0 for a singular matrix */
+int orc_inv3(const double S[9], double T[9]);
 /* cv::solve(A, b, DECOMP_EIG) and diag(cv::invert(A, DECOMP_EIG)) for symmetric 3x3 A. */
 void orc_eig_solve3(const double A[9], const double b[3], double x[3]);
 void orc_eig_inv_diag3(const double A[9], double diag[3]);
@@ -73,6 +75,11 @@ int orc_triangulate_points_f32(const orc_camera* cams, int n_cams, int n_point_c
 int orc_classify(const orc_camera* cams, int n_cams, int mode, int n_drones, const int32_t* det_offsets,
                  const double* dets_xy, int n_frames, double* out_paths, int8_t* out_assign,
                  uint8_t* out_phase, orc_stats* stats);
+
+/* Margin audit of the last orc_classify call on this thread: the smallest |lhs - rhs| over the compares that
+ * decide an index -- [0] error vs error_, [1] step vs MAX_STEP, [2] ray gate vs MAX_STEP, [3] error vs error
+ * within a priority class, [4] path-tail distances (HUGE_VAL where no such compare happened). */
+void orc_last_margins(double out[5]);
 
 /* fillCombinationQueue over one full frame: leaves in DFS order.  Returns the number of leaves
  * (may exceed max_leaves; only max_leaves are written). */
