@@ -21,6 +21,7 @@
 //     path-assignment logic on one thread.  Ties on (unused cameras, error) are broken by DFS order
 //     (the reference's heap order is an artefact of libstdc++); they are counted in stats.ties.
 #include <float.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -35,28 +36,53 @@ namespace tri {
 
 constexpr int CLS_MAX_CAMS = 16;   // 4 bits per camera in a 64-bit combination
 constexpr int CLS_THREADS = 128;
-constexpr int LINK_THREADS = 256;
-constexpr int LINK_MAX_FINAL = 64;
-constexpr int LINK_STAGE_LEAVES = 2048;  // leaves of one frame staged in (dynamic) shared memory, 40 B each; two buffers
+constexpr int LINK_MAX_FINAL = 128;  // combinations pickBestCombinations can keep in one frame: <= 15 * C / 2 = 120 disjoint ones
 typedef unsigned long long u64;
 
 // DroneClassifier.h:11-17
 constexpr double MAX_ERROR_MATRIX = 1e+5, MAX_ERROR_RAY = 120, MAX_STEP = 200;
 constexpr int MIN_CAMERAS = 2, PATH_TAIL = 3;
 
+// ---- what (A) hands to (B), per frame, all of it independent of the tracking state ------------------------
+// The frame's detections are numbered camera-major (pref[c] + d); a detection MASK has one bit per such number.
+// A candidate ("leaf") record, stored in PRIORITY order (Combination::operator<, :12-20):
+//   mask[W]   the leaf's detections.  Two combinations collide (isCombinationUnique, :32-41) <=> their masks
+//             intersect; a combination is inside a path's ray gate <=> its mask is a subset of the gate mask.  The top
+//             bit of the last word is a poison bit: set on a leaf whose error is not < error_ (it can never be
+//             accepted, :209, :243) and in every "used" mask.
+//   xyz[3]    the triangulated point, comb = the 4-bit-per-camera combination word (for the assignment output)
+// W = 2 (<= 8 cameras, 48-byte records) or 4 (<= 16 cameras, 80-byte records: both strides are conflict-free for the
+// 16-byte shared-memory loads of a warp).
+__host__ __device__ constexpr int rec_words(int W) { return W == 2 ? 6 : 10; }
+constexpr int HDR_INTS = 40;   // per frame: [0 .. C+1] zstart[z] = leaves with fewer than z unused cameras; [20 .. 20+C] pref[c]
+constexpr int HDR_PREF = 20;
+struct __align__(16) FrameDet {  // a detection of the frame with its pixel ray (Triangulator.cpp:27-55); 80 B, a conflict-free stride
+  double dir[3], org[3];
+  int cam, slot;
+  double pad[3];
+};
+constexpr int LINK_MAX_DETS = CLS_MAX_CAMS * TRI_MAX_DETS;  // 240
+
 struct ClsParams {
   int n_cams, n_drones, solver;  // solver: 0 matrix, 1 ray reference LM, 2 ray closed form
   int n_frames;                  // whole sequence (row length of the CSR offsets is n_frames + 1)
   int f0, f1;                    // frame batch [f0, f1)
   int cap;                       // frontier capacity per CTA
-  long long leaf_cap;
+  int W;                         // mask words per leaf
+  long long leaf_cap;            // leaf records
   double error_;
 };
 
 struct ClsCounters {
-  u64 leaf_total, nodes, solves, leaves, lm_iters, phase1, phase2, ties;
-  int max_frontier, overflow_frontier, overflow_leaves, bad_input;
+  u64 leaf_total, fdet_total, nodes, solves, leaves, lm_iters, phase1, phase2, ties;
+  int max_frontier, overflow_frontier, overflow_leaves, overflow_final, bad_input;
+  u64 prof[8];  // tuning builds: clock cycles of the linking pass by section (wait, gates, phase 1, phase 2, classifyPaths)
 };
+#ifdef TRI_TUNING
+#define CLS_PROF(k) do { const long long now__ = clock64(); prof_acc[k] += (u64)(now__ - prof_t); prof_t = now__; } while (0)
+#else
+#define CLS_PROF(k) do { } while (0)
+#endif
 
 struct LinkState {
   double tail[TRI_MAX_DRONES][PATH_TAIL][3];  // oldest .. newest of the last min(n,3) points
@@ -114,10 +140,11 @@ __device__ inline double solve_combination(const DltRig<double>& dlt, const RayR
 __global__ void __launch_bounds__(CLS_THREADS)
 enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_constant__ RayRig ray, ClsParams p,
                  const int32_t* __restrict__ offs, const double* __restrict__ dets, u64* __restrict__ front,
-                 double* __restrict__ tmp_xyz, double* __restrict__ tmp_err, u64* __restrict__ leaf_comb,
-                 double* __restrict__ leaf_err, double* __restrict__ leaf_xyz, long long* __restrict__ leaf_off,
-                 int* __restrict__ leaf_cnt, ClsCounters* ctr) {
-  __shared__ int s_n[CLS_MAX_CAMS];
+                 double* __restrict__ tmp_xyz, double* __restrict__ tmp_err, u64* __restrict__ leaf_rec,
+                 long long* __restrict__ leaf_off, int* __restrict__ leaf_cnt, int* __restrict__ hdr,
+                 FrameDet* __restrict__ fdet, long long* __restrict__ fdet_off, int* __restrict__ fdet_cnt, ClsCounters* ctr) {
+  __shared__ int s_n[CLS_MAX_CAMS], s_pref[CLS_MAX_CAMS + 1], s_hist[CLS_MAX_CAMS + 2];
+  __shared__ long long s_doff;
   __shared__ double s_px[CLS_MAX_CAMS][TRI_MAX_DETS], s_py[CLS_MAX_CAMS][TRI_MAX_DETS];
   __shared__ int s_warp[CLS_THREADS / 32];
   __shared__ long long s_off;
@@ -140,8 +167,29 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
       }
       if (d < b - a) { s_px[c][d] = dets[2 * (size_t)(a + d)]; s_py[c][d] = dets[2 * (size_t)(a + d) + 1]; }
     }
-    if (tid == 0) buf0[0] = 0;
+    __syncthreads();  // s_n is complete
+    if (tid == 0) {
+      buf0[0] = 0;
+      int n = 0;
+      for (int c = 0; c < C; c++) { s_pref[c] = n; n += s_n[c]; }
+      s_pref[C] = n;
+      s_doff = (long long)atomicAdd(&ctr->fdet_total, (u64)n);  // the buffer holds every detection of the batch: no overflow
+      fdet_off[f - p.f0] = s_doff;
+      fdet_cnt[f - p.f0] = n;
+    }
     __syncthreads();
+    // the frame's detections with their pixel rays, camera-major: the linking pass gates them against every path
+    for (int i = tid; i < C * TRI_MAX_DETS; i += CLS_THREADS) {
+      const int c = i / TRI_MAX_DETS, d = i % TRI_MAX_DETS;
+      if (d < s_n[c]) {
+        FrameDet fd;
+        ref::make_dir(ray, c, s_px[c][d], s_py[c][d], fd.dir);
+        fd.org[0] = ray.pos[c][0]; fd.org[1] = ray.pos[c][1]; fd.org[2] = ray.pos[c][2];
+        fd.cam = c; fd.slot = d;
+        fd.pad[0] = fd.pad[1] = fd.pad[2] = 0;
+        fdet[s_doff + s_pref[c] + d] = fd;
+      }
+    }
     u64 *fin = buf0, *fout = buf1;
     int m = 1;
     for (int c = 0; c < C && m > 0; c++) {
@@ -192,16 +240,16 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
       }
       m = min(out_base, p.cap);
       if (tid == 0) atomicMax(&ctr->max_frontier, out_base);
-      if (last && m > 64 * LINK_THREADS && tid == 0) atomicExch(&ctr->bad_input, 2);  // the linking pass keeps one live bit per leaf in a u64 per thread
       u64* t = fin; fin = fout; fout = t;
       if (m == 0) break;
       if (last) {
-        // publish this frame's leaves (in order) into a contiguous range of the global leaf arrays
+        // publish this frame's leaves as records into a contiguous range of the global leaf array
         if (tid == 0) {
           long long off = (long long)atomicAdd(&ctr->leaf_total, (u64)m);
           if (off + m > p.leaf_cap) { atomicExch(&ctr->overflow_leaves, 1); off = -1; }
           s_off = off;
         }
+        for (int i = tid; i < CLS_MAX_CAMS + 2; i += CLS_THREADS) s_hist[i] = 0;
         __syncthreads();
         const long long off = s_off;
         if (off >= 0) {
@@ -210,6 +258,7 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
           // :12-20), ties by DFS order.  Rank by counting (m is ~1e3; frames are independent, so this is
           // parallel work) and scatter; the sequential linking kernel then only walks prefixes.
           const u64 cam_bits = C == 16 ? ~0ull : ((1ull << (4 * C)) - 1);
+          const int RW = rec_words(p.W);
           u64 n_tie = 0;
           for (int i = tid; i < m; i += CLS_THREADS) {
             const u64 ci = fin[i];
@@ -225,19 +274,40 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
               tie = tie || (eq && j != i);
             }
             n_tie += tie;
-            leaf_comb[off + rank] = ci;
-            leaf_err[off + rank] = ei;
-            leaf_xyz[3 * (off + rank)] = t_xyz[3 * i]; leaf_xyz[3 * (off + rank) + 1] = t_xyz[3 * i + 1]; leaf_xyz[3 * (off + rank) + 2] = t_xyz[3 * i + 2];
+            atomicAdd(&s_hist[zi + 1], 1);
+            u64* rec = leaf_rec + (size_t)(off + rank) * RW;
+            u64 mk[4] = {0, 0, 0, 0};
+            for (int c = 0; c < C; c++) {
+              const int k = (int)((ci >> (4 * c)) & 15);
+              if (k) { const int bit = s_pref[c] + k - 1; mk[bit >> 6] |= 1ull << (bit & 63); }
+            }
+            if (!(ei < p.error_)) mk[p.W - 1] |= 1ull << 63;  // poison: a leaf (:185-196) that no acceptance test passes (:209, :243)
+            for (int w = 0; w < p.W; w++) rec[w] = mk[w];
+            rec[p.W] = (u64)__double_as_longlong(t_xyz[3 * i]);
+            rec[p.W + 1] = (u64)__double_as_longlong(t_xyz[3 * i + 1]);
+            rec[p.W + 2] = (u64)__double_as_longlong(t_xyz[3 * i + 2]);
+            rec[p.W + 3] = ci;
           }
           if (n_tie) atomicAdd(&ctr->ties, n_tie);
-          if (tid == 0) { leaf_off[f - p.f0] = off; leaf_cnt[f - p.f0] = m; atomicAdd(&ctr->leaves, (u64)m); }
+          __syncthreads();
+          if (tid == 0) {
+            leaf_off[f - p.f0] = off; leaf_cnt[f - p.f0] = m; atomicAdd(&ctr->leaves, (u64)m);
+            int run = 0;
+            int* zs = hdr + (size_t)(f - p.f0) * HDR_INTS;
+            for (int z = 0; z <= C + 1; z++) { run += s_hist[z]; zs[z] = run; }  // zs[z] = leaves with fewer than z unused cameras
+            for (int c = 0; c <= C; c++) zs[HDR_PREF + c] = s_pref[c];
+          }
         } else if (tid == 0) {
           leaf_off[f - p.f0] = 0; leaf_cnt[f - p.f0] = 0;
         }
         m = -1;  // done
       }
     }
-    if (m >= 0 && tid == 0) { leaf_off[f - p.f0] = 0; leaf_cnt[f - p.f0] = 0; }  // the tree died out (or no cameras)
+    if (m >= 0 && tid == 0) {  // the tree died out (or no cameras)
+      leaf_off[f - p.f0] = 0; leaf_cnt[f - p.f0] = 0;
+      for (int z = 0; z <= C + 1; z++) hdr[(size_t)(f - p.f0) * HDR_INTS + z] = 0;
+      for (int c = 0; c <= C; c++) hdr[(size_t)(f - p.f0) * HDR_INTS + HDR_PREF + c] = s_pref[c];
+    }
   }
   // block totals of the per-thread statistics
   for (int o = 16; o > 0; o >>= 1) {
@@ -249,308 +319,382 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
 }
 
 // ---- (B) linking -------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+// One WARP per sequence, no block barrier anywhere.  Everything that does not depend on the tracking state was
+// prepared by (A): the leaves in priority order as (detection mask, point, combination) records, the number of
+// leaves per count of unused cameras, the frame's detections with their pixel rays.  A frame's records, detections
+// and zstart table arrive in shared memory as three bulk async copies (cp.async.bulk -> UBLKCP) that complete on an
+// mbarrier, issued one frame ahead into the other buffer.  Per frame the warp then does, in registers and shuffles:
+//   gates     the MAX_STEP ray gate of every (tracked path, detection) -> one detection mask per path (:228-236)
+//   phase 1   per path in order: the FIRST leaf (priority order) whose mask lies inside the path's gate, misses the
+//             used mask, and whose point is within MAX_STEP of the path's last point -- the first element the
+//             reference's priority_queue pops that passes :241-246.  The scan starts at the first leaf with at least
+//             as many unused cameras as the gate leaves empty (zstart) and tests 32 leaves per step.
+//   phase 2   pickBestCombinations (:200-217) is ONE forward pass over the list with a running used mask: a leaf is
+//             kept iff it misses everything kept so far -- literally the reference's pop loop, 32 leaves per step.
+//   classifyPaths (:262-332): tail distances one (combination, path) pair per lane, the assignment on lane 0.
+// Round 1 ran this on a 256-thread CTA with ~15 block barriers per frame (10 us per frame on S09_D6, profiles/
+// r1_link_kernel_lines.txt); a lone warp has no one to wait for.
+__device__ __forceinline__ uint32_t cls_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cls_mbar_init(u64* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cls_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void cls_mbar_expect_tx(u64* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cls_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cls_mbar_wait(u64* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(cls_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void cls_bulk_load(void* smem_dst, const void* gmem_src, uint32_t bytes, u64* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(cls_smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(cls_smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ double dist3(const double* a, const double* b) {  // cv::norm(a - b)
   const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
   return sqrt(x * x + y * y + z * z);
 }
+// sqrt(s) < MAX_STEP without the square root unless s is within rounding reach of MAX_STEP^2 (sqrt is monotonic and
+// correctly rounded, so away from the boundary the two compares agree)
+__device__ __forceinline__ bool sqrt_below_step(double s) {
+  const double t = MAX_STEP * MAX_STEP;
+  if (s < t * (1 - 1e-12)) return true;
+  if (s > t * (1 + 1e-12)) return false;
+  return sqrt(s) < MAX_STEP;
+}
 
-__global__ void __launch_bounds__(LINK_THREADS)
-link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int32_t* __restrict__ offs, const double* __restrict__ dets,
-            const u64* __restrict__ leaf_comb, const double* __restrict__ leaf_err, const double* __restrict__ leaf_xyz,
-            const long long* __restrict__ leaf_off, const int* __restrict__ leaf_cnt, LinkState* state,
-            double* __restrict__ out_paths, int8_t* __restrict__ out_assign, uint8_t* __restrict__ out_phase, ClsCounters* ctr) {
+template <int W>
+struct LinkLayout {
+  static constexpr int RW = rec_words(W);
+  static constexpr int MAX_LEAVES = W == 2 ? 1664 : 960;  // staged leaves per frame; longer lists are read from global memory
+  static constexpr int REC_BYTES = MAX_LEAVES * RW * 8;
+  static constexpr int DET_BYTES = LINK_MAX_DETS * (int)sizeof(FrameDet);
+  static constexpr int HDR_BYTES = HDR_INTS * 4;
+  static constexpr int BUF_BYTES = REC_BYTES + DET_BYTES + HDR_BYTES;
+  static constexpr int BYTES = 2 * BUF_BYTES + 16;  // + the two mbarriers
+};
+
+template <int W>
+__global__ void __launch_bounds__(32)
+link_warp_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __restrict__ seq_bounds,
+                 const u64* __restrict__ leaf_rec, const long long* __restrict__ leaf_off, const int* __restrict__ leaf_cnt,
+                 const int* __restrict__ hdr, const FrameDet* __restrict__ fdet, const long long* __restrict__ fdet_off,
+                 const int* __restrict__ fdet_cnt, LinkState* state, double* __restrict__ out_paths, int8_t* __restrict__ out_assign,
+                 uint8_t* __restrict__ out_phase, ClsCounters* ctr) {
+  using L_ = LinkLayout<W>;
+  constexpr int RW = L_::RW;
+  constexpr u64 POISON = 1ull << 63;  // in word W - 1
+  extern __shared__ __align__(128) unsigned char link_dyn[];
   __shared__ LinkState S;
-  __shared__ unsigned s_gate[CLS_MAX_CAMS][16];  // [camera][choice] -> bit np: path np may use that choice (choice 0 = "none")
-  __shared__ unsigned s_active_mask, s_found_mask;
-  __shared__ double s_dir[CLS_MAX_CAMS * TRI_MAX_DETS][3];
-  __shared__ bool s_ndet[CLS_MAX_CAMS * TRI_MAX_DETS];
-  __shared__ int s_cand[TRI_MAX_DRONES];
-  __shared__ bool s_active[TRI_MAX_DRONES];
+  __shared__ unsigned s_gate[TRI_MAX_DRONES][2 * W];  // 32-bit slices of each tracked path's gate mask
+  __shared__ int s_act[TRI_MAX_DRONES];
+  __shared__ int s_fin_idx[LINK_MAX_FINAL], s_cp_comb[LINK_MAX_FINAL], s_cp_path[LINK_MAX_FINAL];
+  __shared__ double s_cp_err[LINK_MAX_FINAL];
   __shared__ double s_pdist[LINK_MAX_FINAL][TRI_MAX_DRONES];
-  __shared__ u64 s_used[TRI_MAX_DRONES];
-  __shared__ u64 s_fin[LINK_MAX_FINAL];
-  __shared__ int s_fin_idx[LINK_MAX_FINAL];
-  __shared__ int s_n_fin, s_n_used;
-  __shared__ int s_first[2][LINK_THREADS / 32];
-  __shared__ unsigned s_processed;
-  // This frame's candidates (combination, error, point) are staged in shared memory, and the NEXT frame's are
-  // already on their way (cp.async into the other buffer) while this one is processed: a lone CTA cannot hide a
-  // ~1 us global round trip behind anything else.
-  extern __shared__ __align__(16) unsigned char link_dyn[];
-  constexpr int LINK_BUF_BYTES = (int)((sizeof(u64) + 4 * sizeof(double)) * LINK_STAGE_LEAVES);
-  const int tid = threadIdx.x, C = p.n_cams, D = p.n_drones;
-  for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += LINK_THREADS) ((int*)&S)[i] = ((const int*)state)[i];
-  u64 n_phase1 = 0, n_phase2 = 0;  // thread 0 only
-  __syncthreads();
+  u64* full = reinterpret_cast<u64*>(link_dyn + 2 * L_::BUF_BYTES);
+  const int lane = threadIdx.x, C = p.n_cams, D = p.n_drones;
+  const int fa = seq_bounds ? seq_bounds[blockIdx.x].x : p.f0, fb = seq_bounds ? seq_bounds[blockIdx.x].y : p.f1;
+  LinkState* st = state + blockIdx.x;
+  for (int i = lane; i < (int)(sizeof(LinkState) / sizeof(int)); i += 32) ((int*)&S)[i] = ((const int*)st)[i];
+  if (lane == 0) {
+    cls_mbar_init(&full[0], 1); cls_mbar_init(&full[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  u64 n_phase1 = 0, n_phase2 = 0;  // lane 0
+  bool overflow_final = false;
+#ifdef TRI_TUNING
+  u64 prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long prof_t = clock64();
+#endif
 
-  auto emit = [&](int path, int f, u64 comb, const double* pt, int phase) {  // one thread: push a point to a path
+  // stage frame f's records / detections / header into buffer b (lane 0)
+  auto stage = [&](int b, int f, int L, long long off, int nd, long long doff) {
+    unsigned char* base = link_dyn + (size_t)b * L_::BUF_BYTES;
+    const uint32_t rec_bytes = L <= L_::MAX_LEAVES ? (uint32_t)L * RW * 8 : 0, det_bytes = (uint32_t)nd * (uint32_t)sizeof(FrameDet);
+    cls_mbar_expect_tx(&full[b], rec_bytes + det_bytes + L_::HDR_BYTES);
+    if (rec_bytes) cls_bulk_load(base, leaf_rec + (size_t)off * RW, rec_bytes, &full[b]);
+    if (det_bytes) cls_bulk_load(base + L_::REC_BYTES, fdet + doff, det_bytes, &full[b]);
+    cls_bulk_load(base + L_::REC_BYTES + L_::DET_BYTES, hdr + (size_t)(f - p.f0) * HDR_INTS, L_::HDR_BYTES, &full[b]);
+  };
+  auto emit = [&](int path, int f, u64 comb, double x, double y, double z, int phase) {  // one lane: push a point to a path
     const int n = S.n[path];
+    double(*t)[3] = S.tail[path];
     if (n >= PATH_TAIL) {
-      for (int k = 0; k < PATH_TAIL - 1; k++) for (int j = 0; j < 3; j++) S.tail[path][k][j] = S.tail[path][k + 1][j];
-      for (int j = 0; j < 3; j++) S.tail[path][PATH_TAIL - 1][j] = pt[j];
+      for (int k = 0; k < PATH_TAIL - 1; k++) for (int j = 0; j < 3; j++) t[k][j] = t[k + 1][j];
+      t[PATH_TAIL - 1][0] = x; t[PATH_TAIL - 1][1] = y; t[PATH_TAIL - 1][2] = z;
     } else {
-      for (int j = 0; j < 3; j++) S.tail[path][n][j] = pt[j];
+      t[n][0] = x; t[n][1] = y; t[n][2] = z;
     }
     if (n < 0x3fffffff) S.n[path] = n + 1;
     double* o = out_paths + ((size_t)path * p.n_frames + f) * 3;
-    o[0] = pt[0]; o[1] = pt[1]; o[2] = pt[2];
+    o[0] = x; o[1] = y; o[2] = z;
     if (out_assign) {
       int8_t* dst = out_assign + ((size_t)path * p.n_frames + f) * C;
       if (C == 8) {  // the 8 nibbles spread to 8 bytes, one store (rows of 8 bytes are 8-byte aligned)
-        u64 x = comb & 0xffffffffull;
-        x = (x | (x << 16)) & 0x0000ffff0000ffffull;
-        x = (x | (x << 8)) & 0x00ff00ff00ff00ffull;
-        x = (x | (x << 4)) & 0x0f0f0f0f0f0f0f0full;
-        *reinterpret_cast<u64*>(dst) = x;
+        u64 v = comb & 0xffffffffull;
+        v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+        v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+        v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+        *reinterpret_cast<u64*>(dst) = v;
       } else {
         for (int c = 0; c < C; c++) dst[c] = (int8_t)((comb >> (4 * c)) & 15);
       }
     }
     if (out_phase) out_phase[(size_t)path * p.n_frames + f] = (uint8_t)phase;
   };
-
-  auto stage = [&](int buf, int L, long long off) {  // cp.async of one frame's candidate list (8-byte pieces: off is arbitrary)
-    unsigned char* base = link_dyn + (size_t)buf * LINK_BUF_BYTES;
-    u64* d_comb = reinterpret_cast<u64*>(base);
-    double* d_err = reinterpret_cast<double*>(base + sizeof(u64) * LINK_STAGE_LEAVES);
-    double* d_xyz = reinterpret_cast<double*>(base + (sizeof(u64) + sizeof(double)) * LINK_STAGE_LEAVES);
-    if (L <= LINK_STAGE_LEAVES) {
-      for (int i = tid; i < L; i += LINK_THREADS) { cp_async8(d_comb + i, leaf_comb + off + i); cp_async8(d_err + i, leaf_err + off + i); }
-      for (int i = tid; i < 3 * L; i += LINK_THREADS) cp_async8(d_xyz + i, leaf_xyz + 3 * off + i);
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+  auto rec_point = [&](const u64* r, double& x, double& y, double& z) {
+    x = __longlong_as_double((long long)r[W]); y = __longlong_as_double((long long)r[W + 1]); z = __longlong_as_double((long long)r[W + 2]);
   };
-  // software pipeline over the frames: candidate-list extents two frames ahead, the list itself and the
-  // detections one frame ahead
-  const int nf = p.f1 - p.f0;
-  int L_next = nf > 0 ? leaf_cnt[0] : 0, L_next2 = nf > 1 ? leaf_cnt[1] : 0;
-  long long off_next = nf > 0 ? leaf_off[0] : 0, off_next2 = nf > 1 ? leaf_off[1] : 0;
-  const int det_c = tid / TRI_MAX_DETS, det_d = tid % TRI_MAX_DETS;  // thread tid < C * TRI_MAX_DETS owns detection slot (c, d)
-  const bool det_thread = tid < C * TRI_MAX_DETS;
-  bool det_has_next = false;
-  double det_x_next = 0, det_y_next = 0;
-  auto fetch_det = [&](int f, bool& has, double& x, double& y) {
-    has = false;
-    if (det_thread && f < p.f1) {
-      const int a = offs[(size_t)det_c * (p.n_frames + 1) + f], b = offs[(size_t)det_c * (p.n_frames + 1) + f + 1];
-      has = det_d < b - a;
-      if (has) { x = dets[2 * (size_t)(a + det_d)]; y = dets[2 * (size_t)(a + det_d) + 1]; }
-    }
+
+  // frame metadata runs two frames ahead in registers, the staged copy one frame ahead
+  const int nf = fb - fa;
+  auto meta = [&](int k, int& L, long long& off, int& nd, long long& doff) {
+    L = 0; off = 0; nd = 0; doff = 0;
+    if (k < nf) { const int g = fa + k - p.f0; L = leaf_cnt[g]; off = leaf_off[g]; nd = fdet_cnt[g]; doff = fdet_off[g]; }
   };
-  fetch_det(p.f0, det_has_next, det_x_next, det_y_next);
-  stage(0, L_next, off_next);
+  int L_n1, nd_n1, L_n2, nd_n2;
+  long long off_n1, doff_n1, off_n2, doff_n2;
+  meta(0, L_n1, off_n1, nd_n1, doff_n1);
+  meta(1, L_n2, off_n2, nd_n2, doff_n2);
+  if (lane == 0 && nf > 0) stage(0, fa, L_n1, off_n1, nd_n1, doff_n1);
 
-  for (int f = p.f0; f < p.f1; f++) {
-    const int k = f - p.f0;
-    const int L = L_next;
-    const long long off = off_next;
-    L_next = L_next2; off_next = off_next2;
-    const bool det_has = det_has_next;
-    const double det_x = det_x_next, det_y = det_y_next;
-    const bool staged = L <= LINK_STAGE_LEAVES;
-    const unsigned char* cur = link_dyn + (size_t)(k & 1) * LINK_BUF_BYTES;
-    const u64* lc = staged ? reinterpret_cast<const u64*>(cur) : leaf_comb + off;
-    const double* le = staged ? reinterpret_cast<const double*>(cur + sizeof(u64) * LINK_STAGE_LEAVES) : leaf_err + off;
-    const double* lx = staged ? reinterpret_cast<const double*>(cur + (sizeof(u64) + sizeof(double)) * LINK_STAGE_LEAVES) : leaf_xyz + 3 * off;
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();  // this frame's list has landed; everyone is done with the previous frame (and its buffer)
-    if (k + 1 < nf) stage((k + 1) & 1, L_next, off_next); else asm volatile("cp.async.commit_group;" ::: "memory");
-    if (k + 2 < nf) { L_next2 = leaf_cnt[k + 2]; off_next2 = leaf_off[k + 2]; }
-    fetch_det(f + 1, det_has_next, det_x_next, det_y_next);
+  for (int k = 0; k < nf; k++) {
+    const int f = fa + k, b = k & 1;
+    const int L = L_n1, nd = nd_n1;
+    const long long off = off_n1;
+    L_n1 = L_n2; off_n1 = off_n2; nd_n1 = nd_n2; doff_n1 = doff_n2;
+    __syncwarp();  // every lane is done with the other buffer (frame k - 1)
+    if (lane == 0 && k + 1 < nf) stage(b ^ 1, f + 1, L_n1, off_n1, nd_n1, doff_n1);
+    meta(k + 2, L_n2, off_n2, nd_n2, doff_n2);
+    CLS_PROF(0);
+    cls_mbar_wait(&full[b], (uint32_t)((k >> 1) & 1));
+    CLS_PROF(1);
+    const unsigned char* base = link_dyn + (size_t)b * L_::BUF_BYTES;
+    const u64* rec = L <= L_::MAX_LEAVES ? reinterpret_cast<const u64*>(base) : leaf_rec + (size_t)off * RW;
+    const FrameDet* dets = reinterpret_cast<const FrameDet*>(base + L_::REC_BYTES);
+    const int* zs = reinterpret_cast<const int*>(base + L_::REC_BYTES + L_::DET_BYTES);
 
-    // ---- phase 1: tracking (:119-135) ----
-    // (i) the pixel rays of this frame's detections, once (they do not depend on the path)
-    if (det_thread) {
-      s_ndet[tid] = det_has;
-      if (det_has) ref::make_dir(ray, det_c, det_x, det_y, s_dir[tid]);
+    // ---- which paths track (:121-123) ----
+    bool act = false;
+    if (lane < D) {
+      const int n = S.n[lane];
+      const double* last = S.tail[lane][min(max(n, 1), PATH_TAIL) - 1];
+      act = n != 0 && !(last[0] == 0 && last[1] == 0 && last[2] == 0);
     }
-    for (int i = tid; i < C * 16; i += LINK_THREADS) s_gate[i / 16][i % 16] = (i % 16) == 0 ? 0xffffffffu : 0u;  // choice 0 ("none") is always available
-    if (tid < D) {
-      const int n = S.n[tid];
-      const double* last = S.tail[tid][min(max(n, 1), PATH_TAIL) - 1];
-      s_active[tid] = n != 0 && !(last[0] == 0 && last[1] == 0 && last[2] == 0);  // :121-123
-      s_cand[tid] = 0x7fffffff;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      unsigned m = 0;
-      for (int np = 0; np < D; np++) m |= (s_active[np] ? 1u : 0u) << np;
-      s_active_mask = m;
-      s_found_mask = 0;
-    }
-    // (ii) the MAX_STEP ray gate of every (path, detection), :228-236 -- a path's last point is last frame's
-    for (int i = tid; i < D * C * TRI_MAX_DETS; i += LINK_THREADS) {
-      const int np = i / (C * TRI_MAX_DETS), k = i % (C * TRI_MAX_DETS), c = k / TRI_MAX_DETS, d = k % TRI_MAX_DETS;
-      const int n = S.n[np];
-      if (n == 0 || !s_ndet[k]) continue;
-      const double* last = S.tail[np][min(n, PATH_TAIL) - 1];
-      if (ref::dist_to_ray(ray.pos[c], s_dir[k], last[0], last[1], last[2]) < MAX_STEP) atomicOr(&s_gate[c][d + 1], 1u << np);
-    }
-    __syncthreads();
-    // (iii) The leaves are stored in priority order, so "the first element the reference's priority_queue pops
-    // that passes :241-246" is, per path, the admissible leaf of SMALLEST index.  All threads scan the list 256
-    // leaves at a time; one AND over the cameras of the transposed gate words gives the set of paths a leaf is
-    // gated for, the distance test runs only for those, and the winners are taken with atomicMin.  The scan
-    // stops as soon as every tracked path has a candidate.  Combinations used by earlier paths are ignored here ...
-    const int lane = tid & 31, warp = tid >> 5;
-    auto gate_ok = [&](int np, u64 comb) {
-      bool ok = true;
-      for (int c = 0; c < C; c++) ok = ok && ((s_gate[c][(comb >> (4 * c)) & 15] >> np) & 1u);
-      return ok;
-    };
+    const unsigned act_mask = __ballot_sync(0xffffffffu, act);
+    const int n_act = __popc(act_mask);
+    if (act) s_act[__popc(act_mask & ((1u << lane) - 1))] = lane;
+    // this lane's camera (lane < C): the bits of its detections, to count the cameras a gate touches
+    u64 cam_bits[W];
     {
-      const unsigned active_mask = s_active_mask;
-      for (int base = 0; active_mask && base < L; base += LINK_THREADS) {
-        const int i = base + tid;
-        if (i < L) {
-          const u64 comb = lc[i];
-          unsigned ap = active_mask;
-          for (int c = 0; c < C; c++) ap &= s_gate[c][(comb >> (4 * c)) & 15];
-          if (ap && le[i] < p.error_) {
-            while (ap) {
-              const int np = __ffs(ap) - 1;
-              ap &= ap - 1;
-              const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
-              if (dist3(lx + 3 * i, last) < MAX_STEP) {  // cv::norm(c.point - pos) < MAX_STEP, :244
-                atomicMin(&s_cand[np], i);
-                atomicOr(&s_found_mask, 1u << np);
-              }
-            }
-          }
-        }
-        __syncthreads();
-        if (__syncthreads_and(s_found_mask == active_mask)) break;  // (second barrier: everyone has read the mask before the next round writes it)
+      const int b0 = lane < C ? zs[HDR_PREF + lane] : 0, b1 = lane < C ? zs[HDR_PREF + lane + 1] : 0;
+#pragma unroll
+      for (int w = 0; w < W; w++) {
+        const int lo = max(b0 - 64 * w, 0), hi = min(b1 - 64 * w, 64);
+        cam_bits[w] = hi > lo ? ((hi == 64 ? ~0ull : ((1ull << hi) - 1)) & ~((1ull << lo) - 1)) : 0ull;
       }
     }
-    if (tid < D && s_cand[tid] == 0x7fffffff) s_cand[tid] = -1;
-    __syncthreads();
-    // (iv) ... and resolved here in path order by warp 0: a candidate that does not collide with an earlier
-    // path's pick is also the first of the filtered list; otherwise walk the list again with the filter.
-    // Phase 2 (pickBestCombinations, :200-217) follows on the same warp: ONE pass in priority order keeping
-    // every leaf that collides with nothing kept so far -- literally the reference's pop loop.
-    if (warp == 0) {
-      // lane np owns path np's speculative pick; the picks are confirmed in path order with shuffles (the
-      // common case touches no memory), and all confirmed paths are written at once, one lane per path
-      int cand = (lane < D && s_active[lane]) ? s_cand[lane] : -1;
-      u64 comb = cand >= 0 ? lc[cand] : 0ull;
-      bool clashed = false;  // my pick collides with a confirmed earlier one
-      unsigned accepted = 0;
-      for (int np = 0; np < D; np++) {
-        int c_np = __shfl_sync(0xffffffffu, cand, np);
-        if (c_np < 0) continue;
-        if (__shfl_sync(0xffffffffu, (int)clashed, np)) {  // rare (404 of 14 738 picks on S09_D6): walk the list again with the used filter
-          const int n_used = __popc(accepted);
-          const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
-          c_np = -1;
-          for (int base = 0; base < L && c_np < 0; base += 32) {
-            const int i = base + lane;
-            bool ok = i < L && gate_ok(np, lc[i]) && le[i] < p.error_;
-            for (int u = 0; u < n_used && ok; u++) ok = !conflicts(lc[i], s_used[u]);
-            if (ok) ok = dist3(lx + 3 * i, last) < MAX_STEP;
-            const unsigned hit = __ballot_sync(0xffffffffu, ok);
-            if (hit) c_np = base + __ffs(hit) - 1;
-          }
-          if (lane == np) { cand = c_np; comb = c_np >= 0 ? lc[c_np] : 0ull; }
-          if (c_np < 0) continue;
+    __syncwarp();
+    // ---- the MAX_STEP ray gate (:228-236): lane <-> detection, one ballot per (32 detections, path) IS a slice of the gate mask ----
+    for (int t = 0; 32 * t < nd; t++) {
+      const int di = 32 * t + lane;
+      const bool have = di < nd;
+      const FrameDet& fd = dets[have ? di : 0];
+      const double d0 = fd.dir[0], d1 = fd.dir[1], d2 = fd.dir[2], o0 = fd.org[0], o1 = fd.org[1], o2 = fd.org[2];
+      for (int ai = 0; ai < n_act; ai += 2) {  // two paths per step: independent chains
+        const int npa = s_act[ai], npb = s_act[min(ai + 1, n_act - 1)];
+        const double* la = S.tail[npa][min(S.n[npa], PATH_TAIL) - 1];
+        const double* lb = S.tail[npb][min(S.n[npb], PATH_TAIL) - 1];
+        const double ax = la[0] - o0, ay = la[1] - o1, az = la[2] - o2, bx = lb[0] - o0, by = lb[1] - o1, bz = lb[2] - o2;  // distToRay, Triangulator.cpp:3-9
+        const double acx = d1 * az - d2 * ay, acy = d2 * ax - d0 * az, acz = d0 * ay - d1 * ax;
+        const double bcx = d1 * bz - d2 * by, bcy = d2 * bx - d0 * bz, bcz = d0 * by - d1 * bx;
+        const bool ga = have && sqrt_below_step(acx * acx + acy * acy + acz * acz);
+        const bool gb = have && sqrt_below_step(bcx * bcx + bcy * bcy + bcz * bcz);
+        const unsigned sa = __ballot_sync(0xffffffffu, ga), sb = __ballot_sync(0xffffffffu, gb);
+        if (lane == 0) { s_gate[npa][t] = sa; if (ai + 1 < n_act) s_gate[npb][t] = sb; }
+      }
+    }
+    __syncwarp();
+    CLS_PROF(2);
+
+    // ---- phase 1: tracking (:119-135), paths in order ----
+    u64 used[W];
+#pragma unroll
+    for (int w = 0; w < W; w++) used[w] = w == W - 1 ? POISON : 0ull;
+    unsigned processed = 0;
+    const int n_slices = (nd + 31) >> 5;
+    for (int ai = 0; ai < n_act; ai++) {
+      const int np = s_act[ai];
+      u64 g[W];
+#pragma unroll
+      for (int w = 0; w < W; w++) {
+        const unsigned lo = 2 * w < n_slices ? s_gate[np][2 * w] : 0u, hi = 2 * w + 1 < n_slices ? s_gate[np][2 * w + 1] : 0u;
+        g[w] = ((u64)hi << 32) | lo;
+      }
+      bool touched = false;
+#pragma unroll
+      for (int w = 0; w < W; w++) touched = touched || (g[w] & cam_bits[w]);
+      const int cams_in_gate = __popc(__ballot_sync(0xffffffffu, touched));
+      if (cams_in_gate < MIN_CAMERAS) continue;  // fillCombinationQueue on the gated container yields nothing
+      const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
+      const double lx = last[0], ly = last[1], lz = last[2];
+      int pick = -1;
+      // leaves with fewer unused cameras than the gate leaves empty cannot lie inside it: start at their end; 128 leaves per step
+      for (int i0 = zs[C - cams_in_gate] & ~31; i0 < L && pick < 0; i0 += 128) {
+        unsigned cand[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + 32 * u + lane;
+          bool ok = i < L;
+          const u64* r = rec + (size_t)(ok ? i : 0) * RW;
+#pragma unroll
+          for (int w = 0; w < W; w++) { const u64 m = r[w]; ok = ok && !(m & ~g[w]) && !(m & used[w]); }
+          cand[u] = __ballot_sync(0xffffffffu, ok);
         }
-        const u64 pick = __shfl_sync(0xffffffffu, comb, np);
-        if (lane == np) s_used[__popc(accepted)] = pick;
-        accepted |= 1u << np;
-        if (lane > np && cand >= 0) clashed = clashed || conflicts(comb, pick);
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (cand[u] && pick < 0) {  // cv::norm(c.point - pos) < MAX_STEP, :244 -- only for the few leaves inside the gate
+            bool ok = (cand[u] >> lane) & 1u;
+            if (ok) {
+              double x, y, z;
+              rec_point(rec + (size_t)(i0 + 32 * u + lane) * RW, x, y, z);
+              x -= lx; y -= ly; z -= lz;
+              ok = sqrt_below_step(x * x + y * y + z * z);
+            }
+            const unsigned hit = __ballot_sync(0xffffffffu, ok);
+            if (hit) pick = i0 + 32 * u + __ffs(hit) - 1;
+          }
+        }
+      }
+      if (pick >= 0) {
+        const u64* r = rec + (size_t)pick * RW;
+#pragma unroll
+        for (int w = 0; w < W; w++) used[w] |= r[w];
+        processed |= 1u << np;
+        if (lane == 0) {
+          double x, y, z;
+          rec_point(r, x, y, z);
+          emit(np, f, r[W + 3], x, y, z, 1);
+          n_phase1++;
+        }
         __syncwarp();
       }
-      if (accepted >> lane & 1u) emit(lane, f, comb, lx + 3 * cand, 1);
-      if (lane == 0) { n_phase1 += __popc(accepted); s_processed = accepted; s_n_used = __popc(accepted); s_n_fin = 0; }
     }
-    __syncthreads();
-    if (__popc(s_processed) == D) continue;  // :137
-    // ---- phase 2: pickBestCombinations (:200-217).  The reference pops the whole queue in priority order
-    // and keeps every combination that collides with nothing kept so far; with the leaves in priority
-    // order that is: repeatedly take the FIRST live leaf and kill everything that collides with it.  All
-    // threads filter (each owns leaves tid, tid+256, ...; live flags in a register), one block-wide
-    // min-index reduction per kept combination.
-    {
-      const int n_used = s_n_used;
-      u64 live = 0;  // bit k <=> leaf tid + k * LINK_THREADS is still a candidate (L <= 64 * LINK_THREADS, checked in (A))
-      for (int k = 0, i = tid; i < L; k++, i += LINK_THREADS) {
-        bool ok = le[i] < p.error_;
-        for (int u = 0; u < n_used && ok; u++) ok = !conflicts(lc[i], s_used[u]);
-        live |= (ok ? 1ull : 0ull) << k;
-      }
-      for (int round = 0; round < LINK_MAX_FINAL; round++) {
-        int first = live ? tid + (__ffsll((long long)live) - 1) * LINK_THREADS : 0x7fffffff;
-        for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
-        if (lane == 0) s_first[round & 1][warp] = first;
-        __syncthreads();
-        first = s_first[round & 1][0];
-        for (int w = 1; w < LINK_THREADS / 32; w++) first = min(first, s_first[round & 1][w]);
-        if (first == 0x7fffffff) break;
-        const u64 pick = lc[first];
-        if (tid == 0) { s_fin[round] = pick; s_fin_idx[round] = first; s_n_fin = round + 1; }
-        for (int k = 0, i = tid; i < L; k++, i += LINK_THREADS)
-          if ((live >> k & 1ull) && (i == first || conflicts(lc[i], pick))) live &= ~(1ull << k);
-      }
-    }
-    __syncthreads();
+    CLS_PROF(3);
+    if (__popc(processed) == D) continue;  // :137
 
-    // ---- classifyPaths (:262-332): the (combination, path) tail distances in parallel, the rest on one thread ----
-    {
-      const int nf = s_n_fin;
-      for (int i = tid; i < nf * D; i += LINK_THREADS) {
-        const int ci = i / D, j = i % D;
-        const int npc = min(S.n[j], PATH_TAIL);
-        double dist = -1;
-        if (npc > 0) {
-          const double* pt = lx + 3 * s_fin_idx[ci];
-          dist = 0;
-          for (int t = 0; t < npc; t++) dist += dist3(S.tail[j][t], pt);
-          dist /= (double)npc;
+    // ---- phase 2: pickBestCombinations (:200-217), one forward pass with a running used mask, 128 leaves per step ----
+    int n_fin = 0;
+    for (int i0 = 0; i0 < L; i0 += 128) {
+      u64 m[4][W];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + 32 * u + lane;
+#pragma unroll
+        for (int w = 0; w < W; w++) m[u][w] = i < L ? rec[(size_t)i * RW + w] : ~0ull;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        bool ok = true;
+#pragma unroll
+        for (int w = 0; w < W; w++) ok = ok && !(m[u][w] & used[w]);
+        unsigned hit = __ballot_sync(0xffffffffu, ok);
+        while (hit) {
+          const int j = __ffs(hit) - 1;
+          bool clash = false;
+#pragma unroll
+          for (int w = 0; w < W; w++) {
+            const u64 mj = __shfl_sync(0xffffffffu, m[u][w], j);
+            used[w] |= mj;
+            clash = clash || (m[u][w] & mj);
+          }
+          if (n_fin < LINK_MAX_FINAL) { if (lane == 0) s_fin_idx[n_fin] = i0 + 32 * u + j; n_fin++; }
+          else overflow_final = true;
+          ok = ok && !clash;  // lane j clashes with itself
+          hit = __ballot_sync(0xffffffffu, ok);
         }
-        s_pdist[ci][j] = dist;
       }
     }
-    __syncthreads();
-    if (tid == 0) {
-      const int nf = s_n_fin;
-      int cp_comb[LINK_MAX_FINAL], cp_path[LINK_MAX_FINAL];
-      double cp_err[LINK_MAX_FINAL];
-      unsigned processed = s_processed;
-      for (int i = 0; i < nf; i++) {
-        int bestPath = 0;
-        double bestDist = -1;
-        for (int j = 0; j < D; j++) {
-          if (processed >> j & 1u) continue;
-          if (min(S.n[j], PATH_TAIL) == 0) continue;
-          const double dist = s_pdist[i][j];
-          if (dist < bestDist || bestDist == -1) { bestDist = dist; bestPath = j; }
-        }
-        // std::sort(greater<>) of <= 16 elements is an insertion sort in libstdc++: stable, ascending error
-        int k = i - 1;
-        while (k >= 0 && bestDist < cp_err[k]) { cp_comb[k + 1] = cp_comb[k]; cp_path[k + 1] = cp_path[k]; cp_err[k + 1] = cp_err[k]; k--; }
-        cp_comb[k + 1] = i; cp_path[k + 1] = bestPath; cp_err[k + 1] = bestDist;
+    __syncwarp();
+    CLS_PROF(4);
+
+    // ---- classifyPaths (:262-332): the (combination, path) tail distances one pair per lane, then per combination its
+    // nearest unprocessed path (lane <-> combination), the insertion sort and the assignment on lane 0 ----
+    for (int q = lane; q < n_fin * D; q += 32) {
+      const int ci = q / D, j = q - ci * D;
+      const int npc = min(S.n[j], PATH_TAIL);
+      double dist = -1;
+      if (npc > 0) {
+        double pt[3];
+        rec_point(rec + (size_t)s_fin_idx[ci] * RW, pt[0], pt[1], pt[2]);
+        dist = 0;
+        for (int t = 0; t < npc; t++) dist += dist3(S.tail[j][t], pt);
+        dist /= (double)npc;
       }
-      for (int k = 0; k < nf; k++) {
+      s_pdist[ci][j] = dist;
+    }
+    __syncwarp();
+    for (int i = lane; i < n_fin; i += 32) {  // :269-297 (the processed set does not change until the assignment loop)
+      int bestPath = 0;
+      double bestDist = -1;
+      for (int j = 0; j < D; j++) {
+        if (processed >> j & 1u) continue;
+        if (min(S.n[j], PATH_TAIL) == 0) continue;
+        const double dist = s_pdist[i][j];
+        if (dist < bestDist || bestDist == -1) { bestDist = dist; bestPath = j; }
+      }
+      s_cp_path[i] = bestPath; s_cp_err[i] = bestDist;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      // std::sort(greater<>) of <= 16 elements is an insertion sort in libstdc++: stable, ascending error
+      for (int i = 0; i < n_fin; i++) {
+        const int pth = s_cp_path[i];
+        const double e = s_cp_err[i];
+        int kk = i - 1;
+        while (kk >= 0 && e < s_cp_err[kk]) { s_cp_comb[kk + 1] = s_cp_comb[kk]; s_cp_path[kk + 1] = s_cp_path[kk]; s_cp_err[kk + 1] = s_cp_err[kk]; kk--; }
+        s_cp_comb[kk + 1] = i; s_cp_path[kk + 1] = pth; s_cp_err[kk + 1] = e;
+      }
+      unsigned done = processed;
+      for (int kk = 0; kk < n_fin; kk++) {
         int target = -1;
-        if (processed >> cp_path[k] & 1u) {
+        if (done >> s_cp_path[kk] & 1u) {
           for (int i = 0; i < D; i++) if (S.n[i] == 0) { target = i; break; }
         } else {
-          target = cp_path[k];
+          target = s_cp_path[kk];
         }
         if (target != -1) {
-          emit(target, f, s_fin[cp_comb[k]], lx + 3 * s_fin_idx[cp_comb[k]], 2);
-          processed |= 1u << target;
+          const u64* r = rec + (size_t)s_fin_idx[s_cp_comb[kk]] * RW;
+          double x, y, z;
+          rec_point(r, x, y, z);
+          emit(target, f, r[W + 3], x, y, z, 2);
+          done |= 1u << target;
           n_phase2++;
         }
       }
     }
-    __syncthreads();
+    __syncwarp();
+    CLS_PROF(5);
   }
-  __syncthreads();
-  for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += LINK_THREADS) ((int*)state)[i] = ((const int*)&S)[i];
-  if (tid == 0) { atomicAdd(&ctr->phase1, n_phase1); atomicAdd(&ctr->phase2, n_phase2); }
+  __syncwarp();
+  for (int i = lane; i < (int)(sizeof(LinkState) / sizeof(int)); i += 32) ((int*)st)[i] = ((const int*)&S)[i];
+#ifdef TRI_TUNING
+  if (lane == 0) for (int q = 0; q < 8; q++) atomicAdd(&ctr->prof[q], prof_acc[q]);
+#endif
+  if (lane == 0) {
+    atomicAdd(&ctr->phase1, n_phase1); atomicAdd(&ctr->phase2, n_phase2);
+    if (overflow_final) atomicExch(&ctr->overflow_final, 1);
+  }
 }
 
 // Grow-only device buffer: the classifier's work space lives on the engine across calls (cudaMalloc /
@@ -571,7 +715,15 @@ struct DevBuf {
 };
 
 struct ClsWork {
-  DevBuf offs, dets, paths, assign, phase, state, ctr, front, txyz, terr, lcomb, lerr, lxyz, loff, lcnt;
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  double enumerate_ms = 0, link_ms = 0;  // of the call in progress
+  ~ClsWork() { for (cudaEvent_t v : ev) if (v) cudaEventDestroy(v); }
+  cudaError_t events() {
+    for (cudaEvent_t& v : ev)
+      if (!v) { cudaError_t err = cudaEventCreate(&v); if (err != cudaSuccess) return err; }
+    return cudaSuccess;
+  }
+  DevBuf offs, dets, paths, assign, phase, state, ctr, front, txyz, terr, lrec, loff, lcnt, hdr, fdet, fdoff, fdcnt, seq;
   // tri_classify_begin / tri_classify_finish: the enumerated shard waiting for its linking pass
   bool pending = false;
   ClsParams job;
@@ -589,135 +741,226 @@ using namespace tri;
     if (err__ != cudaSuccess) return cuda_fail(err__, #call);  \
   } while (0)
 
-extern "C" int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t* det_offsets,
-                            const double* dets_xy, int n_frames, double* out_paths, int8_t* out_assign, uint8_t* out_phase,
-                            tri_classify_stats* stats) {
+namespace {
+
+// argument checks shared by the entry points; *n_det = detections in the CSR
+int cls_check(tri_engine* e, int mode, int n_drones, const int32_t* det_offsets, const double* dets_xy, int n_frames, int64_t* n_det) {
   if (!e) return fail(TRI_ERR_ARG, "null engine");
   if (mode != TRI_MATRIX && mode != TRI_RAY) return fail(TRI_ERR_ARG, "mode must be TRI_MATRIX or TRI_RAY");
   const int C = e->n_cams;
   if (C > CLS_MAX_CAMS) return fail(TRI_ERR_ARG, "the classifier handles at most 16 cameras (the search is exponential in the camera count)");
   if (n_drones < 1 || n_drones > TRI_MAX_DRONES) return fail(TRI_ERR_ARG, "n_drones must be in [1, TRI_MAX_DRONES]");
-  if (n_frames < 0 || !out_paths) return fail(TRI_ERR_ARG, "bad output arguments");
-  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n_frames < 0) return fail(TRI_ERR_ARG, "bad frame count");
+  *n_det = 0;
   if (n_frames == 0) return TRI_OK;
   if (!det_offsets) return fail(TRI_ERR_ARG, "null detection offsets");
-  const size_t n_offs = (size_t)C * (n_frames + 1);
-  int64_t n_det = 0;
   for (int c = 0; c < C; c++) {
     const int32_t* o = det_offsets + (size_t)c * (n_frames + 1);
     for (int f = 0; f < n_frames; f++) {
       if (o[f + 1] < o[f]) return fail(TRI_ERR_ARG, "detection offsets must be non-decreasing");
       if (o[f + 1] - o[f] > TRI_MAX_DETS) return fail(TRI_ERR_CAPACITY, "more than TRI_MAX_DETS detections on one camera in one frame");
     }
-    n_det = std::max<int64_t>(n_det, o[n_frames]);
+    *n_det = std::max<int64_t>(*n_det, o[n_frames]);
   }
-  if (n_det > 0 && !dets_xy) return fail(TRI_ERR_ARG, "null detections");
-  DeviceGuard g(e->device);
-  cudaStream_t s = e->stream;
+  if (*n_det > 0 && !dets_xy) return fail(TRI_ERR_ARG, "null detections");
+  return TRI_OK;
+}
 
-  ClsParams p;
-  p.n_cams = C; p.n_drones = n_drones; p.n_frames = n_frames;
+ClsParams cls_params(const tri_engine* e, int mode, unsigned flags, int n_drones, int n_frames) {
+  ClsParams p{};
+  p.n_cams = e->n_cams; p.n_drones = n_drones; p.n_frames = n_frames;
   p.solver = mode == TRI_MATRIX ? 0 : (flags & TRI_RAY_REFERENCE_LM) ? 1 : 2;
   p.error_ = mode == TRI_MATRIX ? MAX_ERROR_MATRIX : MAX_ERROR_RAY;  // DroneClassifier.cpp:3-10
+  p.W = e->n_cams <= 8 ? 2 : 4;
+  return p;
+}
 
-  if (!e->cls_work) { e->cls_work = new ClsWork(); e->cls_work_free = free_cls_work; }
-  ClsWork& W = *static_cast<ClsWork*>(e->cls_work);
-  DevBuf &d_offs = W.offs, &d_dets = W.dets, &d_paths = W.paths, &d_assign = W.assign, &d_phase = W.phase, &d_state = W.state,
-         &d_ctr = W.ctr, &d_front = W.front, &d_txyz = W.txyz, &d_terr = W.terr, &d_lcomb = W.lcomb, &d_lerr = W.lerr,
-         &d_lxyz = W.lxyz, &d_loff = W.loff, &d_lcnt = W.lcnt;
-  const size_t sz_paths = sizeof(double) * 3 * n_drones * (size_t)n_frames, sz_assign = (size_t)n_drones * n_frames * C,
-               sz_phase = (size_t)n_drones * n_frames;
-  TRI_CUDA(d_offs.alloc(sizeof(int32_t) * n_offs));
-  TRI_CUDA(d_dets.alloc(sizeof(double) * 2 * n_det));
-  TRI_CUDA(d_paths.alloc(sz_paths));
-  TRI_CUDA(d_assign.alloc(sz_assign));
-  TRI_CUDA(d_phase.alloc(sz_phase));
-  TRI_CUDA(d_state.alloc(sizeof(LinkState)));
-  TRI_CUDA(d_ctr.alloc(sizeof(ClsCounters)));
-  TRI_CUDA(cudaMemcpyAsync(d_offs.p, det_offsets, sizeof(int32_t) * n_offs, cudaMemcpyHostToDevice, s));
-  if (n_det) TRI_CUDA(cudaMemcpyAsync(d_dets.p, dets_xy, sizeof(double) * 2 * n_det, cudaMemcpyHostToDevice, s));
-  TRI_CUDA(cudaMemsetAsync(d_paths.p, 0, sz_paths, s));
-  TRI_CUDA(cudaMemsetAsync(d_assign.p, 0xff, sz_assign, s));
-  TRI_CUDA(cudaMemsetAsync(d_phase.p, 0, sz_phase, s));
-  TRI_CUDA(cudaMemsetAsync(d_state.p, 0, sizeof(LinkState), s));
-  TRI_CUDA(cudaMemsetAsync(d_ctr.p, 0, sizeof(ClsCounters), s));
+int cls_grid(const tri_engine* e, int frames) {
+  // every resident CTA slot gets a frame: the tree expansion is latency-bound (dependent FP64 chains, idle
+  // lanes on narrow levels), so occupancy is what hides it -- 4 CTAs per SM instead of 2: S09_D6 with the
+  // exact LM 3.88 -> 2.82 s (profiles/r1_cls_grid_sweep.log)
+  int per_sm = 2;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, enumerate_kernel, CLS_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+#ifdef TRI_TUNING
+  if (const char* v = getenv("TRI_CLS_CTAS_PER_SM")) per_sm = std::max(1, atoi(v));
+#endif
+  return std::max(1, std::min(frames, per_sm * e->sm_count));
+}
 
-  int batch = std::min(n_frames, 8192);
-  int cap = 1 << 14;
-  long long leaf_cap = 4ll << 20;
-  int grid = 0;
-  auto alloc_work = [&]() -> int {
-    // every resident CTA slot gets a frame: the tree expansion is latency-bound (dependent FP64 chains, idle
-    // lanes on narrow levels), so occupancy is what hides it -- 4 CTAs per SM instead of 2: S09_D6 with the
-    // exact LM 3.88 -> 2.82 s (profiles/r1_cls_grid_sweep.log)
-    int per_sm = 2;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, enumerate_kernel, CLS_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
-    if (const char* v = getenv("TRI_CLS_CTAS_PER_SM")) per_sm = std::max(1, atoi(v));  // tuning override
-    grid = std::max(1, std::min(batch, per_sm * e->sm_count));
-    TRI_CUDA(d_front.alloc(sizeof(u64) * 2 * (size_t)cap * grid));
-    TRI_CUDA(d_txyz.alloc(sizeof(double) * 3 * (size_t)cap * grid));
-    TRI_CUDA(d_terr.alloc(sizeof(double) * (size_t)cap * grid));
-    TRI_CUDA(d_lcomb.alloc(sizeof(u64) * leaf_cap));
-    TRI_CUDA(d_lerr.alloc(sizeof(double) * leaf_cap));
-    TRI_CUDA(d_lxyz.alloc(sizeof(double) * 3 * leaf_cap));
-    TRI_CUDA(d_loff.alloc(sizeof(long long) * batch));
-    TRI_CUDA(d_lcnt.alloc(sizeof(int) * batch));
+// (A) on frames [p.f0, p.f1) with the work buffers sized by (cap, leaf_cap); *h = the counters after the launch
+int cls_enumerate(tri_engine* e, ClsWork& W, ClsParams& p, int cap, long long leaf_cap, int64_t n_det_batch, ClsCounters* h) {
+  cudaStream_t s = e->stream;
+  const int frames = p.f1 - p.f0, grid = cls_grid(e, frames);
+  TRI_CUDA(W.front.alloc(sizeof(u64) * 2 * (size_t)cap * grid));
+  TRI_CUDA(W.txyz.alloc(sizeof(double) * 3 * (size_t)cap * grid));
+  TRI_CUDA(W.terr.alloc(sizeof(double) * (size_t)cap * grid));
+  TRI_CUDA(W.lrec.alloc(sizeof(u64) * rec_words(p.W) * (size_t)leaf_cap));
+  TRI_CUDA(W.loff.alloc(sizeof(long long) * frames));
+  TRI_CUDA(W.lcnt.alloc(sizeof(int) * frames));
+  TRI_CUDA(W.hdr.alloc(sizeof(int) * HDR_INTS * (size_t)frames));
+  TRI_CUDA(W.fdet.alloc(sizeof(FrameDet) * (size_t)std::max<int64_t>(n_det_batch, 1)));
+  TRI_CUDA(W.fdoff.alloc(sizeof(long long) * frames));
+  TRI_CUDA(W.fdcnt.alloc(sizeof(int) * frames));
+  p.cap = cap; p.leaf_cap = leaf_cap;
+  ClsCounters* ctr = W.ctr.as<ClsCounters>();
+  TRI_CUDA(cudaMemsetAsync(&ctr->leaf_total, 0, 2 * sizeof(u64), s));  // leaf_total, fdet_total: offsets within this batch
+  TRI_CUDA(W.events());
+  TRI_CUDA(cudaEventRecord(W.ev[0], s));
+  enumerate_kernel<<<grid, CLS_THREADS, 0, s>>>(e->rig64, e->ray, p, W.offs.as<int32_t>(), W.dets.as<double>(), W.front.as<u64>(),
+                                                 W.txyz.as<double>(), W.terr.as<double>(), W.lrec.as<u64>(), W.loff.as<long long>(),
+                                                 W.lcnt.as<int>(), W.hdr.as<int>(), W.fdet.as<FrameDet>(), W.fdoff.as<long long>(),
+                                                 W.fdcnt.as<int>(), ctr);
+  e->launches++;
+  TRI_CUDA(cudaGetLastError());
+  TRI_CUDA(cudaEventRecord(W.ev[1], s));
+  TRI_CUDA(cudaMemcpyAsync(h, ctr, sizeof(*h), cudaMemcpyDeviceToHost, s));
+  TRI_CUDA(cudaStreamSynchronize(s));
+  float ms = 0;
+  TRI_CUDA(cudaEventElapsedTime(&ms, W.ev[0], W.ev[1]));
+  W.enumerate_ms += ms;
+  return TRI_OK;
+}
+
+// (B) on the batch last enumerated: one warp per sequence (seq == nullptr: the single sequence [p.f0, p.f1))
+int cls_link(tri_engine* e, ClsWork& W, const ClsParams& p, int n_seq, const int2* d_seq, bool want_assign, bool want_phase) {
+  cudaStream_t s = e->stream;
+  auto go = [&](auto kern, int bytes) -> int {
+    TRI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    TRI_CUDA(W.events());
+    TRI_CUDA(cudaEventRecord(W.ev[1], s));
+    kern<<<n_seq, 32, bytes, s>>>(e->ray, p, d_seq, W.lrec.as<u64>(), W.loff.as<long long>(), W.lcnt.as<int>(), W.hdr.as<int>(),
+                                  W.fdet.as<FrameDet>(), W.fdoff.as<long long>(), W.fdcnt.as<int>(), W.state.as<LinkState>(),
+                                  W.paths.as<double>(), want_assign ? W.assign.as<int8_t>() : nullptr,
+                                  want_phase ? W.phase.as<uint8_t>() : nullptr, W.ctr.as<ClsCounters>());
+    e->launches++;
+    TRI_CUDA(cudaGetLastError());
+    TRI_CUDA(cudaEventRecord(W.ev[2], s));
+    TRI_CUDA(cudaEventSynchronize(W.ev[2]));  // the next batch's enumeration reuses the buffers this pass reads
+    float ms = 0;
+    TRI_CUDA(cudaEventElapsedTime(&ms, W.ev[1], W.ev[2]));
+    W.link_ms += ms;
     return TRI_OK;
   };
-  int st = alloc_work();
-  if (st != TRI_OK) return st;
-  constexpr int LINK_DYN_BYTES = 2 * (int)((sizeof(u64) + 4 * sizeof(double)) * LINK_STAGE_LEAVES);
-  TRI_CUDA(cudaFuncSetAttribute(link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LINK_DYN_BYTES));
+  return p.W == 2 ? go(link_warp_kernel<2>, LinkLayout<2>::BYTES) : go(link_warp_kernel<4>, LinkLayout<4>::BYTES);
+}
 
+int64_t dets_in_frames(const int32_t* det_offsets, int C, int n_frames, int f0, int f1) {
+  int64_t n = 0;
+  for (int c = 0; c < C; c++) { const int32_t* o = det_offsets + (size_t)c * (n_frames + 1); n += o[f1] - o[f0]; }
+  return n;
+}
+
+void cls_stats(tri_classify_stats* stats, const ClsCounters& h, int max_frontier, const ClsWork& W) {
+  if (!stats) return;
+  stats->enumerate_us = (int64_t)(W.enumerate_ms * 1e3); stats->link_us = (int64_t)(W.link_ms * 1e3);
+  stats->nodes = (int64_t)h.nodes; stats->solves = (int64_t)h.solves; stats->leaves = (int64_t)h.leaves;
+  stats->lm_iters = (int64_t)h.lm_iters; stats->phase1 = (int64_t)h.phase1; stats->phase2 = (int64_t)h.phase2;
+  stats->ties = (int64_t)h.ties; stats->max_frontier = max_frontier;
+}
+
+// Classify n_seq independent sequences laid back to back in one CSR of n_frames frames (seq_bounds[s] .. seq_bounds[s+1]).
+int cls_run(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t* det_offsets, const double* dets_xy, int n_frames,
+            int n_seq, const int32_t* seq_bounds, double* out_paths, int8_t* out_assign, uint8_t* out_phase, tri_classify_stats* stats) {
+  int64_t n_det = 0;
+  int st = cls_check(e, mode, n_drones, det_offsets, dets_xy, n_frames, &n_det);
+  if (st != TRI_OK) return st;
+  if (!out_paths && n_frames > 0) return fail(TRI_ERR_ARG, "bad output arguments");
+  if (stats) memset(stats, 0, sizeof(*stats));
+  if (n_frames == 0) return TRI_OK;
+  const int C = e->n_cams;
+  DeviceGuard g(e->device);
+  cudaStream_t s = e->stream;
+  ClsParams p = cls_params(e, mode, flags, n_drones, n_frames);
+  if (!e->cls_work) { e->cls_work = new ClsWork(); e->cls_work_free = free_cls_work; }
+  ClsWork& W = *static_cast<ClsWork*>(e->cls_work);
+  W.pending = false;
+  W.enumerate_ms = W.link_ms = 0;
+  const size_t n_offs = (size_t)C * (n_frames + 1);
+  const size_t sz_paths = sizeof(double) * 3 * n_drones * (size_t)n_frames, sz_assign = (size_t)n_drones * n_frames * C,
+               sz_phase = (size_t)n_drones * n_frames;
+  const bool multi = n_seq > 1;
+  TRI_CUDA(W.offs.alloc(sizeof(int32_t) * n_offs));
+  TRI_CUDA(W.dets.alloc(sizeof(double) * 2 * n_det));
+  TRI_CUDA(W.paths.alloc(sz_paths));
+  TRI_CUDA(W.assign.alloc(sz_assign));
+  TRI_CUDA(W.phase.alloc(sz_phase));
+  TRI_CUDA(W.state.alloc(sizeof(LinkState) * (size_t)std::max(n_seq, 1)));
+  TRI_CUDA(W.ctr.alloc(sizeof(ClsCounters)));
+  TRI_CUDA(cudaMemcpyAsync(W.offs.p, det_offsets, sizeof(int32_t) * n_offs, cudaMemcpyHostToDevice, s));
+  if (n_det) TRI_CUDA(cudaMemcpyAsync(W.dets.p, dets_xy, sizeof(double) * 2 * n_det, cudaMemcpyHostToDevice, s));
+  TRI_CUDA(cudaMemsetAsync(W.paths.p, 0, sz_paths, s));
+  TRI_CUDA(cudaMemsetAsync(W.assign.p, 0xff, sz_assign, s));
+  TRI_CUDA(cudaMemsetAsync(W.phase.p, 0, sz_phase, s));
+  TRI_CUDA(cudaMemsetAsync(W.state.p, 0, sizeof(LinkState) * (size_t)std::max(n_seq, 1), s));
+  TRI_CUDA(cudaMemsetAsync(W.ctr.p, 0, sizeof(ClsCounters), s));
+  std::vector<int2> seq;
+  if (multi) {  // every sequence links on its own warp: all frames are enumerated first, in one batch
+    for (int q = 0; q < n_seq; q++) {
+      if (seq_bounds[q] < 0 || seq_bounds[q + 1] < seq_bounds[q] || seq_bounds[q + 1] > n_frames) return fail(TRI_ERR_ARG, "sequence bounds must be non-decreasing within [0, n_frames]");
+      seq.push_back(make_int2(seq_bounds[q], seq_bounds[q + 1]));
+    }
+    TRI_CUDA(W.seq.alloc(sizeof(int2) * n_seq));
+    TRI_CUDA(cudaMemcpyAsync(W.seq.p, seq.data(), sizeof(int2) * n_seq, cudaMemcpyHostToDevice, s));
+  }
+
+  int batch = multi ? n_frames : std::min(n_frames, 8192);
+  int cap = 1 << 14;
+  long long leaf_cap = multi ? std::max<long long>(4ll << 20, 1024ll * n_frames) : 4ll << 20;
   ClsCounters h{};
   int max_frontier = 0;
   for (int f0 = 0; f0 < n_frames;) {
     const int f1 = std::min(n_frames, f0 + batch);
-    p.f0 = f0; p.f1 = f1; p.cap = cap; p.leaf_cap = leaf_cap;
+    p.f0 = f0; p.f1 = f1;
     ClsCounters before;
-    TRI_CUDA(cudaMemcpyAsync(&before, d_ctr.p, sizeof(before), cudaMemcpyDeviceToHost, s));
+    TRI_CUDA(cudaMemcpyAsync(&before, W.ctr.p, sizeof(before), cudaMemcpyDeviceToHost, s));
     TRI_CUDA(cudaStreamSynchronize(s));
-    TRI_CUDA(cudaMemsetAsync(&d_ctr.as<ClsCounters>()->leaf_total, 0, sizeof(u64), s));
-    enumerate_kernel<<<grid, CLS_THREADS, 0, s>>>(e->rig64, e->ray, p, d_offs.as<int32_t>(), d_dets.as<double>(), d_front.as<u64>(),
-                                                   d_txyz.as<double>(), d_terr.as<double>(), d_lcomb.as<u64>(), d_lerr.as<double>(),
-                                                   d_lxyz.as<double>(), d_loff.as<long long>(), d_lcnt.as<int>(), d_ctr.as<ClsCounters>());
-    e->launches++;
-    TRI_CUDA(cudaGetLastError());
-    TRI_CUDA(cudaMemcpyAsync(&h, d_ctr.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-    TRI_CUDA(cudaStreamSynchronize(s));
-    if (h.bad_input == 2) return fail(TRI_ERR_CAPACITY, "more than 16384 candidate combinations in one frame");
+    if ((st = cls_enumerate(e, W, p, cap, leaf_cap, dets_in_frames(det_offsets, C, n_frames, f0, f1), &h)) != TRI_OK) return st;
     if (h.bad_input) return fail(TRI_ERR_ARG, "malformed detection offsets");
     if (h.overflow_frontier || h.overflow_leaves) {
-      // grow the work buffers (or shrink the batch) and redo this batch; the statistics of the
-      // aborted attempt are rolled back
-      if (h.overflow_frontier) { if (cap >= (1 << 22)) return fail(TRI_ERR_CAPACITY, "combination frontier exceeds 4M nodes in one frame"); cap *= 4; batch = std::max(1, batch / 4); }
-      if (h.overflow_leaves) { if (batch > 64) batch /= 4; else if (leaf_cap < (256ll << 20)) leaf_cap *= 4; else return fail(TRI_ERR_CAPACITY, "candidate list exceeds device buffer"); }
+      // grow the work buffers (or shrink the batch) and redo this batch; the statistics of the aborted attempt are rolled back
+      if (h.overflow_frontier) { if (cap >= (1 << 22)) return fail(TRI_ERR_CAPACITY, "combination frontier exceeds 4M nodes in one frame"); cap *= 4; if (!multi) batch = std::max(1, batch / 4); }
+      if (h.overflow_leaves) { if (!multi && batch > 64) batch /= 4; else if (leaf_cap < (1ll << 30)) leaf_cap *= 4; else return fail(TRI_ERR_CAPACITY, "candidate list exceeds device buffer"); }
       before.overflow_frontier = before.overflow_leaves = 0;
-      TRI_CUDA(cudaMemcpyAsync(d_ctr.p, &before, sizeof(before), cudaMemcpyHostToDevice, s));
+      TRI_CUDA(cudaMemcpyAsync(W.ctr.p, &before, sizeof(before), cudaMemcpyHostToDevice, s));
       TRI_CUDA(cudaStreamSynchronize(s));
-      if ((st = alloc_work()) != TRI_OK) return st;
       continue;
     }
     max_frontier = std::max(max_frontier, h.max_frontier);
-    link_kernel<<<1, LINK_THREADS, LINK_DYN_BYTES, s>>>(e->ray, p, d_offs.as<int32_t>(), d_dets.as<double>(), d_lcomb.as<u64>(), d_lerr.as<double>(),
-                                            d_lxyz.as<double>(), d_loff.as<long long>(), d_lcnt.as<int>(), d_state.as<LinkState>(),
-                                            d_paths.as<double>(), out_assign ? d_assign.as<int8_t>() : nullptr,
-                                            out_phase ? d_phase.as<uint8_t>() : nullptr, d_ctr.as<ClsCounters>());
-    e->launches++;
-    TRI_CUDA(cudaGetLastError());
+    if ((st = cls_link(e, W, p, multi ? n_seq : 1, multi ? W.seq.as<int2>() : nullptr, out_assign != nullptr, out_phase != nullptr)) != TRI_OK) return st;
     f0 = f1;
   }
-  TRI_CUDA(cudaMemcpyAsync(out_paths, d_paths.p, sz_paths, cudaMemcpyDeviceToHost, s));
-  if (out_assign) TRI_CUDA(cudaMemcpyAsync(out_assign, d_assign.p, sz_assign, cudaMemcpyDeviceToHost, s));
-  if (out_phase) TRI_CUDA(cudaMemcpyAsync(out_phase, d_phase.p, sz_phase, cudaMemcpyDeviceToHost, s));
-  TRI_CUDA(cudaMemcpyAsync(&h, d_ctr.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  TRI_CUDA(cudaMemcpyAsync(out_paths, W.paths.p, sz_paths, cudaMemcpyDeviceToHost, s));
+  if (out_assign) TRI_CUDA(cudaMemcpyAsync(out_assign, W.assign.p, sz_assign, cudaMemcpyDeviceToHost, s));
+  if (out_phase) TRI_CUDA(cudaMemcpyAsync(out_phase, W.phase.p, sz_phase, cudaMemcpyDeviceToHost, s));
+  TRI_CUDA(cudaMemcpyAsync(&h, W.ctr.p, sizeof(h), cudaMemcpyDeviceToHost, s));
   TRI_CUDA(cudaStreamSynchronize(s));
-  if (stats) {
-    stats->nodes = (int64_t)h.nodes; stats->solves = (int64_t)h.solves; stats->leaves = (int64_t)h.leaves;
-    stats->lm_iters = (int64_t)h.lm_iters; stats->phase1 = (int64_t)h.phase1; stats->phase2 = (int64_t)h.phase2;
-    stats->ties = (int64_t)h.ties; stats->max_frontier = max_frontier;
-  }
+  if (h.overflow_final) return fail(TRI_ERR_CAPACITY, "more than 128 disjoint combinations kept in one frame");
+#ifdef TRI_TUNING
+  if (getenv("TRI_CLS_PROFILE"))
+    fprintf(stderr, "link cycles: top %llu | wait %llu | gates %llu | phase1 %llu | phase2 %llu | classifyPaths %llu\n", h.prof[0], h.prof[1],
+            h.prof[2], h.prof[3], h.prof[4], h.prof[5]);
+#endif
+  cls_stats(stats, h, max_frontier, W);
   return TRI_OK;
+}
+
+}  // namespace
+
+extern "C" int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t* det_offsets,
+                            const double* dets_xy, int n_frames, double* out_paths, int8_t* out_assign, uint8_t* out_phase,
+                            tri_classify_stats* stats) {
+  return cls_run(e, mode, flags, n_drones, det_offsets, dets_xy, n_frames, 1, nullptr, out_paths, out_assign, out_phase, stats);
+}
+
+// Many independent sequences (recordings) in one call: sequence q holds the frames [seq_bounds[q], seq_bounds[q+1]) of the
+// CSR; every frame of every sequence is enumerated in one launch and each sequence is linked by its own warp.
+extern "C" int tri_classify_sequences(tri_engine* e, int mode, unsigned flags, int n_drones, int n_seq, const int32_t* seq_bounds,
+                                      const int32_t* det_offsets, const double* dets_xy, int n_frames, double* out_paths,
+                                      int8_t* out_assign, uint8_t* out_phase, tri_classify_stats* stats) {
+  if (n_seq < 1 || !seq_bounds) return fail(TRI_ERR_ARG, "no sequences");
+  if (seq_bounds[0] != 0 || seq_bounds[n_seq] != n_frames) return fail(TRI_ERR_ARG, "sequence bounds must cover [0, n_frames]");
+  if (n_seq == 1) return cls_run(e, mode, flags, n_drones, det_offsets, dets_xy, n_frames, 1, nullptr, out_paths, out_assign, out_phase, stats);
+  return cls_run(e, mode, flags, n_drones, det_offsets, dets_xy, n_frames, n_seq, seq_bounds, out_paths, out_assign, out_phase, stats);
 }
 
 // ---- frame-sharded classification: candidate generation is independent per frame, linking is a
@@ -729,70 +972,36 @@ extern "C" int tri_classify_state_bytes(void) { return (int)sizeof(LinkState); }
 
 extern "C" int tri_classify_begin(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t* det_offsets,
                                   const double* dets_xy, int n_frames) {
-  if (!e) return fail(TRI_ERR_ARG, "null engine");
-  if (mode != TRI_MATRIX && mode != TRI_RAY) return fail(TRI_ERR_ARG, "mode must be TRI_MATRIX or TRI_RAY");
-  const int C = e->n_cams;
-  if (C > CLS_MAX_CAMS) return fail(TRI_ERR_ARG, "the classifier handles at most 16 cameras (the search is exponential in the camera count)");
-  if (n_drones < 1 || n_drones > TRI_MAX_DRONES) return fail(TRI_ERR_ARG, "n_drones must be in [1, TRI_MAX_DRONES]");
-  if (n_frames < 0) return fail(TRI_ERR_ARG, "bad frame count");
-  if (n_frames > 0 && !det_offsets) return fail(TRI_ERR_ARG, "null detection offsets");
-  const size_t n_offs = (size_t)C * (n_frames + 1);
   int64_t n_det = 0;
-  for (int c = 0; c < C && n_frames > 0; c++) {
-    const int32_t* o = det_offsets + (size_t)c * (n_frames + 1);
-    for (int f = 0; f < n_frames; f++) {
-      if (o[f + 1] < o[f]) return fail(TRI_ERR_ARG, "detection offsets must be non-decreasing");
-      if (o[f + 1] - o[f] > TRI_MAX_DETS) return fail(TRI_ERR_CAPACITY, "more than TRI_MAX_DETS detections on one camera in one frame");
-    }
-    n_det = std::max<int64_t>(n_det, o[n_frames]);
-  }
-  if (n_det > 0 && !dets_xy) return fail(TRI_ERR_ARG, "null detections");
+  int st = cls_check(e, mode, n_drones, det_offsets, dets_xy, n_frames, &n_det);
+  if (st != TRI_OK) return st;
+  const int C = e->n_cams;
   DeviceGuard g(e->device);
   cudaStream_t s = e->stream;
   if (!e->cls_work) { e->cls_work = new ClsWork(); e->cls_work_free = free_cls_work; }
   ClsWork& W = *static_cast<ClsWork*>(e->cls_work);
   W.pending = false;
-  ClsParams p;
-  p.n_cams = C; p.n_drones = n_drones; p.n_frames = n_frames;
-  p.solver = mode == TRI_MATRIX ? 0 : (flags & TRI_RAY_REFERENCE_LM) ? 1 : 2;
-  p.error_ = mode == TRI_MATRIX ? MAX_ERROR_MATRIX : MAX_ERROR_RAY;
+  W.enumerate_ms = W.link_ms = 0;
+  ClsParams p = cls_params(e, mode, flags, n_drones, n_frames);
   p.f0 = 0; p.f1 = n_frames;
   W.job = p;
   W.job_max_frontier = 0;
   if (n_frames == 0) { W.pending = true; return TRI_OK; }
+  const size_t n_offs = (size_t)C * (n_frames + 1);
   TRI_CUDA(W.offs.alloc(sizeof(int32_t) * n_offs));
   TRI_CUDA(W.dets.alloc(sizeof(double) * 2 * n_det));
   TRI_CUDA(W.ctr.alloc(sizeof(ClsCounters)));
-  TRI_CUDA(W.loff.alloc(sizeof(long long) * n_frames));
-  TRI_CUDA(W.lcnt.alloc(sizeof(int) * n_frames));
   TRI_CUDA(cudaMemcpyAsync(W.offs.p, det_offsets, sizeof(int32_t) * n_offs, cudaMemcpyHostToDevice, s));
   if (n_det) TRI_CUDA(cudaMemcpyAsync(W.dets.p, dets_xy, sizeof(double) * 2 * n_det, cudaMemcpyHostToDevice, s));
-  int per_sm = 2;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, enumerate_kernel, CLS_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
   int cap = 1 << 14;
   long long leaf_cap = std::max<long long>(4ll << 20, 1024ll * n_frames);
   for (;;) {  // the whole shard's candidates stay resident: on overflow grow the buffers and enumerate again
-    const int grid = std::max(1, std::min(n_frames, per_sm * e->sm_count));
-    TRI_CUDA(W.front.alloc(sizeof(u64) * 2 * (size_t)cap * grid));
-    TRI_CUDA(W.txyz.alloc(sizeof(double) * 3 * (size_t)cap * grid));
-    TRI_CUDA(W.terr.alloc(sizeof(double) * (size_t)cap * grid));
-    TRI_CUDA(W.lcomb.alloc(sizeof(u64) * leaf_cap));
-    TRI_CUDA(W.lerr.alloc(sizeof(double) * leaf_cap));
-    TRI_CUDA(W.lxyz.alloc(sizeof(double) * 3 * leaf_cap));
     TRI_CUDA(cudaMemsetAsync(W.ctr.p, 0, sizeof(ClsCounters), s));
-    p.cap = cap; p.leaf_cap = leaf_cap;
-    enumerate_kernel<<<grid, CLS_THREADS, 0, s>>>(e->rig64, e->ray, p, W.offs.as<int32_t>(), W.dets.as<double>(), W.front.as<u64>(),
-                                                   W.txyz.as<double>(), W.terr.as<double>(), W.lcomb.as<u64>(), W.lerr.as<double>(),
-                                                   W.lxyz.as<double>(), W.loff.as<long long>(), W.lcnt.as<int>(), W.ctr.as<ClsCounters>());
-    e->launches++;
-    TRI_CUDA(cudaGetLastError());
     ClsCounters h{};
-    TRI_CUDA(cudaMemcpyAsync(&h, W.ctr.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-    TRI_CUDA(cudaStreamSynchronize(s));
-    if (h.bad_input == 2) return fail(TRI_ERR_CAPACITY, "more than 16384 candidate combinations in one frame");
+    if ((st = cls_enumerate(e, W, p, cap, leaf_cap, n_det, &h)) != TRI_OK) return st;
     if (h.bad_input) return fail(TRI_ERR_ARG, "malformed detection offsets");
     if (h.overflow_frontier) { if (cap >= (1 << 22)) return fail(TRI_ERR_CAPACITY, "combination frontier exceeds 4M nodes in one frame"); cap *= 4; continue; }
-    if (h.overflow_leaves) { if (leaf_cap >= (256ll << 20)) return fail(TRI_ERR_CAPACITY, "candidate list exceeds device buffer"); leaf_cap *= 4; continue; }
+    if (h.overflow_leaves) { if (leaf_cap >= (1ll << 30)) return fail(TRI_ERR_CAPACITY, "candidate list exceeds device buffer"); leaf_cap *= 4; continue; }
     W.job_max_frontier = h.max_frontier;
     break;
   }
@@ -828,14 +1037,8 @@ extern "C" int tri_classify_finish(tri_engine* e, const void* state_in, void* st
   TRI_CUDA(cudaMemsetAsync(W.phase.p, 0, sz_phase, s));
   if (state_in) TRI_CUDA(cudaMemcpyAsync(W.state.p, state_in, sizeof(LinkState), cudaMemcpyHostToDevice, s));
   else TRI_CUDA(cudaMemsetAsync(W.state.p, 0, sizeof(LinkState), s));
-  constexpr int LINK_DYN_BYTES = 2 * (int)((sizeof(u64) + 4 * sizeof(double)) * LINK_STAGE_LEAVES);
-  TRI_CUDA(cudaFuncSetAttribute(link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LINK_DYN_BYTES));
-  link_kernel<<<1, LINK_THREADS, LINK_DYN_BYTES, s>>>(e->ray, p, W.offs.as<int32_t>(), W.dets.as<double>(), W.lcomb.as<u64>(), W.lerr.as<double>(),
-                                                      W.lxyz.as<double>(), W.loff.as<long long>(), W.lcnt.as<int>(), W.state.as<LinkState>(),
-                                                      W.paths.as<double>(), out_assign ? W.assign.as<int8_t>() : nullptr,
-                                                      out_phase ? W.phase.as<uint8_t>() : nullptr, W.ctr.as<ClsCounters>());
-  e->launches++;
-  TRI_CUDA(cudaGetLastError());
+  int st = cls_link(e, W, p, 1, nullptr, out_assign != nullptr, out_phase != nullptr);
+  if (st != TRI_OK) return st;
   ClsCounters h{};
   TRI_CUDA(cudaMemcpyAsync(out_paths, W.paths.p, sz_paths, cudaMemcpyDeviceToHost, s));
   if (out_assign) TRI_CUDA(cudaMemcpyAsync(out_assign, W.assign.p, sz_assign, cudaMemcpyDeviceToHost, s));
@@ -843,11 +1046,8 @@ extern "C" int tri_classify_finish(tri_engine* e, const void* state_in, void* st
   if (state_out) TRI_CUDA(cudaMemcpyAsync(state_out, W.state.p, sizeof(LinkState), cudaMemcpyDeviceToHost, s));
   TRI_CUDA(cudaMemcpyAsync(&h, W.ctr.p, sizeof(h), cudaMemcpyDeviceToHost, s));
   TRI_CUDA(cudaStreamSynchronize(s));
-  if (stats) {
-    stats->nodes = (int64_t)h.nodes; stats->solves = (int64_t)h.solves; stats->leaves = (int64_t)h.leaves;
-    stats->lm_iters = (int64_t)h.lm_iters; stats->phase1 = (int64_t)h.phase1; stats->phase2 = (int64_t)h.phase2;
-    stats->ties = (int64_t)h.ties; stats->max_frontier = W.job_max_frontier;
-  }
+  if (h.overflow_final) return fail(TRI_ERR_CAPACITY, "more than 128 disjoint combinations kept in one frame");
+  cls_stats(stats, h, W.job_max_frontier, W);
   return TRI_OK;
 }
 
@@ -915,6 +1115,7 @@ extern "C" int tri_classify_multi(tri_engine* const* engines, int n_engines, int
     if (stats) {
       stats->nodes += st.nodes; stats->solves += st.solves; stats->leaves += st.leaves; stats->lm_iters += st.lm_iters;
       stats->phase1 += st.phase1; stats->phase2 += st.phase2; stats->ties += st.ties;
+      stats->enumerate_us = std::max(stats->enumerate_us, st.enumerate_us); stats->link_us += st.link_us;
       stats->max_frontier = std::max(stats->max_frontier, st.max_frontier);
     }
   }

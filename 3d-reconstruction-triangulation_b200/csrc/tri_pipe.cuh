@@ -5,9 +5,14 @@
 // the 12-byte points leave through a per-warp transpose as 16-byte streaming stores.  Two feeders for the ring:
 //   * stream_kernel: every thread prefetches its own pixels with cp.async (LDGSTS) and waits on its own copy group --
 //     no cross-warp synchronisation at all;
-//   * tma_kernel: a producer warp streams each camera's row segment with 1-D bulk async copies (cp.async.bulk, SASS
-//     UBLKCP) that complete on a per-stage `full` mbarrier; the eight consumer warps wait on it, pull their pixels
-//     into registers and release the stage through an `empty` mbarrier (one arrival per warp) -- no CTA barrier.
+//   * tma_kernel (TUNING builds only): a producer warp streams each camera's row segment with 1-D bulk async copies
+//     (cp.async.bulk, SASS UBLKCP) that complete on a per-stage `full` mbarrier; the eight consumer warps wait on it,
+//     pull their pixels into registers and release the stage through an `empty` mbarrier (one arrival per warp) -- no
+//     CTA barrier.  Measured in round 2 (profiles/r2_dlt_variants.log): with a near-empty solve it is the faster
+//     feeder (1.10 ms per 100 M frames = 6.9 TB/s, above the driver's copy figure), but under every real solve it
+//     loses to the per-thread feeder (FP32 DLT 1.295 vs 1.269 ms, FP32 ray 1.45 vs 1.32, FP64 DLT 1.96 vs 1.86): the
+//     ninth warp costs registers (288 threads per CTA) and the consumers of a CTA wake together on the stage's
+//     barrier instead of drifting apart.  So the product library ships stream_kernel only.
 // Algorithmic traffic: 8 B x cameras in, 12 B out per frame; nothing is re-read (profiles/: 7.59 GB per 100 M frames).
 #pragma once
 #include "tri_batch.cuh"
@@ -278,7 +283,8 @@ stream_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restri
 }
 
 
-// ---- warp-specialised TMA feeder ---------------------------------------------------------------------
+// ---- warp-specialised TMA feeder (tuning builds) ---------------------------------------------------
+#ifdef TRI_TUNING
 constexpr int TMA_THREADS = BATCH_THREADS + 32;  // eight consumer warps + one producer warp
 
 template <class TS, int NC, int PIX, int STAGES, int MINB, bool WIDE>
@@ -368,11 +374,22 @@ tma_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restrict_
   }
 }
 
+#endif  // TRI_TUNING
+
 // which optional outputs the caller wants -> the WIDE instantiation; alignment of whatever is written
 static inline bool wants_wide(const BatchOut& out) { return out.xyz_f64 || out.err || out.iters; }
 static inline bool stream_aligned(const void* xy, int64_t row_bytes, int align, const BatchOut& out) {
   return !(((uintptr_t)xy % align) || (row_bytes % align) || ((uintptr_t)out.xyz_f32 & 15) || ((uintptr_t)out.xyz_f64 & 15) ||
            ((uintptr_t)out.mask & 7) || ((uintptr_t)out.err & 15) || ((uintptr_t)out.iters & 7));
+}
+
+template <class TS, int N, int PIX, int STAGES, int MINB, bool WIDE, bool TMA>
+static auto feeder_kernel() {
+#ifdef TRI_TUNING
+  if constexpr (TMA) return tma_kernel<TS, N, PIX, STAGES, MINB, WIDE>;
+  else
+#endif
+  return stream_kernel<TS, N, PIX, STAGES, MINB, WIDE>;
 }
 
 template <class TS, int PIX, int STAGES, int MINB, bool WIDE, bool TMA>
@@ -383,8 +400,8 @@ static cudaError_t launch_stream_w(const LaunchCtx& ctx, const typename TS::Rig&
   cudaError_t err = cudaSuccess;
 #define TRI_CASE(N)                                                                                                     \
   case N: {                                                                                                             \
-    auto kern = TMA ? tma_kernel<TS, N, PIX, STAGES, MINB, WIDE> : stream_kernel<TS, N, PIX, STAGES, MINB, WIDE>;        \
-    constexpr int threads = TMA ? TMA_THREADS : BATCH_THREADS;                                                          \
+    auto kern = feeder_kernel<TS, N, PIX, STAGES, MINB, WIDE, TMA>();                                                    \
+    constexpr int threads = TMA ? BATCH_THREADS + 32 : BATCH_THREADS;                                                   \
     constexpr int bytes = STAGES * N * BATCH_THREADS * (int)sizeof(Raw) + (BATCH_THREADS / 32) * 32 * FPT * 12 +         \
                           ((TS::CONST_BYTES + 15) & ~15) + (TMA ? 2 * STAGES * 8 : 0);                                  \
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);                               \
