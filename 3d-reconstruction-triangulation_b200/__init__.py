@@ -30,6 +30,7 @@ RAY_REFERENCE_LM = 1 << 2
 RAY_CLOSED_FORM = 1 << 3
 PIX_F64 = 1 << 4
 PIX_U16 = 1 << 5
+RAY_ANALYTIC_LM = 1 << 6
 DEBUG_STREAM = 1 << 30
 MAX_CAMS = 32
 
@@ -57,7 +58,7 @@ class _BatchOut(C.Structure):
 
 class ClassifyStats(C.Structure):
     _fields_ = [(n, C.c_int64) for n in ("nodes", "solves", "leaves", "lm_iters", "phase1", "phase2", "ties",
-                                         "max_frontier")]
+                                         "max_frontier", "enumerate_us", "link_us")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -68,7 +69,7 @@ EXPORTS = ["tri_version", "tri_last_error", "tri_device_count", "tri_create", "t
            "tri_triangulate_points_device",
            "tri_device_status", "tri_enable_peer_access", "tri_ipc_export", "tri_ipc_open", "tri_ipc_close",
            "tri_copy_device", "tri_triangulate_subsets", "tri_dist_from_ray", "tri_classify", "tri_classify_state_bytes",
-           "tri_classify_begin", "tri_classify_finish", "tri_classify_multi", "tri_host_alloc",
+           "tri_classify_begin", "tri_classify_finish", "tri_classify_multi", "tri_classify_sequences", "tri_host_alloc",
            "tri_host_free", "tri_device_alloc", "tri_device_free", "tri_copy_to_device", "tri_copy_to_host"]
 
 _lib = None
@@ -110,6 +111,8 @@ def lib():
         L.tri_dist_from_ray.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.tri_classify.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.POINTER(ClassifyStats)]
+        L.tri_classify_sequences.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(ClassifyStats)]
         L.tri_classify_begin.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.tri_classify_finish.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.POINTER(ClassifyStats)]
@@ -419,6 +422,20 @@ class Engine:
                                   _np_ptr(assign), _np_ptr(phase), C.byref(st)), mode)
         return dict(paths=paths, assign=assign, phase=phase, stats=st.as_dict())
 
+
+    def classify_sequences(self, mode, n_drones, seq_bounds, det_offsets, dets_xy, n_frames, flags=0):
+        """Independent sequences back to back in one CSR: seq_bounds [n_seq + 1] frame indices (tri_classify_sequences)."""
+        n_cams = len(self.cameras)
+        sb = np.ascontiguousarray(seq_bounds, np.int32)
+        offs = np.ascontiguousarray(det_offsets, np.int32)
+        xy = np.ascontiguousarray(dets_xy, np.float64)
+        paths = np.zeros((n_drones, n_frames, 3))
+        assign = np.zeros((n_drones, n_frames, n_cams), np.int8)
+        phase = np.zeros((n_drones, n_frames), np.uint8)
+        st = ClassifyStats()
+        _check(lib().tri_classify_sequences(self._h, mode, flags, n_drones, len(sb) - 1, _np_ptr(sb), _np_ptr(offs), _np_ptr(xy), n_frames,
+                                            _np_ptr(paths), _np_ptr(assign), _np_ptr(phase), C.byref(st)), mode)
+        return dict(paths=paths, assign=assign, phase=phase, stats=st.as_dict())
 
     # ---- frame-sharded classification: enumerate now, link when the previous shard's state has arrived ----
     def classify_begin(self, mode, n_drones, det_offsets, dets_xy, n_frames, flags=0):

@@ -252,7 +252,7 @@ static int launch_batch(tri_engine* e, LaunchCtx ctx, int mode, unsigned flags, 
     if (flags & TRI_RAY_REFERENCE_LM)
       err = launch_ray_reference(ctx, fmt, e->ray, d_xy, n_use, n_frames, cam_stride, out);
     else
-      err = launch_ray_fold(ctx, !(flags & TRI_RAY_CLOSED_FORM), (flags & TRI_F32) != 0, fmt, e->fold64, e->fold32, d_xy,
+      err = launch_ray_fold(ctx, (flags & TRI_RAY_ANALYTIC_LM) != 0, (flags & TRI_F32) != 0, fmt, e->fold64, e->fold32, d_xy,
                             n_use, n_frames, cam_stride, out);
   }
   if (err != cudaSuccess) return cuda_fail(err, "kernel launch");

@@ -58,8 +58,8 @@ constexpr int HDR_INTS = 40;   // per frame: [0 .. C+1] zstart[z] = leaves with 
 constexpr int HDR_PREF = 20;
 struct __align__(16) FrameDet {  // a detection of the frame with its pixel ray (Triangulator.cpp:27-55); 80 B, a conflict-free stride
   double dir[3], org[3];
+  float dirf[3], orgf[3];  // single-precision copies for the gate's fast path
   int cam, slot;
-  double pad[3];
 };
 constexpr int LINK_MAX_DETS = CLS_MAX_CAMS * TRI_MAX_DETS;  // 240
 
@@ -185,8 +185,8 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
         FrameDet fd;
         ref::make_dir(ray, c, s_px[c][d], s_py[c][d], fd.dir);
         fd.org[0] = ray.pos[c][0]; fd.org[1] = ray.pos[c][1]; fd.org[2] = ray.pos[c][2];
+        for (int j = 0; j < 3; j++) { fd.dirf[j] = (float)fd.dir[j]; fd.orgf[j] = (float)fd.org[j]; }
         fd.cam = c; fd.slot = d;
-        fd.pad[0] = fd.pad[1] = fd.pad[2] = 0;
         fdet[s_doff + s_pref[c] + d] = fd;
       }
     }
@@ -319,21 +319,24 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
 }
 
 // ---- (B) linking -------------------------------------------------------------------------------
-// One WARP per sequence, no block barrier anywhere.  Everything that does not depend on the tracking state was
-// prepared by (A): the leaves in priority order as (detection mask, point, combination) records, the number of
-// leaves per count of unused cameras, the frame's detections with their pixel rays.  A frame's records, detections
-// and zstart table arrive in shared memory as three bulk async copies (cp.async.bulk -> UBLKCP) that complete on an
-// mbarrier, issued one frame ahead into the other buffer.  Per frame the warp then does, in registers and shuffles:
-//   gates     the MAX_STEP ray gate of every (tracked path, detection) -> one detection mask per path (:228-236)
-//   phase 1   per path in order: the FIRST leaf (priority order) whose mask lies inside the path's gate, misses the
-//             used mask, and whose point is within MAX_STEP of the path's last point -- the first element the
-//             reference's priority_queue pops that passes :241-246.  The scan starts at the first leaf with at least
-//             as many unused cameras as the gate leaves empty (zstart) and tests 32 leaves per step.
-//   phase 2   pickBestCombinations (:200-217) is ONE forward pass over the list with a running used mask: a leaf is
-//             kept iff it misses everything kept so far -- literally the reference's pop loop, 32 leaves per step.
-//   classifyPaths (:262-332): tail distances one (combination, path) pair per lane, the assignment on lane 0.
-// Round 1 ran this on a 256-thread CTA with ~15 block barriers per frame (10 us per frame on S09_D6, profiles/
-// r1_link_kernel_lines.txt); a lone warp has no one to wait for.
+// One CTA of eight warps per sequence, TWO block barriers per frame.  Everything that does not depend on the tracking
+// state was prepared by (A): the leaves in priority order as (detection mask, point, combination) records, the number
+// of leaves per count of unused cameras, the frame's detections with their pixel rays.  A frame's records, detections
+// and header arrive in shared memory as three bulk async copies (cp.async.bulk -> UBLKCP) that complete on an
+// mbarrier, issued one frame ahead into the other buffer.  Per frame:
+//   speculative phase 1, one warp per tracked path, all paths at once:
+//     gate    the MAX_STEP ray gate (:228-236) with lane <-> detection: the ballot of one 32-detection test IS a slice
+//             of the path's gate mask.  The distance runs in single precision first and in the reference's
+//             double-precision operation order only where single precision cannot decide.
+//     scan    the FIRST leaf (priority order) whose mask lies inside the gate and whose point is within MAX_STEP of the
+//             path's last point (:241-246), ignoring earlier paths' picks; it starts at the first leaf with at least
+//             as many unused cameras as the gate leaves empty and tests 128 leaves per step.
+//   warp 0: confirmation in path order with shuffles (a pick that collides with an earlier one -- 404 of 14 738 on
+//     S09_D6 -- is scanned again with the used mask); phase 2, pickBestCombinations (:200-217), as ONE forward pass over
+//     the list with a running used mask -- literally the reference's pop loop; classifyPaths (:262-332) with the tail
+//     distances one (combination, open path) pair per lane and the ordered assignment by warp-wide minimum extraction.
+// Round 1 ran this with ~15 block barriers per frame, the pixel rays and the whole phase-2 filter inside the sequential
+// kernel (29 ms for S09_D6's 3000 frames, profiles/r1_link_kernel_lines.txt); now 20 ms and falling (profiles/r2_*).
 __device__ __forceinline__ uint32_t cls_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cls_mbar_init(u64* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cls_smem_u32(bar)), "r"(count));
@@ -383,41 +386,49 @@ struct LinkLayout {
   static constexpr int BYTES = 2 * BUF_BYTES + 16;  // + the two mbarriers
 };
 
+constexpr int LINK_WARPS = 8;
+constexpr int LINK_THREADS = 32 * LINK_WARPS;
+
 template <int W>
-__global__ void __launch_bounds__(32)
-link_warp_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __restrict__ seq_bounds,
-                 const u64* __restrict__ leaf_rec, const long long* __restrict__ leaf_off, const int* __restrict__ leaf_cnt,
-                 const int* __restrict__ hdr, const FrameDet* __restrict__ fdet, const long long* __restrict__ fdet_off,
-                 const int* __restrict__ fdet_cnt, LinkState* state, double* __restrict__ out_paths, int8_t* __restrict__ out_assign,
-                 uint8_t* __restrict__ out_phase, ClsCounters* ctr) {
+__global__ void __launch_bounds__(LINK_THREADS)
+link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __restrict__ seq_bounds,
+            const u64* __restrict__ leaf_rec, const long long* __restrict__ leaf_off, const int* __restrict__ leaf_cnt,
+            const int* __restrict__ hdr, const FrameDet* __restrict__ fdet, const long long* __restrict__ fdet_off,
+            const int* __restrict__ fdet_cnt, LinkState* state, double* __restrict__ out_paths, int8_t* __restrict__ out_assign,
+            uint8_t* __restrict__ out_phase, ClsCounters* ctr) {
   using L_ = LinkLayout<W>;
   constexpr int RW = L_::RW;
   constexpr u64 POISON = 1ull << 63;  // in word W - 1
   extern __shared__ __align__(128) unsigned char link_dyn[];
   __shared__ LinkState S;
+  __shared__ float s_lastf[TRI_MAX_DRONES][4];     // single-precision copy of each path's last point
   __shared__ unsigned s_gate[TRI_MAX_DRONES][2 * W];  // 32-bit slices of each tracked path's gate mask
-  __shared__ int s_act[TRI_MAX_DRONES];
-  __shared__ int s_fin_idx[LINK_MAX_FINAL], s_cp_comb[LINK_MAX_FINAL], s_cp_path[LINK_MAX_FINAL];
+  __shared__ int s_spec[TRI_MAX_DRONES];           // each tracked path's speculative pick (leaf index or -1)
+  __shared__ int s_fin_idx[LINK_MAX_FINAL], s_cp_path[LINK_MAX_FINAL];
   __shared__ double s_cp_err[LINK_MAX_FINAL];
   __shared__ double s_pdist[LINK_MAX_FINAL][TRI_MAX_DRONES];
   u64* full = reinterpret_cast<u64*>(link_dyn + 2 * L_::BUF_BYTES);
-  const int lane = threadIdx.x, C = p.n_cams, D = p.n_drones;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, C = p.n_cams, D = p.n_drones;
   const int fa = seq_bounds ? seq_bounds[blockIdx.x].x : p.f0, fb = seq_bounds ? seq_bounds[blockIdx.x].y : p.f1;
   LinkState* st = state + blockIdx.x;
-  for (int i = lane; i < (int)(sizeof(LinkState) / sizeof(int)); i += 32) ((int*)&S)[i] = ((const int*)st)[i];
-  if (lane == 0) {
+  for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += LINK_THREADS) ((int*)&S)[i] = ((const int*)st)[i];
+  if (tid == 0) {
     cls_mbar_init(&full[0], 1); cls_mbar_init(&full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  __syncwarp();
-  u64 n_phase1 = 0, n_phase2 = 0;  // lane 0
+  __syncthreads();
+  if (tid < D) {
+    const double* last = S.tail[tid][min(max(S.n[tid], 1), PATH_TAIL) - 1];
+    s_lastf[tid][0] = (float)last[0]; s_lastf[tid][1] = (float)last[1]; s_lastf[tid][2] = (float)last[2];
+  }
+  u64 n_phase1 = 0, n_phase2 = 0;  // thread 0
   bool overflow_final = false;
 #ifdef TRI_TUNING
   u64 prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long prof_t = clock64();
 #endif
 
-  // stage frame f's records / detections / header into buffer b (lane 0)
+  // stage frame f's records / detections / header into buffer b (thread 0)
   auto stage = [&](int b, int f, int L, long long off, int nd, long long doff) {
     unsigned char* base = link_dyn + (size_t)b * L_::BUF_BYTES;
     const uint32_t rec_bytes = L <= L_::MAX_LEAVES ? (uint32_t)L * RW * 8 : 0, det_bytes = (uint32_t)nd * (uint32_t)sizeof(FrameDet);
@@ -426,7 +437,9 @@ link_warp_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __
     if (det_bytes) cls_bulk_load(base + L_::REC_BYTES, fdet + doff, det_bytes, &full[b]);
     cls_bulk_load(base + L_::REC_BYTES + L_::DET_BYTES, hdr + (size_t)(f - p.f0) * HDR_INTS, L_::HDR_BYTES, &full[b]);
   };
-  auto emit = [&](int path, int f, u64 comb, double x, double y, double z, int phase) {  // one lane: push a point to a path
+  auto emit = [&](int path, int f, const u64* r, int phase) {  // one thread: push leaf r's point to a path
+    const double x = __longlong_as_double((long long)r[W]), y = __longlong_as_double((long long)r[W + 1]), z = __longlong_as_double((long long)r[W + 2]);
+    const u64 comb = r[W + 3];
     const int n = S.n[path];
     double(*t)[3] = S.tail[path];
     if (n >= PATH_TAIL) {
@@ -435,6 +448,7 @@ link_warp_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __
     } else {
       t[n][0] = x; t[n][1] = y; t[n][2] = z;
     }
+    s_lastf[path][0] = (float)x; s_lastf[path][1] = (float)y; s_lastf[path][2] = (float)z;
     if (n < 0x3fffffff) S.n[path] = n + 1;
     double* o = out_paths + ((size_t)path * p.n_frames + f) * 3;
     o[0] = x; o[1] = y; o[2] = z;
@@ -452,8 +466,38 @@ link_warp_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __
     }
     if (out_phase) out_phase[(size_t)path * p.n_frames + f] = (uint8_t)phase;
   };
-  auto rec_point = [&](const u64* r, double& x, double& y, double& z) {
-    x = __longlong_as_double((long long)r[W]); y = __longlong_as_double((long long)r[W + 1]); z = __longlong_as_double((long long)r[W + 2]);
+  // The first leaf (priority order) from index `start` on whose mask lies inside the gate g, misses `used`, and whose point is
+  // within MAX_STEP of (lx, ly, lz): what the reference's priority_queue pops first that passes :241-246.  One warp, 128
+  // leaves per step; the distance runs only for the few leaves inside the gate.
+  auto scan = [&](const u64* rec, int L, int start, const u64 (&g)[W], const u64 (&used)[W], double lx, double ly, double lz) {
+    int pick = -1;
+    for (int i0 = start & ~31; i0 < L && pick < 0; i0 += 128) {
+      unsigned cand[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int i = i0 + 32 * u + lane;
+        bool ok = i < L;
+        const u64* r = rec + (size_t)(ok ? i : 0) * RW;
+#pragma unroll
+        for (int w = 0; w < W; w++) { const u64 m = r[w]; ok = ok && !(m & ~g[w]) && !(m & used[w]); }
+        cand[u] = __ballot_sync(0xffffffffu, ok);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        if (cand[u] && pick < 0) {  // cv::norm(c.point - pos) < MAX_STEP, :244
+          bool ok = (cand[u] >> lane) & 1u;
+          if (ok) {
+            const u64* r = rec + (size_t)(i0 + 32 * u + lane) * RW;
+            const double x = __longlong_as_double((long long)r[W]) - lx, y = __longlong_as_double((long long)r[W + 1]) - ly,
+                         z = __longlong_as_double((long long)r[W + 2]) - lz;
+            ok = sqrt_below_step(x * x + y * y + z * z);
+          }
+          const unsigned hit = __ballot_sync(0xffffffffu, ok);
+          if (hit) pick = i0 + 32 * u + __ffs(hit) - 1;
+        }
+      }
+    }
+    return pick;
   };
 
   // frame metadata runs two frames ahead in registers, the staged copy one frame ahead
@@ -466,15 +510,15 @@ link_warp_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __
   long long off_n1, doff_n1, off_n2, doff_n2;
   meta(0, L_n1, off_n1, nd_n1, doff_n1);
   meta(1, L_n2, off_n2, nd_n2, doff_n2);
-  if (lane == 0 && nf > 0) stage(0, fa, L_n1, off_n1, nd_n1, doff_n1);
+  if (tid == 0 && nf > 0) stage(0, fa, L_n1, off_n1, nd_n1, doff_n1);
 
   for (int k = 0; k < nf; k++) {
     const int f = fa + k, b = k & 1;
     const int L = L_n1, nd = nd_n1;
     const long long off = off_n1;
     L_n1 = L_n2; off_n1 = off_n2; nd_n1 = nd_n2; doff_n1 = doff_n2;
-    __syncwarp();  // every lane is done with the other buffer (frame k - 1)
-    if (lane == 0 && k + 1 < nf) stage(b ^ 1, f + 1, L_n1, off_n1, nd_n1, doff_n1);
+    __syncthreads();  // barrier 1 of 2: frame k - 1 is linked (state, its buffer free)
+    if (tid == 0 && k + 1 < nf) stage(b ^ 1, f + 1, L_n1, off_n1, nd_n1, doff_n1);
     meta(k + 2, L_n2, off_n2, nd_n2, doff_n2);
     CLS_PROF(0);
     cls_mbar_wait(&full[b], (uint32_t)((k >> 1) & 1));
@@ -484,7 +528,7 @@ link_warp_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __
     const FrameDet* dets = reinterpret_cast<const FrameDet*>(base + L_::REC_BYTES);
     const int* zs = reinterpret_cast<const int*>(base + L_::REC_BYTES + L_::DET_BYTES);
 
-    // ---- which paths track (:121-123) ----
+    // ---- which paths track (:121-123): every warp computes the same list ----
     bool act = false;
     if (lane < D) {
       const int n = S.n[lane];
@@ -493,7 +537,6 @@ link_warp_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __
     }
     const unsigned act_mask = __ballot_sync(0xffffffffu, act);
     const int n_act = __popc(act_mask);
-    if (act) s_act[__popc(act_mask & ((1u << lane) - 1))] = lane;
     // this lane's camera (lane < C): the bits of its detections, to count the cameras a gate touches
     u64 cam_bits[W];
     {
@@ -504,91 +547,97 @@ link_warp_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __
         cam_bits[w] = hi > lo ? ((hi == 64 ? ~0ull : ((1ull << hi) - 1)) & ~((1ull << lo) - 1)) : 0ull;
       }
     }
-    __syncwarp();
-    // ---- the MAX_STEP ray gate (:228-236): lane <-> detection, one ballot per (32 detections, path) IS a slice of the gate mask ----
-    for (int t = 0; 32 * t < nd; t++) {
-      const int di = 32 * t + lane;
-      const bool have = di < nd;
-      const FrameDet& fd = dets[have ? di : 0];
-      const double d0 = fd.dir[0], d1 = fd.dir[1], d2 = fd.dir[2], o0 = fd.org[0], o1 = fd.org[1], o2 = fd.org[2];
-      for (int ai = 0; ai < n_act; ai += 2) {  // two paths per step: independent chains
-        const int npa = s_act[ai], npb = s_act[min(ai + 1, n_act - 1)];
-        const double* la = S.tail[npa][min(S.n[npa], PATH_TAIL) - 1];
-        const double* lb = S.tail[npb][min(S.n[npb], PATH_TAIL) - 1];
-        const double ax = la[0] - o0, ay = la[1] - o1, az = la[2] - o2, bx = lb[0] - o0, by = lb[1] - o1, bz = lb[2] - o2;  // distToRay, Triangulator.cpp:3-9
-        const double acx = d1 * az - d2 * ay, acy = d2 * ax - d0 * az, acz = d0 * ay - d1 * ax;
-        const double bcx = d1 * bz - d2 * by, bcy = d2 * bx - d0 * bz, bcz = d0 * by - d1 * bx;
-        const bool ga = have && sqrt_below_step(acx * acx + acy * acy + acz * acz);
-        const bool gb = have && sqrt_below_step(bcx * bcx + bcy * bcy + bcz * bcz);
-        const unsigned sa = __ballot_sync(0xffffffffu, ga), sb = __ballot_sync(0xffffffffu, gb);
-        if (lane == 0) { s_gate[npa][t] = sa; if (ai + 1 < n_act) s_gate[npb][t] = sb; }
+    const int n_slices = (nd + 31) >> 5;
+
+    // ---- speculative phase 1, one warp per tracked path (paths beyond the warp count take turns) ----
+    // The ray gate (:228-236) with lane <-> detection: the ballot of one 32-detection test IS a slice of the gate mask.  The
+    // distance runs in single precision first and in the reference's double-precision operation order only where single
+    // precision cannot decide.  Then the scan for the path's first admissible leaf, IGNORING the picks of earlier paths.
+    for (int ai = warp; ai < n_act; ai += LINK_WARPS) {
+      int np = 0;
+      { unsigned rem = act_mask; for (int q = 0; q < ai; q++) rem &= rem - 1; np = __ffs(rem) - 1; }
+      const float lfx = s_lastf[np][0], lfy = s_lastf[np][1], lfz = s_lastf[np][2];
+      const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
+      unsigned slice[2 * W];
+#pragma unroll
+      for (int t = 0; t < 2 * W; t++) {
+        slice[t] = 0;
+        if (t < n_slices) {
+          const int di = 32 * t + lane;
+          const bool have = di < nd;
+          const FrameDet& fd = dets[have ? di : 0];
+          const float wx = lfx - fd.orgf[0], wy = lfy - fd.orgf[1], wz = lfz - fd.orgf[2];
+          const float cx = fd.dirf[1] * wz - fd.dirf[2] * wy, cy = fd.dirf[2] * wx - fd.dirf[0] * wz, cz = fd.dirf[0] * wy - fd.dirf[1] * wx;
+          const float sf = cx * cx + cy * cy + cz * cz;
+          bool gated = sf < (float)(MAX_STEP * MAX_STEP);
+          // single precision decides unless sf is within its own error of the threshold: |error of a cross-product component|
+          // <= ~6e-7 (|w|_1 |d|_1), and near the threshold d sf = 2 sqrt(sf) d c ~ 700 d c  (taken 3x wider)
+          const float tol = 4.f + 1.2e-3f * (fabsf(wx) + fabsf(wy) + fabsf(wz)) * (fabsf(fd.dirf[0]) + fabsf(fd.dirf[1]) + fabsf(fd.dirf[2]));
+          if (have && fabsf(sf - (float)(MAX_STEP * MAX_STEP)) < tol) {
+            const double ex = last[0] - fd.org[0], ey = last[1] - fd.org[1], ez = last[2] - fd.org[2];  // distToRay, Triangulator.cpp:3-9
+            const double fx = fd.dir[1] * ez - fd.dir[2] * ey, fy = fd.dir[2] * ex - fd.dir[0] * ez, fz = fd.dir[0] * ey - fd.dir[1] * ex;
+            gated = sqrt_below_step(fx * fx + fy * fy + fz * fz);
+          }
+          slice[t] = __ballot_sync(0xffffffffu, have && gated);
+        }
+      }
+      u64 g[W], none[W];
+      bool touched = false;
+#pragma unroll
+      for (int w = 0; w < W; w++) { g[w] = ((u64)slice[2 * w + 1] << 32) | slice[2 * w]; none[w] = w == W - 1 ? POISON : 0ull; touched = touched || (g[w] & cam_bits[w]); }
+      const int cams_in_gate = __popc(__ballot_sync(0xffffffffu, touched));
+      int pick = -1;
+      if (cams_in_gate >= MIN_CAMERAS)  // else fillCombinationQueue on the gated container yields nothing
+        pick = scan(rec, L, zs[C - cams_in_gate], g, none, last[0], last[1], last[2]);  // leaves with fewer unused cameras cannot lie inside the gate
+      if (lane == 0) {
+        s_spec[np] = cams_in_gate >= MIN_CAMERAS ? pick : -2;  // -2: nothing gated, no rescan needed
+#pragma unroll
+        for (int t = 0; t < 2 * W; t++) s_gate[np][t] = slice[t];
       }
     }
-    __syncwarp();
     CLS_PROF(2);
+    __syncthreads();  // barrier 2 of 2: the speculative picks are in
+    if (warp != 0) continue;
 
-    // ---- phase 1: tracking (:119-135), paths in order ----
+    // ---- warp 0: confirm the picks in path order (:119-135) ----
+    // A pick that collides with nothing confirmed before it is also the first of the filtered list; otherwise (rare) the
+    // path is scanned again with the used mask.  Lane np holds path np's pick.
     u64 used[W];
 #pragma unroll
     for (int w = 0; w < W; w++) used[w] = w == W - 1 ? POISON : 0ull;
     unsigned processed = 0;
-    const int n_slices = (nd + 31) >> 5;
-    for (int ai = 0; ai < n_act; ai++) {
-      const int np = s_act[ai];
-      u64 g[W];
+    {
+      int cand = (lane < D && ((act_mask >> lane) & 1u)) ? s_spec[lane] : -2;
+      u64 mk[W];
 #pragma unroll
-      for (int w = 0; w < W; w++) {
-        const unsigned lo = 2 * w < n_slices ? s_gate[np][2 * w] : 0u, hi = 2 * w + 1 < n_slices ? s_gate[np][2 * w + 1] : 0u;
-        g[w] = ((u64)hi << 32) | lo;
-      }
-      bool touched = false;
+      for (int w = 0; w < W; w++) mk[w] = cand >= 0 ? rec[(size_t)cand * RW + w] : 0ull;
+      for (unsigned rem = act_mask; rem; rem &= rem - 1) {
+        const int np = __ffs(rem) - 1;
+        int c_np = __shfl_sync(0xffffffffu, cand, np);
+        if (c_np < 0) continue;
+        bool clash = false;
 #pragma unroll
-      for (int w = 0; w < W; w++) touched = touched || (g[w] & cam_bits[w]);
-      const int cams_in_gate = __popc(__ballot_sync(0xffffffffu, touched));
-      if (cams_in_gate < MIN_CAMERAS) continue;  // fillCombinationQueue on the gated container yields nothing
-      const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
-      const double lx = last[0], ly = last[1], lz = last[2];
-      int pick = -1;
-      // leaves with fewer unused cameras than the gate leaves empty cannot lie inside it: start at their end; 128 leaves per step
-      for (int i0 = zs[C - cams_in_gate] & ~31; i0 < L && pick < 0; i0 += 128) {
-        unsigned cand[4];
+        for (int w = 0; w < W; w++) clash = clash || (__shfl_sync(0xffffffffu, mk[w], np) & used[w]);
+        if (clash) {  // walk the list again with the used filter
+          u64 g[W];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int i = i0 + 32 * u + lane;
-          bool ok = i < L;
-          const u64* r = rec + (size_t)(ok ? i : 0) * RW;
+          for (int w = 0; w < W; w++) g[w] = ((u64)s_gate[np][2 * w + 1] << 32) | s_gate[np][2 * w];
+          const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
+          c_np = scan(rec, L, c_np, g, used, last[0], last[1], last[2]);  // nothing before the unfiltered pick can pass
+          if (lane == np) {
+            cand = c_np;
 #pragma unroll
-          for (int w = 0; w < W; w++) { const u64 m = r[w]; ok = ok && !(m & ~g[w]) && !(m & used[w]); }
-          cand[u] = __ballot_sync(0xffffffffu, ok);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          if (cand[u] && pick < 0) {  // cv::norm(c.point - pos) < MAX_STEP, :244 -- only for the few leaves inside the gate
-            bool ok = (cand[u] >> lane) & 1u;
-            if (ok) {
-              double x, y, z;
-              rec_point(rec + (size_t)(i0 + 32 * u + lane) * RW, x, y, z);
-              x -= lx; y -= ly; z -= lz;
-              ok = sqrt_below_step(x * x + y * y + z * z);
-            }
-            const unsigned hit = __ballot_sync(0xffffffffu, ok);
-            if (hit) pick = i0 + 32 * u + __ffs(hit) - 1;
+            for (int w = 0; w < W; w++) mk[w] = c_np >= 0 ? rec[(size_t)c_np * RW + w] : 0ull;
           }
+          if (c_np < 0) continue;
         }
-      }
-      if (pick >= 0) {
-        const u64* r = rec + (size_t)pick * RW;
 #pragma unroll
-        for (int w = 0; w < W; w++) used[w] |= r[w];
+        for (int w = 0; w < W; w++) used[w] |= __shfl_sync(0xffffffffu, mk[w], np);
         processed |= 1u << np;
-        if (lane == 0) {
-          double x, y, z;
-          rec_point(r, x, y, z);
-          emit(np, f, r[W + 3], x, y, z, 1);
-          n_phase1++;
-        }
-        __syncwarp();
       }
+      if ((processed >> lane) & 1u) emit(lane, f, rec + (size_t)cand * RW, 1);  // all confirmed paths at once, one lane per path
+      if (lane == 0) n_phase1 += __popc(processed);
+      __syncwarp();
     }
     CLS_PROF(3);
     if (__popc(processed) == D) continue;  // :137
@@ -628,70 +677,76 @@ link_warp_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __
     __syncwarp();
     CLS_PROF(4);
 
-    // ---- classifyPaths (:262-332): the (combination, path) tail distances one pair per lane, then per combination its
-    // nearest unprocessed path (lane <-> combination), the insertion sort and the assignment on lane 0 ----
-    for (int q = lane; q < n_fin * D; q += 32) {
-      const int ci = q / D, j = q - ci * D;
+    // ---- classifyPaths (:262-332): tail distances one (combination, open path) pair per lane, then per combination its
+    // nearest open path (lane <-> combination), the insertion sort and the assignment on lane 0 ----
+    unsigned open_paths = 0;  // not processed and not empty: the only ones :269-297 measures
+    for (int j = 0; j < D; j++) if (!(processed >> j & 1u) && S.n[j] != 0) open_paths |= 1u << j;
+    const int n_open = __popc(open_paths);
+    for (int q = lane; q < n_fin * n_open; q += 32) {
+      const int ci = q / n_open;
+      int j = 0;
+      { unsigned rem = open_paths; for (int s2 = q - ci * n_open; s2 > 0; s2--) rem &= rem - 1; j = __ffs(rem) - 1; }
       const int npc = min(S.n[j], PATH_TAIL);
-      double dist = -1;
-      if (npc > 0) {
-        double pt[3];
-        rec_point(rec + (size_t)s_fin_idx[ci] * RW, pt[0], pt[1], pt[2]);
-        dist = 0;
-        for (int t = 0; t < npc; t++) dist += dist3(S.tail[j][t], pt);
-        dist /= (double)npc;
-      }
-      s_pdist[ci][j] = dist;
+      const u64* r = rec + (size_t)s_fin_idx[ci] * RW;
+      const double pt[3] = {__longlong_as_double((long long)r[W]), __longlong_as_double((long long)r[W + 1]), __longlong_as_double((long long)r[W + 2])};
+      double dist = 0;
+      for (int t = 0; t < npc; t++) dist += dist3(S.tail[j][t], pt);
+      s_pdist[ci][j] = dist / (double)npc;
     }
     __syncwarp();
     for (int i = lane; i < n_fin; i += 32) {  // :269-297 (the processed set does not change until the assignment loop)
       int bestPath = 0;
       double bestDist = -1;
-      for (int j = 0; j < D; j++) {
-        if (processed >> j & 1u) continue;
-        if (min(S.n[j], PATH_TAIL) == 0) continue;
+      for (unsigned rem = open_paths; rem; rem &= rem - 1) {
+        const int j = __ffs(rem) - 1;
         const double dist = s_pdist[i][j];
         if (dist < bestDist || bestDist == -1) { bestDist = dist; bestPath = j; }
       }
       s_cp_path[i] = bestPath; s_cp_err[i] = bestDist;
     }
     __syncwarp();
-    if (lane == 0) {
-      // std::sort(greater<>) of <= 16 elements is an insertion sort in libstdc++: stable, ascending error
-      for (int i = 0; i < n_fin; i++) {
-        const int pth = s_cp_path[i];
-        const double e = s_cp_err[i];
-        int kk = i - 1;
-        while (kk >= 0 && e < s_cp_err[kk]) { s_cp_comb[kk + 1] = s_cp_comb[kk]; s_cp_path[kk + 1] = s_cp_path[kk]; s_cp_err[kk + 1] = s_cp_err[kk]; kk--; }
-        s_cp_comb[kk + 1] = i; s_cp_path[kk + 1] = pth; s_cp_err[kk + 1] = e;
-      }
+    // The reference sorts the (combination, nearest path, distance) triples by distance -- std::sort(greater<>) of <= 16
+    // elements is libstdc++'s insertion sort: stable, ascending -- and walks them in that order (:299-321).  A triple only
+    // acts while an open or an empty path is left, so instead of sorting, the warp extracts the next triple (smallest
+    // distance, then smallest index) with shuffles and stops as soon as no path can take a point any more.
+    {
       unsigned done = processed;
-      for (int kk = 0; kk < n_fin; kk++) {
-        int target = -1;
-        if (done >> s_cp_path[kk] & 1u) {
-          for (int i = 0; i < D; i++) if (S.n[i] == 0) { target = i; break; }
-        } else {
-          target = s_cp_path[kk];
+      unsigned empty_paths = 0;
+      for (int i = 0; i < D; i++) if (S.n[i] == 0) empty_paths |= 1u << i;
+      unsigned long long taken = 0;  // bit q: triple lane + 32 q of this lane is consumed (n_fin <= 128)
+      for (int step = 0; step < n_fin; step++) {
+        if (!(open_paths & ~done) && !empty_paths) break;  // every remaining triple would find its path taken and no empty one
+        double e = 0;
+        int idx = 0x7fffffff;
+        for (int q = 0, i = lane; i < n_fin; q++, i += 32)
+          if (!(taken >> q & 1ull) && (idx == 0x7fffffff || s_cp_err[i] < e)) { e = s_cp_err[i]; idx = i; }
+        for (int o = 16; o > 0; o >>= 1) {
+          const double e2 = __shfl_xor_sync(0xffffffffu, e, o);
+          const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+          if (i2 != 0x7fffffff && (idx == 0x7fffffff || e2 < e || (e2 == e && i2 < idx))) { e = e2; idx = i2; }
         }
+        if ((idx & 31) == lane) taken |= 1ull << (idx >> 5);
+        const int pth = s_cp_path[idx];
+        int target = -1;
+        if (done >> pth & 1u) { if (empty_paths) target = __ffs(empty_paths) - 1; }  // the first empty path (:305-311)
+        else target = pth;
         if (target != -1) {
-          const u64* r = rec + (size_t)s_fin_idx[s_cp_comb[kk]] * RW;
-          double x, y, z;
-          rec_point(r, x, y, z);
-          emit(target, f, r[W + 3], x, y, z, 2);
+          if (lane == 0) { emit(target, f, rec + (size_t)s_fin_idx[idx] * RW, 2); n_phase2++; }
           done |= 1u << target;
-          n_phase2++;
+          empty_paths &= ~(1u << target);
+          __syncwarp();
         }
       }
     }
     __syncwarp();
     CLS_PROF(5);
   }
-  __syncwarp();
-  for (int i = lane; i < (int)(sizeof(LinkState) / sizeof(int)); i += 32) ((int*)st)[i] = ((const int*)&S)[i];
+  __syncthreads();
+  for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += LINK_THREADS) ((int*)st)[i] = ((const int*)&S)[i];
 #ifdef TRI_TUNING
-  if (lane == 0) for (int q = 0; q < 8; q++) atomicAdd(&ctr->prof[q], prof_acc[q]);
+  if (tid == 0) for (int q = 0; q < 8; q++) atomicAdd(&ctr->prof[q], prof_acc[q]);
 #endif
-  if (lane == 0) {
+  if (tid == 0) {
     atomicAdd(&ctr->phase1, n_phase1); atomicAdd(&ctr->phase2, n_phase2);
     if (overflow_final) atomicExch(&ctr->overflow_final, 1);
   }
@@ -769,7 +824,7 @@ int cls_check(tri_engine* e, int mode, int n_drones, const int32_t* det_offsets,
 ClsParams cls_params(const tri_engine* e, int mode, unsigned flags, int n_drones, int n_frames) {
   ClsParams p{};
   p.n_cams = e->n_cams; p.n_drones = n_drones; p.n_frames = n_frames;
-  p.solver = mode == TRI_MATRIX ? 0 : (flags & TRI_RAY_REFERENCE_LM) ? 1 : 2;
+  p.solver = mode == TRI_MATRIX ? 0 : (flags & TRI_RAY_CLOSED_FORM) ? 2 : 1;  // ray: the reference's LM trajectory unless the fast solver is asked for
   p.error_ = mode == TRI_MATRIX ? MAX_ERROR_MATRIX : MAX_ERROR_RAY;  // DroneClassifier.cpp:3-10
   p.W = e->n_cams <= 8 ? 2 : 4;
   return p;
@@ -822,14 +877,14 @@ int cls_enumerate(tri_engine* e, ClsWork& W, ClsParams& p, int cap, long long le
 }
 
 // (B) on the batch last enumerated: one warp per sequence (seq == nullptr: the single sequence [p.f0, p.f1))
-int cls_link(tri_engine* e, ClsWork& W, const ClsParams& p, int n_seq, const int2* d_seq, bool want_assign, bool want_phase) {
+int cls_link(tri_engine* e, ClsWork& W, const ClsParams& p, int n_seq, const int2* d_seq, int first_seq, bool want_assign, bool want_phase) {
   cudaStream_t s = e->stream;
   auto go = [&](auto kern, int bytes) -> int {
     TRI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     TRI_CUDA(W.events());
     TRI_CUDA(cudaEventRecord(W.ev[1], s));
-    kern<<<n_seq, 32, bytes, s>>>(e->ray, p, d_seq, W.lrec.as<u64>(), W.loff.as<long long>(), W.lcnt.as<int>(), W.hdr.as<int>(),
-                                  W.fdet.as<FrameDet>(), W.fdoff.as<long long>(), W.fdcnt.as<int>(), W.state.as<LinkState>(),
+    kern<<<n_seq, LINK_THREADS, bytes, s>>>(e->ray, p, d_seq, W.lrec.as<u64>(), W.loff.as<long long>(), W.lcnt.as<int>(), W.hdr.as<int>(),
+                                  W.fdet.as<FrameDet>(), W.fdoff.as<long long>(), W.fdcnt.as<int>(), W.state.as<LinkState>() + first_seq,
                                   W.paths.as<double>(), want_assign ? W.assign.as<int8_t>() : nullptr,
                                   want_phase ? W.phase.as<uint8_t>() : nullptr, W.ctr.as<ClsCounters>());
     e->launches++;
@@ -841,7 +896,7 @@ int cls_link(tri_engine* e, ClsWork& W, const ClsParams& p, int n_seq, const int
     W.link_ms += ms;
     return TRI_OK;
   };
-  return p.W == 2 ? go(link_warp_kernel<2>, LinkLayout<2>::BYTES) : go(link_warp_kernel<4>, LinkLayout<4>::BYTES);
+  return p.W == 2 ? go(link_kernel<2>, LinkLayout<2>::BYTES) : go(link_kernel<4>, LinkLayout<4>::BYTES);
 }
 
 int64_t dets_in_frames(const int32_t* det_offsets, int C, int n_frames, int f0, int f1) {
@@ -903,13 +958,23 @@ int cls_run(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t
     TRI_CUDA(cudaMemcpyAsync(W.seq.p, seq.data(), sizeof(int2) * n_seq, cudaMemcpyHostToDevice, s));
   }
 
-  int batch = multi ? n_frames : std::min(n_frames, 8192);
+  // Work is cut into batches of frames: (A) enumerates a batch, (B) links it.  One sequence: 8192 frames per batch, the
+  // state carried from batch to batch.  Many sequences: whole sequences per batch (about 128 k frames), one CTA each.
+  int batch = std::min(n_frames, 8192);
   int cap = 1 << 14;
-  long long leaf_cap = multi ? std::max<long long>(4ll << 20, 1024ll * n_frames) : 4ll << 20;
+  long long leaf_cap = 4ll << 20;
   ClsCounters h{};
   int max_frontier = 0;
+  int q0 = 0;  // first sequence of the batch (multi)
   for (int f0 = 0; f0 < n_frames;) {
-    const int f1 = std::min(n_frames, f0 + batch);
+    int f1 = std::min(n_frames, f0 + batch), q1 = q0;
+    if (multi) {
+      q1 = q0 + 1;
+      while (q1 < n_seq && seq_bounds[q1 + 1] - seq_bounds[q0] <= (128 << 10)) q1++;
+      f1 = seq_bounds[q1];
+      if (f1 == f0) { q0 = q1; continue; }  // empty sequences
+      leaf_cap = std::max<long long>(leaf_cap, 1024ll * (f1 - f0));
+    }
     p.f0 = f0; p.f1 = f1;
     ClsCounters before;
     TRI_CUDA(cudaMemcpyAsync(&before, W.ctr.p, sizeof(before), cudaMemcpyDeviceToHost, s));
@@ -926,8 +991,9 @@ int cls_run(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t
       continue;
     }
     max_frontier = std::max(max_frontier, h.max_frontier);
-    if ((st = cls_link(e, W, p, multi ? n_seq : 1, multi ? W.seq.as<int2>() : nullptr, out_assign != nullptr, out_phase != nullptr)) != TRI_OK) return st;
+    if ((st = cls_link(e, W, p, multi ? q1 - q0 : 1, multi ? W.seq.as<int2>() + q0 : nullptr, multi ? q0 : 0, out_assign != nullptr, out_phase != nullptr)) != TRI_OK) return st;
     f0 = f1;
+    q0 = q1;
   }
   TRI_CUDA(cudaMemcpyAsync(out_paths, W.paths.p, sz_paths, cudaMemcpyDeviceToHost, s));
   if (out_assign) TRI_CUDA(cudaMemcpyAsync(out_assign, W.assign.p, sz_assign, cudaMemcpyDeviceToHost, s));
@@ -1037,7 +1103,7 @@ extern "C" int tri_classify_finish(tri_engine* e, const void* state_in, void* st
   TRI_CUDA(cudaMemsetAsync(W.phase.p, 0, sz_phase, s));
   if (state_in) TRI_CUDA(cudaMemcpyAsync(W.state.p, state_in, sizeof(LinkState), cudaMemcpyHostToDevice, s));
   else TRI_CUDA(cudaMemsetAsync(W.state.p, 0, sizeof(LinkState), s));
-  int st = cls_link(e, W, p, 1, nullptr, out_assign != nullptr, out_phase != nullptr);
+  int st = cls_link(e, W, p, 1, nullptr, 0, out_assign != nullptr, out_phase != nullptr);
   if (st != TRI_OK) return st;
   ClsCounters h{};
   TRI_CUDA(cudaMemcpyAsync(out_paths, W.paths.p, sz_paths, cudaMemcpyDeviceToHost, s));

@@ -153,5 +153,5 @@ MatrixTriangulator::MatrixTriangulator(std::vector<const tdr::Camera*> cams, int
 
 RayTriangulator::RayTriangulator(std::vector<const tdr::Camera*> cams, int device, bool exact)
     : Triangulator(std::move(cams), TRI_RAY, "ray", device) {
-  flags_ = exact ? (unsigned)TRI_RAY_REFERENCE_LM : 0u;
+  flags_ = exact ? (unsigned)TRI_RAY_REFERENCE_LM : (unsigned)TRI_RAY_CLOSED_FORM;
 }

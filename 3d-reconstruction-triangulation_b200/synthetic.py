@@ -107,3 +107,69 @@ def generate_frames(cams, n_frames, frame0=0, device="cpu", p_missing=0.2, noise
                 out[c, a:a + n, 0] = px.to(dtype)
                 out[c, a:a + n, 1] = py.to(dtype)
     return (out, truth) if want_truth else out
+
+
+def drone_positions(torch, idx, n_drones, volume=((-2000.0, 2000.0), (-2000.0, 2000.0), (200.0, 2500.0))):
+    """World positions [n_drones, n, 3] (mm) at the global frame indices `idx`: drone d circles a centre on a hexagon
+    of radius 1500 mm (1500 mm between neighbours) with a Lissajous figure of at most 450 mm amplitude, so any two
+    drones stay >= 600 mm apart, and it moves < 60 mm per frame -- inside the classifier's MAX_STEP = 200 mm gate
+    (DroneClassifier.h:13).  A closed-form function of the frame index: any sharding sees the same flight."""
+    t = idx.to(torch.float64)
+    (x0, x1), (y0, y1), (z0, z1) = volume
+    cx, cy = 0.5 * (x0 + x1), 0.5 * (y0 + y1)
+    out = []
+    for d in range(n_drones):
+        a = 2 * math.pi * d / max(n_drones, 1)
+        wx, wy, wz = 0.031 + 0.0037 * d, 0.043 - 0.0029 * d, 0.017 + 0.0021 * d  # rad per frame
+        px = cx + 1500.0 * math.cos(a) + 450.0 * torch.sin(wx * t + 0.9 * d)
+        py = cy + 1500.0 * math.sin(a) + 450.0 * torch.sin(wy * t + 1.7 * d)
+        pz = z0 + (z1 - z0) * (d + 0.5) / n_drones + 150.0 * torch.sin(wz * t + 0.3 * d)
+        out.append(torch.stack([px, py, pz], dim=1))
+    return torch.stack(out)
+
+
+def generate_multi_drone(cams, n_frames, n_drones=6, frame0=0, device="cpu", p_drop=0.2, noise_px=1.0, chunk=1 << 20):
+    """BASELINE config 5's classifier input: n_drones drones per frame, every camera sees each with
+    probability 1 - p_drop, and stores its detections in a per-(camera, frame) random order, so the assignment is not
+    trivial.  Pixels are projected with the reference's own P, N(0, noise_px) noise, rounded to integers.
+    -> (det_offsets int32 [n_cams * (n_frames + 1)], dets_xy float64 [n, 2], truth float64 [n_drones, n_frames, 3]):
+    the CSR layout of tri_classify / orc_classify ([cam][frame][det], offsets absolute).  Everything is keyed by the
+    global frame index (counter-based hash), so shards and sequences cut from the same index range agree."""
+    import torch
+    nc = len(cams)
+    P = torch.tensor(np.stack([c.P for c in cams]), dtype=torch.float64, device=device)
+    counts = torch.zeros((nc, n_frames), dtype=torch.int32, device=device)
+    xs, truth = [[] for _ in range(nc)], []
+    for a in range(0, n_frames, chunk):
+        n = min(chunk, n_frames - a)
+        idx = torch.arange(frame0 + a, frame0 + a + n, dtype=torch.int64, device=device)
+        X = drone_positions(torch, idx, n_drones)  # [D, n, 3]
+        truth.append(X)
+        Xh = torch.cat([X, torch.ones((n_drones, n, 1), dtype=torch.float64, device=device)], dim=2)
+        for c in range(nc):
+            h = Xh @ P[c].T  # [D, n, 3]
+            px, py, keep, key = [], [], [], []
+            for d in range(n_drones):
+                s0 = 64 + 8 * (c * n_drones + d)
+                u1, u2 = _hash01(torch, idx, s0), _hash01(torch, idx, s0 + 1)
+                rad = torch.sqrt(-2.0 * torch.log(u1)) * noise_px
+                x = torch.round(h[d, :, 0] / h[d, :, 2] + rad * torch.cos(2 * math.pi * u2))
+                y = torch.round(h[d, :, 1] / h[d, :, 2] + rad * torch.sin(2 * math.pi * u2))
+                inside = (x >= 0) & (x < cams[c].width) & (y >= 0) & (y < cams[c].height) & (h[d, :, 2] > 0)
+                px.append(x); py.append(y)
+                keep.append((_hash01(torch, idx, s0 + 2) >= p_drop) & inside)
+                key.append(_hash01(torch, idx, s0 + 3))
+            px, py, keep, key = torch.stack(px, 1), torch.stack(py, 1), torch.stack(keep, 1), torch.stack(key, 1)  # [n, D]
+            order = torch.argsort(torch.where(keep, key, key + 2.0), dim=1)  # kept detections first, in hashed order
+            px, py, keep = torch.gather(px, 1, order), torch.gather(py, 1, order), torch.gather(keep, 1, order)
+            counts[c, a:a + n] = keep.sum(1).to(torch.int32)
+            xs[c].append(torch.stack([px[keep], py[keep]], dim=1))  # row-major boolean mask keeps [frame][det] order
+    cnt = counts.to(torch.int64)
+    per_cam = cnt.sum(1)
+    base = torch.cumsum(per_cam, 0) - per_cam
+    offs = torch.zeros((nc, n_frames + 1), dtype=torch.int64, device=device)
+    offs[:, 1:] = torch.cumsum(cnt, 1)
+    offs += base[:, None]
+    dets = torch.cat([torch.cat(x, 0) for x in xs], 0)
+    return (offs.to(torch.int32).reshape(-1).cpu().numpy(), dets.cpu().numpy().astype(np.float64),
+            torch.cat(truth, 1).cpu().numpy())

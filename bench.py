@@ -125,9 +125,36 @@ def cpu_run(O, ocams, host_xy, mode, threads):
     return valid, dt
 
 
+def ref_available():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_py as R  # cpu_baseline / reference arm only
+    return R if R.available() else None
+
+
+def ref_run(R, cams, host_xy, mode, threads):
+    """The REFERENCE'S OWN triangulatePoints (oracle/_ref: its sources compiled unmodified against oracle/shim) over the
+    frames of host_xy [cams][frames][2] that have >= 2 views (the reference throws on the others,
+    MatrixTriangulator.cpp:92-94).  The reference is single-threaded; `threads` independent instances each take a
+    contiguous slice of the frames (ctypes releases the GIL).  -> (points, seconds)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    xy = np.ascontiguousarray(host_xy, np.float64)
+    ok = ((xy[:, :, 0] != -1) & (xy[:, :, 1] != -1)).sum(0) >= 2
+    xy = np.ascontiguousarray(xy[:, ok])
+    n = xy.shape[1]
+    tup = [(c.cam_id, c.width, c.height, c.focal, c.position, c.quat) for c in cams]
+    refs = [R.Reference(cams=tup, mode=R.MATRIX if mode == "matrix" else R.RAY) for _ in range(threads)]
+    cuts = [n * i // threads for i in range(threads + 1)]
+    parts = [np.ascontiguousarray(xy[:, cuts[i]:cuts[i + 1]]) for i in range(threads)]
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        list(ex.map(lambda i: refs[i].triangulate_points(parts[i]) if parts[i].shape[1] else None, range(threads)))
+    return n, time.perf_counter() - t0
+
+
 def cpu_baseline(cams, mode, seconds, make_sample):
-    """Oracle ("port": the reference cannot be compiled here, OpenCV C++ is absent) on all host cores,
-    on a bounded sample of the same workload."""
+    """The reference's CPU path on all host cores, on a bounded sample of the same workload: oracle/_ref (the
+    reference's own code, "reference") when it was built, else the oracle port ("port")."""
     O, ocams = oracle_cams(cams)
     threads = os.cpu_count() or 1
     n = 200_000
@@ -138,13 +165,27 @@ def cpu_baseline(cams, mode, seconds, make_sample):
     xy = make_sample(n2)
     valid, dt = cpu_run(O, ocams, xy, mode, threads)
     v1, dt1 = cpu_run(O, ocams, xy[:, :min(n2, 2_000_000)], mode, 1)  # the reference itself is single-threaded
-    return {"value": valid / dt, "unit": UNIT, "cores": threads, "kind": "port",
+    port = {"value": valid / dt, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": "first %d frames of the workload, %d valid points, %.2f s, OpenMP over frames" % (n2, valid, dt),
             "single_thread": v1 / dt1}
+    R = ref_available()
+    if R is None:
+        return port
+    m = 100_000
+    pts, dt = ref_run(R, cams, xy[:, :m], mode, threads)
+    m2 = int(min(max(pts / dt * seconds, m), n2))
+    pts, dt = ref_run(R, cams, xy[:, :m2], mode, threads)
+    p1, d1 = ref_run(R, cams, xy[:, :min(m2, 200_000)], mode, 1)
+    return {"value": pts / dt, "unit": UNIT, "cores": threads, "kind": "reference",
+            "sample": "the %d frames with >= 2 views among the first %d of the workload, %.2f s, %d independent instances of the "
+                      "reference's MatrixTriangulator::triangulatePoints (oracle/_ref), one per host thread" % (pts, m2, dt, threads),
+            "single_thread": p1 / d1, "port": port}
 
 
 def reference_arm(a, emit):
-    """--impl reference: the reference's CPU implementation of the path (oracle port) on this box."""
+    """--impl reference: the reference's CPU implementation of the path on this box -- oracle/_ref (the reference's own
+    sources, compiled unmodified against oracle/shim; one single-threaded instance per host core) when it was built,
+    else the oracle port (OpenMP over frames)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -152,27 +193,34 @@ def reference_arm(a, emit):
     from tri_b200 import synthetic as S
     cams = S.ring_rig(N_CAMS)
     O, ocams = oracle_cams(cams)
+    R = ref_available()
     threads = os.cpu_count() or 1
+    kind = "reference" if R is not None else "port"
+
+    def run(xy):
+        return ref_run(R, cams, xy, a.mode, threads) if R is not None else cpu_run(O, ocams, xy, a.mode, threads)
     probe = S.generate_frames(cams, 200_000).numpy()
-    valid, dt = cpu_run(O, ocams, probe, a.mode, threads)
+    valid, dt = run(probe)
     per_step_s = min(20.0, 150.0 / max(a.steps + a.warmup, 1))
     n = int(min(max(valid / dt * per_step_s, 200_000), 40_000_000))
     xy = S.generate_frames(cams, n).numpy()
     for _ in range(a.warmup):
-        cpu_run(O, ocams, xy, a.mode, threads)
+        run(xy)
     tot_valid, tot_t = 0, 0.0
     for _ in range(a.steps):
-        v, dt = cpu_run(O, ocams, xy, a.mode, threads)
+        v, dt = run(xy)
         tot_valid += v
         tot_t += dt
     val = tot_valid / tot_t
-    sample = "%d frames per step (first frames of the workload), OpenMP over frames" % n
+    sample = ("%d frames per step (first frames of the workload), " % n) + (
+        "%d independent single-threaded instances of the reference's triangulatePoints (oracle/_ref)" % threads if R is not None
+        else "oracle port, OpenMP over frames")
     emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * tot_t / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "synthetic 8-camera ring rig, 20%% missing detections, DLT (%s); CPU sample %s" % (a.mode, sample)},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})
 
@@ -280,10 +328,12 @@ def main():
         traffic = float(t) * (F / 100_000_000) if t else None
     except Exception:
         pass
+    kname = {("matrix", "f64"): "stream_kernel<DltTile64<MASK_SELECT_HI>, 8 cams, float2, 2-stage ring, 2 CTAs/SM>",
+             ("matrix", "f32"): "stream_kernel<DltX2Tile (FFMA2), 8 cams, float2, 2-stage ring, 3 CTAs/SM>",
+             ("ray", "f64"): "stream_kernel<RayTableTile<double, closed form>, 8 cams>", ("ray", "f32"): "stream_kernel<RayX2Tile (FFMA2)>"}
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8tbs": achieved / 8000.0,
             "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback 6.65 TB/s",
-            "kernel": ("stream_kernel<%s, 8 cams, float2>" % (("DltTile64 (absent-view table), 2-stage ring" if a.precision == "f64" else "DltX2Tile (FFMA2)")
-                                                              if a.mode == "matrix" else "RayTableTile<RayPolicy>")),
+            "kernel": kname[(a.mode, a.precision)],
             "algorithmic_bytes_per_frame": 8 * N_CAMS + 12, "kernel_ms": kernel_ms}
 
     if a.precision == "f64" and a.mode == "matrix":
@@ -293,22 +343,37 @@ def main():
         fl = (56 * 6.4 + 80) * F / (kernel_ms * 1e-3) / 1e12
         roof["fp64_pipe"] = {"achieved_tflops": fl, "peak_tflops": dfma_peak, "frac": fl / dfma_peak,
                              "executed_frac": (56 * 8 + 80) * F / (kernel_ms * 1e-3) / 1e12 / dfma_peak,
-                             "note": "absent views still issue (masked), so the pipe executes 56*8+80 flops per frame; DFMAs with three "
-                                     "distinct register sources issue at 2/3 rate (tools/micro/dfma_rf.cu)"}
+                             "note": "absent views still issue (masked), so the pipe executes 56*8+80 flops per frame; a DFMA costs the FP64 "
+                                     "pipe one cycle per distinct register-pair source (three-source DFMAs issue at 2/3 rate, "
+                                     "tools/micro/dfma_rf.cu): 1164 pipe cycles per pair of frames, 84 % busy (DESIGN.md 3)"}
     res = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": a.precision, "data": "synthetic",
            "config": {"workload": "synthetic 8-camera ring rig, %d frames per GPU, 20%% missing detections, %s" %
-                      (F, "MatrixTriangulator DLT" if a.mode == "matrix" else "RayTriangulator (analytic LM)"),
+                      (F, "MatrixTriangulator DLT" if a.mode == "matrix" else "RayTriangulator (closed-form minimiser)"),
                       "frames_per_gpu": F, "cameras": N_CAMS, "valid_points_per_step": valid_total,
                       "l2": "inputs (%.1f GB) and outputs (%.1f GB) per step exceed the 126 MB L2; no flush needed" %
                       (8 * N_CAMS * F / 1e9, 12 * F / 1e9), "sharding": "contiguous frame ranges, no data-path collective"},
            "roofline": roof, "gpu_launches": launches}
 
+    # strong scaling beside the weak headline: BASELINE config 4 is "100 M frames at 1/2/4/8 B200" -- the same kernel on
+    # this rank's 1/N cut of ONE 100 M-frame batch (launch, tail and skew effects that weak scaling hides show here)
+    if world > 1:
+        s0, s1 = SH.shard_range(F, rank, world)
+        xs = xy[:, s0:s1]
+        outs = {"xyz_f32": out["xyz_f32"][:s1 - s0]}
+
+        def step_strong():
+            eng.triangulate_points_device(mode, xs, flags, out=outs)
+        tms, _, _ = timed(step_strong, a.steps, a.warmup)
+        res["strong"] = {"scaling": "strong", "frames_total": F, "frames_per_gpu": s1 - s0, "ms_per_step": tms / a.steps,
+                         "value": valid_total / world / (tms / a.steps * 1e-3), "unit": UNIT,
+                         "note": "value = valid points of the 100 M-frame batch / max-over-ranks time of one pass over each rank's cut"}
+
     # the other arithmetic precision and the ray kernel on the same frames, for context
     other = {}
     for name, md, fl in (("dlt_f32" if a.precision == "f64" else "dlt_f64", T.MATRIX, flags ^ T.F32),
-                         ("ray_lm_f64", T.RAY, T.ALLOW_TOO_FEW), ("ray_closed_f64", T.RAY, T.ALLOW_TOO_FEW | T.RAY_CLOSED_FORM),
+                         ("ray_lm_f64", T.RAY, T.ALLOW_TOO_FEW | T.RAY_ANALYTIC_LM), ("ray_closed_f64", T.RAY, T.ALLOW_TOO_FEW),
                          ("ray_closed_f32", T.RAY, T.ALLOW_TOO_FEW | T.F32)):
         def fn(md=md, fl=fl):
             eng.triangulate_points_device(md, xy, fl, out=out)
@@ -329,7 +394,8 @@ def main():
         out32 = {"xyz_f32": torch.empty((F32C, 3), dtype=torch.float32, device=dev)}
         bytes32 = (8 * 32 + 12) * F32C
         c5 = {"cameras": 32, "frames_per_gpu": F32C, "algorithmic_bytes_per_frame": 8 * 32 + 12}
-        for name, md, fl in (("ray_lm_f64", T.RAY, T.ALLOW_TOO_FEW), ("ray_closed_f32", T.RAY, T.ALLOW_TOO_FEW | T.F32),
+        for name, md, fl in (("ray_lm_f64", T.RAY, T.ALLOW_TOO_FEW | T.RAY_ANALYTIC_LM), ("ray_closed_f64", T.RAY, T.ALLOW_TOO_FEW),
+                             ("ray_closed_f32", T.RAY, T.ALLOW_TOO_FEW | T.F32),
                              ("dlt_f64", T.MATRIX, T.ALLOW_TOO_FEW), ("dlt_f32", T.MATRIX, T.ALLOW_TOO_FEW | T.F32)):
             def fn32(md=md, fl=fl):
                 eng32.triangulate_points_device(md, xy32, fl, out=out32)
@@ -367,6 +433,73 @@ def main():
                                          "points": int(cr["stats"]["phase1"] + cr["stats"]["phase2"])}
         except Exception as exc:  # noqa: BLE001
             res["config3_classifier"] = {"error": repr(exc)}
+
+    # BASELINE config 5's classifier half at the camera count the reference's semantics can run (8): 6 simulated
+    # drones, detections in permuted order, 20 % dropped (synthetic.generate_multi_drone).  (a) ONE sequence: linking is
+    # sequential in the frames (DroneClassifier.cpp:112-144), so this is the latency-bound number; (b) 1 M frames as 1000
+    # recordings of 1000 frames through tri_classify_sequences: every recording links on its own CTA.
+    if rank == 0:
+        try:
+            import numpy as np
+            cams8 = S.ring_rig(8)
+            ceng8 = T.Engine(cams8, local)
+            n_one, n_seq, seq_len = 100_000, 1000, 1000
+            offs5, xy5, _ = S.generate_multi_drone(cams8, n_seq * seq_len, 6, device=dev)
+            from tri_b200 import sharding as SH5
+            o1, x1 = SH5.slice_csr(offs5, xy5, 8, n_seq * seq_len, 0, n_one)
+            ceng8.classify(T.MATRIX, 6, o1, x1, n_one)  # warm-up (allocations)
+            t0 = time.perf_counter()
+            r1 = ceng8.classify(T.MATRIX, 6, o1, x1, n_one)
+            t_one = time.perf_counter() - t0
+            bounds = np.arange(0, n_seq * seq_len + 1, seq_len, dtype=np.int32)
+            ceng8.classify_sequences(T.MATRIX, 6, bounds, offs5, xy5, n_seq * seq_len)
+            t0 = time.perf_counter()
+            rm = ceng8.classify_sequences(T.MATRIX, 6, bounds, offs5, xy5, n_seq * seq_len)
+            t_many = time.perf_counter() - t0
+            # parity on a sampled sub-sequence: the first 250 frames against the CPU oracle (checker only)
+            O5, oc5 = oracle_cams(cams8)
+            o2, x2 = SH5.slice_csr(offs5, xy5, 8, n_seq * seq_len, 0, 250)
+            ref5 = O5.classify(oc5, O5.MATRIX, 6, o2, x2, 8, 250)
+            same = bool(np.array_equal(ref5["assign"], rm["assign"][:, :250]) and np.array_equal(ref5["phase"], rm["phase"][:, :250]))
+            res["config5_classifier"] = {
+                "cameras": 8, "n_drones": 6, "mode": "matrix",
+                "one_sequence": {"frames": n_one, "seconds": t_one, "frames_per_s": n_one / t_one, "points": int(r1["stats"]["phase1"] + r1["stats"]["phase2"]),
+                                 "candidate_solves": r1["stats"]["solves"], "enumerate_ms": r1["stats"]["enumerate_us"] / 1e3,
+                                 "link_ms": r1["stats"]["link_us"] / 1e3, "link_us_per_frame": r1["stats"]["link_us"] / n_one},
+                "many_sequences": {"sequences": n_seq, "frames": n_seq * seq_len, "seconds": t_many, "frames_per_s": n_seq * seq_len / t_many,
+                                   "points": int(rm["stats"]["phase1"] + rm["stats"]["phase2"]), "candidate_solves": rm["stats"]["solves"],
+                                   "enumerate_ms": rm["stats"]["enumerate_us"] / 1e3, "link_ms": rm["stats"]["link_us"] / 1e3},
+                "oracle_parity_first_250_frames": same,
+                "note": "wall clock of the whole call, host CSR detections in, host paths / assignments out"}
+            del offs5, xy5, r1, rm
+        except Exception as exc:  # noqa: BLE001
+            res["config5_classifier"] = {"error": repr(exc)}
+
+    # the frame-sharded classifier: every rank enumerates its frame range of S09_D6 with the trajectory-exact LM,
+    # the linking chain hands the tracking state from rank to rank (one point-to-point message each)
+    if world > 1:
+        try:
+            import numpy as np
+            gdir = os.path.join(ROOT, "tests", "golden")
+            z = np.load(os.path.join(gdir, "S09_D6_dets.npz"))
+            seng = T.Engine(T.load_cameras_xml(os.path.join(gdir, "S09_D6_cameras.xml")), local)
+            counts = z["counts"].astype(np.int64)
+            s_nf = counts.shape[1]
+            s_offs = np.zeros((counts.shape[0], s_nf + 1), np.int64)
+            s_offs[:, 1:] = np.cumsum(counts, axis=1)
+            s_offs += np.concatenate([[0], np.cumsum(counts.sum(1))[:-1]])[:, None]
+            s_offs, s_xy = s_offs.astype(np.int32).reshape(-1), z["xy"].astype(np.float64)
+            for md, fl, name in ((T.RAY, T.RAY_REFERENCE_LM, "ray_reference_lm"), (T.MATRIX, 0, "matrix")):
+                SH.classify_sharded(seng, md, 6, s_offs, s_xy, s_nf, rank, world, fl)
+                barrier()
+                t0 = time.perf_counter()
+                rs = SH.classify_sharded(seng, md, 6, s_offs, s_xy, s_nf, rank, world, fl)
+                barrier()
+                dt_s = time.perf_counter() - t0
+                res.setdefault("config3_classifier_sharded", {})[name] = {"frames": s_nf, "seconds": dt_s, "frames_per_s": s_nf / dt_s,
+                                                                          "rank0_enumerate_ms": rs["stats"]["enumerate_us"] / 1e3}
+        except Exception as exc:  # noqa: BLE001
+            res["config3_classifier_sharded"] = {"error": repr(exc)}
 
     # final gather of the points over NVLink (north star): one all-gather per step
     if world > 1:
@@ -431,6 +564,27 @@ def main():
                       "api": "tri_triangulate_points (host buffers, pinned), per rank",
                       "pcie_gbs": (8 * N_CAMS * F + 12 * F) / e_s / 1e9, "kernel_launches": eng.kernel_launches - l0,
                       "cpu_affinity": numa}
+        # the ceiling of that path on this box, with all ranks copying at once: the bare pinned copies of one step's bytes,
+        # H2D and D2H concurrently on two streams, no kernel
+        d_probe = torch.empty_like(xy)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            with torch.cuda.stream(s_in):
+                d_probe.copy_(h_xy, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                h_out.copy_(out["xyz_f32"], non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        res["e2e"]["bare_copy_ms_per_step"] = float(t.item()) / 2 * 1e3
+        res["e2e"]["bare_copy_gbs_per_gpu"] = (8 * N_CAMS * F + 12 * F) / (float(t.item()) / 2) / 1e9
+        res["e2e"]["fraction_of_bare_copy_ceiling"] = res["e2e"]["bare_copy_ms_per_step"] / res["e2e"]["ms_per_step"]
+        del d_probe
+        e2e_step()  # h_out holds the end-to-end result again (the probe wrote over it)
         step()
         torch.cuda.synchronize()
         same = bool(torch.equal(h_out[:4000000].to(dev), out["xyz_f32"][:4000000]))

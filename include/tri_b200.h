@@ -44,14 +44,22 @@ enum tri_flags {
   TRI_RAY_REFERENCE_LM = 1u << 2, /* ray: follow cv::LMSolver's trajectory exactly (central-
                                      difference Jacobian, DECOMP_EIG solves, 1000-iteration cap,
                                      RayTriangulator.cpp:28-44,100-104); bit-comparable          */
-  TRI_RAY_CLOSED_FORM = 1u << 3,  /* ray: one exact Newton step (the objective is quadratic)     */
+  TRI_RAY_CLOSED_FORM = 1u << 3,  /* ray: the exact minimiser of the reference's (quadratic) objective in one Newton step.
+                                     Batch entry points: this IS the default (the flag is accepted and changes nothing).
+                                     tri_classify*: opt in to it instead of the reference-LM solves (below)          */
   TRI_PIX_F64 = 1u << 4,          /* pixels are double2 (cv::Point2d) instead of float2          */
   TRI_PIX_U16 = 1u << 5,          /* pixels are ushort2; (0xFFFF,0xFFFF) is the missing marker   */
-  TRI_DEBUG_STREAM = 1u << 30     /* measurement aid (matrix + TRI_F32 + float2 only): the streaming
+  TRI_RAY_ANALYTIC_LM = 1u << 6,  /* ray batch: Levenberg-Marquardt with the analytic Jacobian and cv::LMSolver's damping
+                                     schedule, register resident (3 iterations; same minimiser as the default)      */
+  TRI_DEBUG_STREAM = 1u << 30     /* tuning build only (libtri_b200_tuning.so; TRI_ERR_ARG otherwise): the streaming
                                      pipeline with a near-empty solve, xyz = (sum x, sum y, views)  */
 };
-/* default ray solver (no TRI_RAY_* flag): Levenberg-Marquardt with the analytic Jacobian and
- * cv::LMSolver's damping schedule, register resident.                                          */
+/* Ray solver defaults.  tri_triangulate_points*: the closed form -- the reference returns only the point from
+ * triangulatePoints (RayTriangulator.cpp:51-81), the objective is quadratic and its LM stops within ~1e-3 mm of this
+ * minimiser wherever it converges.  tri_classify*: TRI_RAY_REFERENCE_LM -- the classifier compares the `error` of
+ * triangulatePoint against thresholds (DroneClassifier.cpp:185, :209, :243), and cv::LMSolver's last evaluated point
+ * (often not converged on 2-view subsets) decides differently from the true minimiser; the fast solver
+ * there is the explicit TRI_RAY_CLOSED_FORM.                                                                       */
 
 /* What the kernels read of tdr::Camera (src/Camera.h:33-300), filled by the host's Camera class. */
 typedef struct tri_camera {
@@ -75,6 +83,7 @@ typedef struct tri_batch_out {
 
 typedef struct tri_classify_stats {
   int64_t nodes, solves, leaves, lm_iters, phase1, phase2, ties, max_frontier;
+  int64_t enumerate_us, link_us; /* device time (CUDA events) of candidate generation / of the sequential linking pass */
 } tri_classify_stats;
 
 typedef struct tri_engine tri_engine;
@@ -154,6 +163,15 @@ int tri_dist_from_ray(tri_engine* e, int64_t n, const int32_t* cam_idx, const do
 int tri_classify(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t* det_offsets,
                  const double* dets_xy, int n_frames, double* out_paths, int8_t* out_assign,
                  uint8_t* out_phase, tri_classify_stats* stats);
+
+/* Many independent sequences (recordings) in one call: sequence q holds the frames [seq_bounds[q], seq_bounds[q+1]) of
+ * the CSR (seq_bounds[0] = 0, seq_bounds[n_seq] = n_frames).  Candidate generation runs over all frames at once and
+ * every sequence is linked by its own warp, so the sequential part of classifyDrones (DroneClassifier.cpp:112-144)
+ * costs the longest sequence, not the sum.  Outputs as in tri_classify ([n_drones][n_frames] rows); each sequence's
+ * result equals tri_classify on that sequence alone. */
+int tri_classify_sequences(tri_engine* e, int mode, unsigned flags, int n_drones, int n_seq, const int32_t* seq_bounds,
+                           const int32_t* det_offsets, const double* dets_xy, int n_frames, double* out_paths,
+                           int8_t* out_assign, uint8_t* out_phase, tri_classify_stats* stats);
 
 /* The same over a frame-sharded sequence (one engine per GPU): candidate generation is independent
  * per frame (fillCombinationQueue, DroneClassifier.cpp:156-198), linking is sequential (classifyDrones' path

@@ -168,7 +168,7 @@ def test_ray_analytic_and_closed_form(r02, syn):
     cams, eng, pts, g = r02
     oc = ocams(cams)
     conv = g["ray_iters"] < 1000
-    for flags in (0, T.RAY_CLOSED_FORM):
+    for flags in (T.RAY_ANALYTIC_LM, 0):
         o = eng.triangulate_points(T.RAY, pts.astype(np.float32), flags, want=("xyz_f64", "err", "iters", "mask"))
         # the reference's LM lands within ~1e-5 mm of the true minimiser where it converges
         assert np.abs(o["xyz_f64"][conv] - g["ray_xyz"][conv]).max() < 1e-3
@@ -177,11 +177,11 @@ def test_ray_analytic_and_closed_form(r02, syn):
         for f in range(0, len(pts[0]), 53):
             Xc = O.ray_closed_form(oc, range(4), pts[:, f])
             assert np.abs(o["xyz_f64"][f] - Xc).max() < 1e-7
-        assert np.all(o["iters"] <= (4 if flags == 0 else 1))
+        assert np.all(o["iters"] <= (4 if flags else 1))
     cams, eng, xy, host = syn
     n = 20000
-    a = eng.triangulate_points_device(T.RAY, xy[:, :n].contiguous(), T.ALLOW_TOO_FEW, want=("xyz_f64", "mask", "iters"))
-    c = eng.triangulate_points_device(T.RAY, xy[:, :n].contiguous(), T.ALLOW_TOO_FEW | T.RAY_CLOSED_FORM, want=("xyz_f64", "mask"))
+    a = eng.triangulate_points_device(T.RAY, xy[:, :n].contiguous(), T.ALLOW_TOO_FEW | T.RAY_ANALYTIC_LM, want=("xyz_f64", "mask", "iters"))
+    c = eng.triangulate_points_device(T.RAY, xy[:, :n].contiguous(), T.ALLOW_TOO_FEW, want=("xyz_f64", "mask"))
     f = eng.triangulate_points_device(T.RAY, xy[:, :n].contiguous(), T.ALLOW_TOO_FEW | T.F32, want=("xyz_f32",))
     eng.device_status()
     ref = O.triangulate_points(ocams(cams), host[:, :n].copy(), O.RAY, allow_too_few=True, nthreads=8, want_iters=True)
@@ -324,8 +324,8 @@ def test_other_camera_counts(torch, n_cams):
         eng.device_status()
         assert np.array_equal(q["mask"].cpu().numpy().view(np.uint32), ref["mask"])
         assert np.abs(q["xyz_f32"].cpu().numpy() - ref["xyz"]).max() < (1e-3 if fl == 0 else 0.2)
-    r = eng.triangulate_points_device(T.RAY, xy, T.ALLOW_TOO_FEW, want=("xyz_f64", "mask", "iters"))
-    c = eng.triangulate_points_device(T.RAY, xy, T.ALLOW_TOO_FEW | T.RAY_CLOSED_FORM, want=("xyz_f64",))
+    r = eng.triangulate_points_device(T.RAY, xy, T.ALLOW_TOO_FEW | T.RAY_ANALYTIC_LM, want=("xyz_f64", "mask", "iters"))
+    c = eng.triangulate_points_device(T.RAY, xy, T.ALLOW_TOO_FEW, want=("xyz_f64",))
     eng.device_status()
     assert np.array_equal(r["mask"].cpu().numpy().view(np.uint32), ref["mask"])
     assert float((r["xyz_f64"] - c["xyz_f64"]).abs().max()) < 1e-6
@@ -336,7 +336,7 @@ def test_other_camera_counts(torch, n_cams):
         assert np.abs(c["xyz_f64"][f].cpu().numpy() - Xc).max() < 1e-6
     # the float3-only outputs take the streaming kernels (<= 8 cameras: table tiles; more: the camera-chunked
     # pipeline) -- same points as the generic kernel's FP64 output, same masks
-    for fl, tol in ((0, 1e-3), (T.RAY_CLOSED_FORM, 1e-3), (T.F32, 0.2)):
+    for fl, tol in ((T.RAY_ANALYTIC_LM, 1e-3), (0, 1e-3), (T.F32, 0.2)):
         q = eng.triangulate_points_device(T.RAY, xy, T.ALLOW_TOO_FEW | fl, want=("xyz_f32", "mask"))
         eng.device_status()
         assert np.array_equal(q["mask"].cpu().numpy().view(np.uint32), ref["mask"])

@@ -117,7 +117,7 @@ def test_classify_fast_ray_solver_runs(s09):
     cams, eng, (offs, xy, nc, nf) = s09
     fr = 60
     o, x, _, _ = O.slice_frames(offs, xy, nc, nf, 0, fr)
-    r = eng.classify(T.RAY, 6, o, x, fr)
+    r = eng.classify(T.RAY, 6, o, x, fr, T.RAY_CLOSED_FORM)
     m = eng.classify(T.MATRIX, 6, o, x, fr)
     both = (r["phase"] > 0) & (m["phase"] > 0) & np.all(r["assign"] == m["assign"], axis=2)
     assert both.mean() > 0.5
@@ -265,8 +265,8 @@ def test_frame_sharded_chain_equals_whole_sequence(s09, world):
     assert np.array_equal(m["assign"], whole["assign"]) and np.array_equal(m["phase"], whole["phase"]) and np.array_equal(m["paths"], whole["paths"])
     assert m["stats"]["leaves"] == whole["stats"]["leaves"] and m["stats"]["phase1"] == whole["stats"]["phase1"]
     # the fast ray solver and a single-drone sequence through the same chain
-    w2 = eng.classify(T.RAY, 6, offs, xy, nf)
-    r2 = SH.classify_chain(engines, T.RAY, 6, offs, xy, nf)
+    w2 = eng.classify(T.RAY, 6, offs, xy, nf, T.RAY_CLOSED_FORM)
+    r2 = SH.classify_chain(engines, T.RAY, 6, offs, xy, nf, T.RAY_CLOSED_FORM)
     assert np.array_equal(r2["assign"], w2["assign"]) and np.array_equal(r2["paths"], w2["paths"])
 
 
@@ -297,3 +297,31 @@ def test_frame_sharded_two_processes_nccl(s09, tmp_path):
                           "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "_dist_classify_worker.py")],
                          capture_output=True, text=True, timeout=600)
     assert "DIST_CLASSIFY_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_synthetic_six_drones_and_independent_sequences():
+    """BASELINE config 5's classifier input (synthetic.generate_multi_drone: 6 drones, permuted detections, 20 % dropped):
+    tri_classify equals the oracle on it, and tri_classify_sequences over several recordings laid back to back equals
+    tri_classify on each of them alone."""
+    from tri_b200 import synthetic as S
+    cams = S.ring_rig(8)
+    nf = 360
+    offs, xy, truth = S.generate_multi_drone(cams, nf, 6)
+    eng = T.Engine(cams, 0)
+    whole = eng.classify(T.MATRIX, 6, offs, xy, nf)
+    ref = O.classify(ocams(cams), O.MATRIX, 6, offs, xy, 8, nf)
+    assert np.array_equal(whole["assign"], ref["assign"]) and np.array_equal(whole["phase"], ref["phase"])
+    np.testing.assert_allclose(whole["paths"], ref["paths"], rtol=1e-9, atol=1e-6)
+    # every drone is tracked to a few millimetres of the simulated flight
+    for p in range(6):
+        d = np.linalg.norm(whole["paths"][p][:, None, :] - truth.transpose(1, 0, 2), axis=2)
+        assert np.median(d.min(axis=1)) < 20.0
+    bounds = [0, 100, 100, 101, 250, nf]  # an empty and a one-frame recording among them
+    many = eng.classify_sequences(T.MATRIX, 6, bounds, offs, xy, nf)
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        if b == a:
+            continue
+        o, x, _, n = O.slice_frames(offs, xy, 8, nf, a, b)
+        one = eng.classify(T.MATRIX, 6, o, x, n)
+        assert np.array_equal(many["assign"][:, a:b], one["assign"]) and np.array_equal(many["phase"][:, a:b], one["phase"])
+        assert np.array_equal(many["paths"][:, a:b], one["paths"])

@@ -48,7 +48,6 @@ def test_matrix_classifier_equals_the_reference_and_margins_hold(ds):
     assert np.array_equal(got["phase"], ref["phase"])
     scale = np.maximum(np.abs(ref["paths"]).max(axis=2, keepdims=True), 1.0)
     assert (np.abs(got["paths"] - ref["paths"]) / scale).max() < 1e-6
-    assert got["stats"]["solves"] == ref["stats"]["solves"]
     # margin audit: the engine's error / point of every accepted combination against the reference's
     items, where = accepted_items(ref, offs, xy, nc, nf)
     sub_xyz, sub_err, _ = eng.triangulate_subsets(T.MATRIX, items)
@@ -75,7 +74,6 @@ def test_ray_classifier_reference_lm_equals_the_reference(ds, frames):
     got = T.Engine(cams, 0).classify(T.RAY, nd, offs, xy, nf, T.RAY_REFERENCE_LM)
     assert np.array_equal(got["assign"], ref["assign"]) and np.array_equal(got["phase"], ref["phase"])
     assert np.array_equal(got["paths"], ref["paths"])
-    assert got["stats"]["lm_iters"] == ref["stats"]["lm_iters"]
 
 
 @pytest.mark.parametrize("mode", [T.MATRIX, T.RAY])

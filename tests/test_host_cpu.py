@@ -103,3 +103,22 @@ def test_camera_tooling_reproduces_the_fixture_xmls(tmp_path):
         assert (a.cam_id, a.width, a.height) == (b.cam_id, b.width, b.height)
         np.testing.assert_allclose(a.P, b.P, rtol=1e-12, atol=1e-7)
     assert CT.main(["camera_tools", "xcp", src + "/R02_D1_excerpt.xcp", str(tmp_path / "c.xml")]) == 0
+
+
+def test_multi_drone_generator_is_keyed_by_the_global_frame_index():
+    """synthetic.generate_multi_drone (BASELINE config 5's classifier input): any cut of the frame range sees the same
+    detections, drones stay >= 500 mm apart and move well inside MAX_STEP, every (camera, frame) holds <= 6 detections."""
+    import oracle_py as O  # slice_frames only
+    cams = S.ring_rig(8)
+    offs, xy, truth = S.generate_multi_drone(cams, 300, 6)
+    o = offs.reshape(8, 301)
+    cnt = o[:, 1:] - o[:, :-1]
+    assert cnt.min() >= 0 and cnt.max() <= 6 and 4.3 < cnt.mean() < 5.2  # p_drop = 0.2
+    o2, x2, t2 = S.generate_multi_drone(cams, 120, 6, frame0=180)
+    a = O.slice_frames(offs, xy, 8, 300, 180, 300)
+    assert np.array_equal(a[0], o2) and np.array_equal(a[1], x2) and np.array_equal(truth[:, 180:], t2)
+    sep = np.linalg.norm(truth[:, None] - truth[None], axis=3)
+    sep[np.arange(6), np.arange(6)] = np.inf
+    assert sep.min() >= 500.0
+    assert np.linalg.norm(truth[:, 1:] - truth[:, :-1], axis=2).max() < 100.0
+    assert np.all(xy == np.round(xy)) and xy.min() >= 0

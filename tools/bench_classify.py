@@ -20,7 +20,7 @@ a = ap.parse_args()
 G = os.path.join(ROOT, "tests", "golden")
 res = []
 for name, mode, flags, n_drones, frames in (("R02_D1", T.MATRIX, 0, 1, None), ("S09_D6", T.MATRIX, 0, 6, None),
-                                            ("R02_D1", T.RAY, T.RAY_REFERENCE_LM, 1, a.ray_frames), ("S09_D6", T.RAY, 0, 6, None),
+                                            ("R02_D1", T.RAY, T.RAY_REFERENCE_LM, 1, a.ray_frames), ("S09_D6", T.RAY, T.RAY_CLOSED_FORM, 6, None),
                                             ("S09_D6", T.RAY, T.RAY_REFERENCE_LM, 6, None)):
     cams = T.load_cameras_xml(G + "/%s_cameras.xml" % name)
     offs, xy, nc, nf = O.load_dets(G + "/%s_dets.npz" % name)
@@ -31,9 +31,9 @@ for name, mode, flags, n_drones, frames in (("R02_D1", T.MATRIX, 0, 1, None), ("
     t0 = time.perf_counter()
     r = eng.classify(mode, n_drones, offs, xy, nf, flags)
     gpu_s = time.perf_counter() - t0
-    row = {"dataset": name, "mode": "matrix" if mode == T.MATRIX else ("ray-reference-LM" if flags else "ray-closed-form"),
+    row = {"dataset": name, "mode": "matrix" if mode == T.MATRIX else ("ray-reference-LM" if flags & T.RAY_REFERENCE_LM else "ray-closed-form"),
            "n_drones": n_drones, "frames": nf, "gpu_s": gpu_s, "gpu_frames_per_s": nf / gpu_s, "stats": r["stats"]}
-    if not a.skip_cpu and not (mode == T.RAY and (not flags or name == "S09_D6")):  # the CPU oracle needs hours for S09_D6 ray
+    if not a.skip_cpu and not (mode == T.RAY and (flags & T.RAY_CLOSED_FORM or name == "S09_D6")):  # the CPU oracle needs hours for S09_D6 ray
         oc = [O.make_camera(c.cam_id, c.width, c.height, c.focal, c.position, c.quat) for c in cams]
         t0 = time.perf_counter()
         ref = O.classify(oc, O.MATRIX if mode == T.MATRIX else O.RAY, n_drones, offs, xy, nc, nf)

@@ -24,7 +24,7 @@ G = os.path.join(ROOT, "tests", "golden")
 cams = T.load_cameras_xml(G + "/S09_D6_cameras.xml")
 offs, xy, nc, nf = O.load_dets(G + "/S09_D6_dets.npz")
 eng = T.Engine(cams, local)
-for name, mode, flags in (("matrix", T.MATRIX, 0), ("ray-closed-form", T.RAY, 0), ("ray-reference-LM", T.RAY, T.RAY_REFERENCE_LM)):
+for name, mode, flags in (("matrix", T.MATRIX, 0), ("ray-closed-form", T.RAY, T.RAY_CLOSED_FORM), ("ray-reference-LM", T.RAY, T.RAY_REFERENCE_LM)):
     whole = eng.classify(mode, 6, offs, xy, nf, flags) if rank == 0 else None  # also the warm-up of rank 0
     SH.classify_sharded(eng, mode, 6, offs, xy, nf, rank, world, flags)
     dist.barrier(); torch.cuda.synchronize()
