@@ -31,6 +31,7 @@ RAY_CLOSED_FORM = 1 << 3
 PIX_F64 = 1 << 4
 PIX_U16 = 1 << 5
 RAY_ANALYTIC_LM = 1 << 6
+CLS_LAZY = 1 << 7
 DEBUG_STREAM = 1 << 30
 MAX_CAMS = 32
 
@@ -178,8 +179,8 @@ class Camera:
         w, h = int(self.width), int(self.height)
         if w == 0 or h == 0:
             raise RuntimeError("Camera: image size is not set")  # Camera.h:79-80
-        self.cx = int(round(w / 2.0))  # Camera.h:81-82
-        self.cy = int(round(h / 2.0))
+        self.cx = int(math.floor(w / 2.0 + 0.5))  # Camera.h:81-82: C round(), half away from zero (Python's round() is half-to-even)
+        self.cy = int(math.floor(h / 2.0 + 0.5))
         fx = float(self.focal)
         if fx == 0:
             raise RuntimeError("Camera: focal length is not set")  # Camera.h:90

@@ -29,112 +29,9 @@
 #include <thread>
 #include <vector>
 
-#include "tri_engine.cuh"
-#include "tri_ref.cuh"
+#include "tri_classify.cuh"
 
 namespace tri {
-
-constexpr int CLS_MAX_CAMS = 16;   // 4 bits per camera in a 64-bit combination
-constexpr int CLS_THREADS = 128;
-constexpr int LINK_MAX_FINAL = 128;  // combinations pickBestCombinations can keep in one frame: <= 15 * C / 2 = 120 disjoint ones
-typedef unsigned long long u64;
-
-// DroneClassifier.h:11-17
-constexpr double MAX_ERROR_MATRIX = 1e+5, MAX_ERROR_RAY = 120, MAX_STEP = 200;
-constexpr int MIN_CAMERAS = 2, PATH_TAIL = 3;
-
-// ---- what (A) hands to (B), per frame, all of it independent of the tracking state ------------------------
-// The frame's detections are numbered camera-major (pref[c] + d); a detection MASK has one bit per such number.
-// A candidate ("leaf") record, stored in PRIORITY order (Combination::operator<, :12-20):
-//   mask[W]   the leaf's detections.  Two combinations collide (isCombinationUnique, :32-41) <=> their masks
-//             intersect; a combination is inside a path's ray gate <=> its mask is a subset of the gate mask.  The top
-//             bit of the last word is a poison bit: set on a leaf whose error is not < error_ (it can never be
-//             accepted, :209, :243) and in every "used" mask.
-//   xyz[3]    the triangulated point, comb = the 4-bit-per-camera combination word (for the assignment output)
-// W = 2 (<= 8 cameras, 48-byte records) or 4 (<= 16 cameras, 80-byte records: both strides are conflict-free for the
-// 16-byte shared-memory loads of a warp).
-__host__ __device__ constexpr int rec_words(int W) { return W == 2 ? 6 : 10; }
-constexpr int HDR_INTS = 40;   // per frame: [0 .. C+1] zstart[z] = leaves with fewer than z unused cameras; [20 .. 20+C] pref[c]
-constexpr int HDR_PREF = 20;
-struct __align__(16) FrameDet {  // a detection of the frame with its pixel ray (Triangulator.cpp:27-55); 80 B, a conflict-free stride
-  double dir[3], org[3];
-  float dirf[3], orgf[3];  // single-precision copies for the gate's fast path
-  int cam, slot;
-};
-constexpr int LINK_MAX_DETS = CLS_MAX_CAMS * TRI_MAX_DETS;  // 240
-
-struct ClsParams {
-  int n_cams, n_drones, solver;  // solver: 0 matrix, 1 ray reference LM, 2 ray closed form
-  int n_frames;                  // whole sequence (row length of the CSR offsets is n_frames + 1)
-  int f0, f1;                    // frame batch [f0, f1)
-  int cap;                       // frontier capacity per CTA
-  int W;                         // mask words per leaf
-  long long leaf_cap;            // leaf records
-  double error_;
-};
-
-struct ClsCounters {
-  u64 leaf_total, fdet_total, nodes, solves, leaves, lm_iters, phase1, phase2, ties;
-  int max_frontier, overflow_frontier, overflow_leaves, overflow_final, bad_input;
-  u64 prof[8];  // tuning builds: clock cycles of the linking pass by section (wait, gates, phase 1, phase 2, classifyPaths)
-};
-#ifdef TRI_TUNING
-#define CLS_PROF(k) do { const long long now__ = clock64(); prof_acc[k] += (u64)(now__ - prof_t); prof_t = now__; } while (0)
-#else
-#define CLS_PROF(k) do { } while (0)
-#endif
-
-struct LinkState {
-  double tail[TRI_MAX_DRONES][PATH_TAIL][3];  // oldest .. newest of the last min(n,3) points
-  int n[TRI_MAX_DRONES];                      // points pushed so far (saturating)
-};
-
-__device__ __forceinline__ u64 nonzero_nibbles(u64 v) { return (v | (v >> 1) | (v >> 2) | (v >> 3)) & 0x1111111111111111ull; }
-
-// isCombinationUnique (DroneClassifier.cpp:32-41): no camera where both use the same detection
-__device__ __forceinline__ bool conflicts(u64 a, u64 b) { return (nonzero_nibbles(a) & ~nonzero_nibbles(a ^ b)) != 0; }
-
-__device__ inline double solve_combination(const DltRig<double>& dlt, const RayRig& ray, int solver, u64 comb, int n_cams,
-                                           const double (*px)[TRI_MAX_DETS], const double (*py)[TRI_MAX_DETS], double X[3],
-                                           int& iters) {
-  iters = 0;
-  if (solver == 0) {
-    int cam[CLS_MAX_CAMS], n = 0;
-    double x[CLS_MAX_CAMS], y[CLS_MAX_CAMS];
-    for (int i = 0; i < n_cams; i++) {
-      const int k = (int)((comb >> (4 * i)) & 15);
-      if (k) { cam[n] = i; x[n] = px[i][k - 1]; y[n] = py[i][k - 1]; n++; }
-    }
-    return ref::dlt_point(dlt, n, cam, x, y, X);
-  }
-  ref::RaySet rs;
-  rs.n = 0;
-  for (int i = 0; i < n_cams; i++) {
-    const int k = (int)((comb >> (4 * i)) & 15);
-    if (k) { rs.cam[rs.n] = i; ref::make_dir(ray, i, px[i][k - 1], py[i][k - 1], rs.d[rs.n]); rs.n++; }
-  }
-  if (solver == 1) return ref::lm_point(ray, rs, X, iters);
-  // closed form about the mean origin (the minimiser the reference's LM converges to)
-  const int n = rs.n;
-  double m[3] = {0, 0, 0};
-  for (int k = 0; k < n; k++) for (int j = 0; j < 3; j++) m[j] += ray.pos[rs.cam[k]][j] / n;
-  double M[6] = {0, 0, 0, 0, 0, 0}, c[3] = {0, 0, 0};
-  for (int k = 0; k < n; k++) {
-    const double* d = rs.d[k];
-    const double dd = d[0] * d[0] + d[1] * d[1] + d[2] * d[2];
-    const double o[3] = {ray.pos[rs.cam[k]][0] - m[0], ray.pos[rs.cam[k]][1] - m[1], ray.pos[rs.cam[k]][2] - m[2]};
-    const double dot = d[0] * o[0] + d[1] * o[1] + d[2] * o[2];
-    M[0] += dd - d[0] * d[0]; M[1] -= d[0] * d[1]; M[2] -= d[0] * d[2];
-    M[3] += dd - d[1] * d[1]; M[4] -= d[1] * d[2]; M[5] += dd - d[2] * d[2];
-    for (int j = 0; j < 3; j++) c[j] += dd * o[j] - d[j] * dot;
-  }
-  solve_sym3<double>(M, c, X);
-  for (int j = 0; j < 3; j++) X[j] += m[j];
-  double S, rmax, e;
-  ref::residual_pass(ray, rs, X, S, rmax, e);
-  iters = 1;
-  return e;
-}
 
 // ---- (A) candidate generation ------------------------------------------------------------------
 __global__ void __launch_bounds__(CLS_THREADS)
@@ -796,14 +693,23 @@ using namespace tri;
     if (err__ != cudaSuccess) return cuda_fail(err__, #call);  \
   } while (0)
 
+namespace tri {
+cudaError_t launch_lazy_link(cudaStream_t s, const DltRig<double>& dlt, const RayRig& ray, const ClsParams& p, int n_seq, const int2* d_seq,
+                             const int32_t* d_offs, const double* d_dets, LinkState* d_state, double* d_paths, int8_t* d_assign,
+                             uint8_t* d_phase, ClsCounters* d_ctr);
+}
+
 namespace {
 
 // argument checks shared by the entry points; *n_det = detections in the CSR
-int cls_check(tri_engine* e, int mode, int n_drones, const int32_t* det_offsets, const double* dets_xy, int n_frames, int64_t* n_det) {
+int cls_check(tri_engine* e, int mode, int n_drones, const int32_t* det_offsets, const double* dets_xy, int n_frames, int64_t* n_det,
+              bool lazy = false) {
   if (!e) return fail(TRI_ERR_ARG, "null engine");
   if (mode != TRI_MATRIX && mode != TRI_RAY) return fail(TRI_ERR_ARG, "mode must be TRI_MATRIX or TRI_RAY");
   const int C = e->n_cams;
-  if (C > CLS_MAX_CAMS) return fail(TRI_ERR_ARG, "the classifier handles at most 16 cameras (the search is exponential in the camera count)");
+  if (C > CLS_MAX_CAMS && !lazy)
+    return fail(TRI_ERR_ARG, "the frame-sharded classifier enumerates the candidate combinations, which is exponential in the camera count: at most "
+                             "16 cameras (tri_classify / tri_classify_sequences take up to 32 through the lazy search)");
   if (n_drones < 1 || n_drones > TRI_MAX_DRONES) return fail(TRI_ERR_ARG, "n_drones must be in [1, TRI_MAX_DRONES]");
   if (n_frames < 0) return fail(TRI_ERR_ARG, "bad frame count");
   *n_det = 0;
@@ -917,7 +823,8 @@ void cls_stats(tri_classify_stats* stats, const ClsCounters& h, int max_frontier
 int cls_run(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t* det_offsets, const double* dets_xy, int n_frames,
             int n_seq, const int32_t* seq_bounds, double* out_paths, int8_t* out_assign, uint8_t* out_phase, tri_classify_stats* stats) {
   int64_t n_det = 0;
-  int st = cls_check(e, mode, n_drones, det_offsets, dets_xy, n_frames, &n_det);
+  const bool lazy = e && (e->n_cams > CLS_MAX_CAMS || (flags & TRI_CLS_LAZY));
+  int st = cls_check(e, mode, n_drones, det_offsets, dets_xy, n_frames, &n_det, lazy);
   if (st != TRI_OK) return st;
   if (!out_paths && n_frames > 0) return fail(TRI_ERR_ARG, "bad output arguments");
   if (stats) memset(stats, 0, sizeof(*stats));
@@ -956,6 +863,31 @@ int cls_run(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t
     }
     TRI_CUDA(W.seq.alloc(sizeof(int2) * n_seq));
     TRI_CUDA(cudaMemcpyAsync(W.seq.p, seq.data(), sizeof(int2) * n_seq, cudaMemcpyHostToDevice, s));
+  }
+
+  if (lazy) {  // more than 16 cameras, or on request: no enumeration, the lazy best-first search of tri_classify_lazy.cu
+    p.f0 = 0; p.f1 = n_frames;
+    TRI_CUDA(W.events());
+    TRI_CUDA(cudaEventRecord(W.ev[1], s));
+    TRI_CUDA(launch_lazy_link(s, e->rig64, e->ray, p, multi ? n_seq : 1, multi ? W.seq.as<int2>() : nullptr, W.offs.as<int32_t>(), W.dets.as<double>(),
+                              W.state.as<LinkState>(), W.paths.as<double>(), out_assign ? W.assign.as<int8_t>() : nullptr,
+                              out_phase ? W.phase.as<uint8_t>() : nullptr, W.ctr.as<ClsCounters>()));
+    e->launches++;
+    TRI_CUDA(cudaEventRecord(W.ev[2], s));
+    TRI_CUDA(cudaMemcpyAsync(out_paths, W.paths.p, sz_paths, cudaMemcpyDeviceToHost, s));
+    if (out_assign) TRI_CUDA(cudaMemcpyAsync(out_assign, W.assign.p, sz_assign, cudaMemcpyDeviceToHost, s));
+    if (out_phase) TRI_CUDA(cudaMemcpyAsync(out_phase, W.phase.p, sz_phase, cudaMemcpyDeviceToHost, s));
+    ClsCounters hz{};
+    TRI_CUDA(cudaMemcpyAsync(&hz, W.ctr.p, sizeof(hz), cudaMemcpyDeviceToHost, s));
+    TRI_CUDA(cudaStreamSynchronize(s));
+    float ms = 0;
+    TRI_CUDA(cudaEventElapsedTime(&ms, W.ev[1], W.ev[2]));
+    W.link_ms = ms;
+    if (hz.bad_input) return fail(TRI_ERR_ARG, "malformed detection offsets");
+    if (hz.overflow_frontier) return fail(TRI_ERR_CAPACITY, "the lazy search visited more than 2^20 nodes for one combination");
+    if (hz.overflow_final) return fail(TRI_ERR_CAPACITY, "more than 128 disjoint combinations kept in one frame");
+    cls_stats(stats, hz, 0, W);
+    return TRI_OK;
   }
 
   // Work is cut into batches of frames: (A) enumerates a batch, (B) links it.  One sequence: 8192 frames per batch, the

@@ -1,0 +1,413 @@
+// tri_classify_lazy.cu -- DroneClassifier::classifyDrones (src/DroneClassifier.cpp:96-332) WITHOUT enumerating the
+// candidate combinations: the classifier for 17..32 cameras (and, on request, for any camera count).
+//
+// The reference's fillCombinationQueue (:156-198) pushes every complete node of a tree whose size grows like
+// n_drones * 2^cameras: fine at 8 cameras (~1e3 leaves per frame), out of reach at 32 -- for the reference
+// itself, for the oracle, and for the enumerating kernels of tri_classify.cu.  But classifyDrones never needs the queue,
+// only, a handful of times per frame, "the first element the queue would pop that passes a test":
+//   phase 1 (:241-246)  the best leaf made of detections inside a path's ray gate, unique against the used ones, with
+//                       error < error_ and its point within MAX_STEP of the path's last point;
+//   phase 2 (:204-213)  repeatedly the best leaf unique against everything used or kept so far.
+// "Best" is Combination::operator< (:12-20): fewest unused cameras, then smallest error (ties: DFS order, as in
+// tri_classify.cu).  A leaf's number of used cameras can only grow along a branch, so that element is found by a
+// depth-first branch and bound over the SAME tree: children that take a detection first, a branch abandoned when even
+// taking a detection on every remaining camera cannot reach the best count found so far, and -- exactly as the reference
+// prunes (:185-187) -- below any node whose error exceeds error_.  Every node is solved with the arithmetic of the
+// enumerating path (ref::dlt_point's accumulation order, ref::lm_point), so at camera counts both can run the two
+// classifiers return bit-identical paths, assignments and phases (tests/test_gpu_classify.py at 8 and 12 cameras).
+// The search is exact; what is bounded is its budget: a search that visits more than LAZY_NODE_BUDGET nodes
+// latches TRI_ERR_CAPACITY instead of returning something else than the reference's answer.
+//
+// One warp per sequence.  Warp-uniform control flow; the lanes evaluate the children of a node in parallel
+// (lane k <-> detection k of the node's camera), each from the parent's accumulated normal equations.
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "tri_classify.cuh"
+
+namespace tri {
+
+constexpr int LZ_CAMS = TRI_MAX_CAMS;          // 32
+constexpr int LZ_SLOTS = TRI_MAX_DETS + 1;     // children of a node: "none" + up to 15 detections
+constexpr long long LAZY_NODE_BUDGET = 1 << 20;  // nodes one best-leaf search may visit
+
+struct LzShared {
+  // the frame
+  int n[LZ_CAMS];
+  double px[LZ_CAMS][TRI_MAX_DETS], py[LZ_CAMS][TRI_MAX_DETS];
+  double dir[LZ_CAMS][TRI_MAX_DETS][3];
+  unsigned short all[LZ_CAMS];      // bit d: detection d exists
+  unsigned short used[LZ_CAMS];     // detections of the combinations accepted so far in this frame
+  unsigned short allowed[LZ_CAMS];  // detections the running search may take
+  unsigned short gate[TRI_MAX_DRONES][LZ_CAMS];
+  int potential[LZ_CAMS + 1];       // cameras >= l with an allowed detection
+  // the search: state of the node at level l (cameras 0 .. l-1 decided)
+  double M[LZ_CAMS + 1][6], v[LZ_CAMS + 1][3], X[LZ_CAMS + 1][3], err[LZ_CAMS + 1];
+  int count[LZ_CAMS + 1];
+  double row[LZ_CAMS][8];           // the two rows (a0 a1 a2 b) of the k-th selected detection, selection order
+  int sel_cam[LZ_CAMS], sel_det[LZ_CAMS];
+  unsigned char choice[LZ_CAMS];
+  unsigned todo[LZ_CAMS];           // children of level l still to visit (bit 0 = none, bit k = detection k - 1)
+  double c_err[LZ_CAMS][LZ_SLOTS], c_X[LZ_CAMS][LZ_SLOTS][3];
+  // the best leaf so far
+  int best_count;
+  double best_err, best_X[3];
+  unsigned char best_choice[LZ_CAMS];
+  // classifyPaths
+  int fin_n;
+  double fin_X[LINK_MAX_FINAL][3];
+  unsigned char fin_choice[LINK_MAX_FINAL][LZ_CAMS];
+  double pdist[LINK_MAX_FINAL][TRI_MAX_DRONES];
+  int cp_path[LINK_MAX_FINAL];
+  double cp_err[LINK_MAX_FINAL];
+  LinkState S;
+};
+
+// The best leaf (fewest unused cameras, then smallest error, then DFS order) whose detections lie in sh.allowed, whose error
+// is < error_ and -- if `near` -- whose point is within MAX_STEP of near[0..2].  Result in sh.best_* (best_count = 0: none).
+// Returns false if the node budget ran out.
+__device__ bool lazy_best_leaf(const DltRig<double>& dlt, const RayRig& ray, const ClsParams& p, LzShared& sh, const double* near,
+                               unsigned long long& nodes, unsigned long long& solves, unsigned long long& lm_iters) {
+  const int lane = threadIdx.x & 31, C = p.n_cams;
+  if (lane == 0) {
+    int run = 0;
+    sh.potential[C] = 0;
+    for (int c = C - 1; c >= 0; c--) { run += sh.allowed[c] ? 1 : 0; sh.potential[c] = run; }
+    sh.best_count = 0;
+    sh.best_err = 0;
+    sh.count[0] = 0;
+    sh.err[0] = 0;
+    for (int k = 0; k < 6; k++) sh.M[0][k] = 0;
+    for (int k = 0; k < 3; k++) { sh.v[0][k] = 0; sh.X[0][k] = 0; }
+  }
+  __syncwarp();
+  int l = 0;
+  bool expanded = false;
+  long long visited = 0;
+  while (l >= 0) {
+    if (!expanded) {
+      // ---- expand the node at level l: lane k evaluates "camera l takes detection k - 1" from the parent's sums ----
+      if (++visited > LAZY_NODE_BUDGET) return false;
+      const int cnt = sh.count[l];
+      unsigned ok_bit = 0;
+      if (lane >= 1 && lane <= sh.n[l] && (sh.allowed[l] >> (lane - 1) & 1)) {
+        const double x = sh.px[l][lane - 1], y = sh.py[l][lane - 1];
+        double X[3] = {0, 0, 0}, e = 0;
+        bool keep = true;
+        if (p.solver == 0) {
+          // ref::dlt_point's arithmetic, the sums of the first cnt detections taken from the parent (same order, same bits)
+          const double* P = dlt.P[l];
+          double M[6], v[3];
+          for (int k = 0; k < 6; k++) M[k] = sh.M[l][k];
+          for (int k = 0; k < 3; k++) v[k] = sh.v[l][k];
+          double r[8];
+          r[0] = P[0] - x * P[8]; r[1] = P[1] - x * P[9]; r[2] = P[2] - x * P[10]; r[3] = x * P[11] - P[3];
+          r[4] = P[4] - y * P[8]; r[5] = P[5] - y * P[9]; r[6] = P[6] - y * P[10]; r[7] = y * P[11] - P[7];
+          for (int h = 0; h < 2; h++) {
+            const double a0 = r[4 * h], a1 = r[4 * h + 1], a2 = r[4 * h + 2], b = r[4 * h + 3];
+            M[0] += a0 * a0; M[1] += a0 * a1; M[2] += a0 * a2; M[3] += a1 * a1; M[4] += a1 * a2; M[5] += a2 * a2;
+            v[0] += a0 * b; v[1] += a1 * b; v[2] += a2 * b;
+          }
+          if (cnt + 1 >= 2) {
+            solve_sym3<double>(M, v, X);
+            double ss = 0;
+            for (int i = 0; i < cnt; i++) {
+              const double* q = sh.row[i];
+              const double e0 = (q[0] * X[0] + q[1] * X[1] + q[2] * X[2]) - q[3];
+              const double e1 = (q[4] * X[0] + q[5] * X[1] + q[6] * X[2]) - q[7];
+              ss += e0 * e0;
+              ss += e1 * e1;
+            }
+            const double e0 = (r[0] * X[0] + r[1] * X[1] + r[2] * X[2]) - r[3];
+            const double e1 = (r[4] * X[0] + r[5] * X[1] + r[6] * X[2]) - r[7];
+            ss += e0 * e0;
+            ss += e1 * e1;
+            e = sqrt(ss / (2 * (cnt + 1)));
+            solves++;
+            keep = !(e > p.error_);  // :185-187
+          }
+        } else if (cnt + 1 >= 2) {
+          ref::RaySet rs;
+          rs.n = cnt + 1;
+          for (int i = 0; i < cnt; i++) {
+            rs.cam[i] = sh.sel_cam[i];
+            for (int j = 0; j < 3; j++) rs.d[i][j] = sh.dir[sh.sel_cam[i]][sh.sel_det[i]][j];
+          }
+          rs.cam[cnt] = l;
+          for (int j = 0; j < 3; j++) rs.d[cnt][j] = sh.dir[l][lane - 1][j];
+          int it = 0;
+          e = solve_rays(ray, p.solver, rs, X, it);
+          lm_iters += it;
+          solves++;
+          keep = !(e > p.error_);
+        }
+        sh.c_err[l][lane] = e;
+        sh.c_X[l][lane][0] = X[0]; sh.c_X[l][lane][1] = X[1]; sh.c_X[l][lane][2] = X[2];
+        ok_bit = keep ? 1u << lane : 0u;
+      }
+      unsigned children = 0;
+      for (int o = 16; o > 0; o >>= 1) ok_bit |= __shfl_xor_sync(0xffffffffu, ok_bit, o);
+      children = ok_bit | 1u;  // "none" repeats the parent's subset: same error, already known to pass
+      if (lane == 0) sh.todo[l] = children;
+      nodes += __popc(children);
+      __syncwarp();
+      expanded = true;
+    }
+    // ---- the next child of level l: detections first (they lead to the leaves with the fewest unused cameras), "none" last ----
+    const unsigned todo = sh.todo[l];
+    if (!todo) { l--; expanded = true; continue; }  // back to the parent, whose todo mask is still in shared memory
+    const int k = 31 - __clz(todo);  // highest bit: detection k - 1 (k = 0: none)
+    __syncwarp();
+    if (lane == 0) sh.todo[l] = todo & ~(1u << k);
+    const int cnt = sh.count[l] + (k ? 1 : 0);
+    // bound: taking a detection on every remaining camera that has an allowed one
+    if (cnt + sh.potential[l + 1] < max(sh.best_count, MIN_CAMERAS)) { __syncwarp(); continue; }
+    if (lane == 0) {
+      sh.choice[l] = (unsigned char)k;
+      sh.count[l + 1] = cnt;
+      if (k) {
+        const int i = sh.count[l];
+        sh.sel_cam[i] = l; sh.sel_det[i] = k - 1;
+        sh.err[l + 1] = sh.c_err[l][k];
+        for (int j = 0; j < 3; j++) sh.X[l + 1][j] = sh.c_X[l][k][j];
+        if (p.solver == 0) {
+          const double* P = dlt.P[l];
+          const double x = sh.px[l][k - 1], y = sh.py[l][k - 1];
+          double* r = sh.row[i];
+          r[0] = P[0] - x * P[8]; r[1] = P[1] - x * P[9]; r[2] = P[2] - x * P[10]; r[3] = x * P[11] - P[3];
+          r[4] = P[4] - y * P[8]; r[5] = P[5] - y * P[9]; r[6] = P[6] - y * P[10]; r[7] = y * P[11] - P[7];
+          double M[6], v[3];
+          for (int q = 0; q < 6; q++) M[q] = sh.M[l][q];
+          for (int q = 0; q < 3; q++) v[q] = sh.v[l][q];
+          for (int h = 0; h < 2; h++) {
+            const double a0 = r[4 * h], a1 = r[4 * h + 1], a2 = r[4 * h + 2], b = r[4 * h + 3];
+            M[0] += a0 * a0; M[1] += a0 * a1; M[2] += a0 * a2; M[3] += a1 * a1; M[4] += a1 * a2; M[5] += a2 * a2;
+            v[0] += a0 * b; v[1] += a1 * b; v[2] += a2 * b;
+          }
+          for (int q = 0; q < 6; q++) sh.M[l + 1][q] = M[q];
+          for (int q = 0; q < 3; q++) sh.v[l + 1][q] = v[q];
+        }
+      } else {
+        sh.err[l + 1] = sh.err[l];
+        for (int j = 0; j < 3; j++) sh.X[l + 1][j] = sh.X[l][j];
+        for (int q = 0; q < 6; q++) sh.M[l + 1][q] = sh.M[l][q];
+        for (int q = 0; q < 3; q++) sh.v[l + 1][q] = sh.v[l][q];
+      }
+    }
+    __syncwarp();
+    if (l + 1 < C) { l++; expanded = false; continue; }
+    // ---- a leaf (:190-196): a candidate if it has >= MIN_CAMERAS detections, error < error_ and passes the caller's test ----
+    if (cnt >= MIN_CAMERAS && sh.err[C] < p.error_) {
+      bool pass = true;
+      if (near) {  // cv::norm(c.point - pos) < MAX_STEP, :244
+        const double dx = sh.X[C][0] - near[0], dy = sh.X[C][1] - near[1], dz = sh.X[C][2] - near[2];
+        pass = sqrt(dx * dx + dy * dy + dz * dz) < MAX_STEP;
+      }
+      if (pass) {
+        bool better = cnt > sh.best_count || (cnt == sh.best_count && sh.err[C] < sh.best_err);
+        if (!better && cnt == sh.best_count && sh.err[C] == sh.best_err) {  // a tie: DFS order = lexicographic in the choices, "none" first
+          int first = C;
+          for (int c0 = 0; c0 < C; c0 += 32) {
+            const int c = c0 + lane;
+            const unsigned diff = __ballot_sync(0xffffffffu, c < C && sh.choice[c] != sh.best_choice[c]);
+            if (diff) { first = c0 + __ffs(diff) - 1; break; }
+          }
+          better = first < C && sh.choice[first] < sh.best_choice[first];
+        }
+        if (better) {
+          __syncwarp();
+          if (lane == 0) { sh.best_count = cnt; sh.best_err = sh.err[C]; for (int j = 0; j < 3; j++) sh.best_X[j] = sh.X[C][j]; }
+          for (int c = lane; c < C; c += 32) sh.best_choice[c] = sh.choice[c];
+        }
+      }
+    }
+    __syncwarp();
+    expanded = true;  // stay on level l: its todo mask decides
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(32)
+lazy_link_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_constant__ RayRig ray, ClsParams p, const int2* __restrict__ seq_bounds,
+                 const int32_t* __restrict__ offs, const double* __restrict__ dets, LinkState* state, double* __restrict__ out_paths,
+                 int8_t* __restrict__ out_assign, uint8_t* __restrict__ out_phase, ClsCounters* ctr) {
+  extern __shared__ __align__(16) unsigned char lazy_dyn[];
+  LzShared& sh = *reinterpret_cast<LzShared*>(lazy_dyn);
+  const int lane = threadIdx.x, C = p.n_cams, D = p.n_drones;
+  const int fa = seq_bounds ? seq_bounds[blockIdx.x].x : p.f0, fb = seq_bounds ? seq_bounds[blockIdx.x].y : p.f1;
+  LinkState* st = state + blockIdx.x;
+  for (int i = lane; i < (int)(sizeof(LinkState) / sizeof(int)); i += 32) ((int*)&sh.S)[i] = ((const int*)st)[i];
+  __syncwarp();
+  unsigned long long nodes = 0, solves = 0, lm_iters = 0, n_phase1 = 0, n_phase2 = 0, leaves = 0;
+  bool out_of_budget = false, overflow_final = false, bad_input = false;
+
+  auto emit = [&](int path, int f, const double* X, const unsigned char* choice, int phase) {  // lane 0
+    const int n = sh.S.n[path];
+    double(*t)[3] = sh.S.tail[path];
+    if (n >= PATH_TAIL) {
+      for (int k = 0; k < PATH_TAIL - 1; k++) for (int j = 0; j < 3; j++) t[k][j] = t[k + 1][j];
+      for (int j = 0; j < 3; j++) t[PATH_TAIL - 1][j] = X[j];
+    } else {
+      for (int j = 0; j < 3; j++) t[n][j] = X[j];
+    }
+    if (n < 0x3fffffff) sh.S.n[path] = n + 1;
+    double* o = out_paths + ((size_t)path * p.n_frames + f) * 3;
+    o[0] = X[0]; o[1] = X[1]; o[2] = X[2];
+    if (out_assign) for (int c = 0; c < C; c++) out_assign[((size_t)path * p.n_frames + f) * C + c] = (int8_t)choice[c];
+    if (out_phase) out_phase[(size_t)path * p.n_frames + f] = (uint8_t)phase;
+  };
+
+  for (int f = fa; f < fb && !out_of_budget; f++) {
+    // ---- the frame's detections and their pixel rays ----
+    for (int c = lane; c < C; c += 32) {
+      const int a = offs[(size_t)c * (p.n_frames + 1) + f], b = offs[(size_t)c * (p.n_frames + 1) + f + 1];
+      if (b < a || b - a > TRI_MAX_DETS) bad_input = true;
+      const int n = min(max(b - a, 0), TRI_MAX_DETS);
+      sh.n[c] = n;
+      sh.all[c] = (unsigned short)((1u << n) - 1u);
+      sh.used[c] = 0;
+    }
+    __syncwarp();
+    for (int i = lane; i < C * TRI_MAX_DETS; i += 32) {
+      const int c = i / TRI_MAX_DETS, d = i - c * TRI_MAX_DETS;
+      if (d < sh.n[c]) {
+        const int a = offs[(size_t)c * (p.n_frames + 1) + f];
+        const double x = dets[2 * (size_t)(a + d)], y = dets[2 * (size_t)(a + d) + 1];
+        sh.px[c][d] = x; sh.py[c][d] = y;
+        ref::make_dir(ray, c, x, y, sh.dir[c][d]);
+      }
+    }
+    __syncwarp();
+
+    // ---- phase 1: tracking (:119-135), paths in order ----
+    unsigned processed = 0;
+    for (int np = 0; np < D && !out_of_budget; np++) {
+      const int n = sh.S.n[np];
+      if (n == 0) continue;
+      const double* last = sh.S.tail[np][min(n, PATH_TAIL) - 1];
+      if (last[0] == 0 && last[1] == 0 && last[2] == 0) continue;  // :121-123
+      // the MAX_STEP ray gate (:228-236): lane <-> camera
+      int cams_in_gate = 0;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        unsigned g = 0;
+        if (c < C)
+          for (int d = 0; d < sh.n[c]; d++)
+            if (ref::dist_to_ray(ray.pos[c], sh.dir[c][d], last[0], last[1], last[2]) < MAX_STEP) g |= 1u << d;
+        if (c < C) { sh.gate[np][c] = (unsigned short)g; sh.allowed[c] = (unsigned short)(g & ~sh.used[c]); }
+        cams_in_gate += __popc(__ballot_sync(0xffffffffu, c < C && (g & ~(c < C ? sh.used[c] : 0u)) != 0));
+      }
+      __syncwarp();
+      if (cams_in_gate < MIN_CAMERAS) continue;
+      if (!lazy_best_leaf(dlt, ray, p, sh, last, nodes, solves, lm_iters)) { out_of_budget = true; break; }
+      if (sh.best_count >= MIN_CAMERAS) {
+        leaves++;
+        processed |= 1u << np;
+        if (lane == 0) { emit(np, f, sh.best_X, sh.best_choice, 1); n_phase1++; }
+        for (int c = lane; c < C; c += 32)
+          if (sh.best_choice[c]) sh.used[c] |= (unsigned short)(1u << (sh.best_choice[c] - 1));
+        __syncwarp();
+      }
+    }
+    if (out_of_budget || __popc(processed) == D) continue;  // :137
+
+    // ---- phase 2: pickBestCombinations (:200-217): the best leaf among the unused detections, again and again ----
+    int n_fin = 0;
+    for (;;) {
+      int live = 0;
+      for (int c0 = 0; c0 < C; c0 += 32) {
+        const int c = c0 + lane;
+        if (c < C) sh.allowed[c] = (unsigned short)(sh.all[c] & ~sh.used[c]);
+        live += __popc(__ballot_sync(0xffffffffu, c < C && (sh.all[c] & ~sh.used[c]) != 0));
+      }
+      __syncwarp();
+      if (live < MIN_CAMERAS) break;
+      if (!lazy_best_leaf(dlt, ray, p, sh, nullptr, nodes, solves, lm_iters)) { out_of_budget = true; break; }
+      if (sh.best_count < MIN_CAMERAS) break;
+      leaves++;
+      if (n_fin >= LINK_MAX_FINAL) { overflow_final = true; break; }
+      if (lane == 0) for (int j = 0; j < 3; j++) sh.fin_X[n_fin][j] = sh.best_X[j];
+      for (int c = lane; c < C; c += 32) {
+        sh.fin_choice[n_fin][c] = sh.best_choice[c];
+        if (sh.best_choice[c]) sh.used[c] |= (unsigned short)(1u << (sh.best_choice[c] - 1));
+      }
+      n_fin++;
+      __syncwarp();
+    }
+    if (out_of_budget) break;
+
+    // ---- classifyPaths (:262-332) ----
+    unsigned open_paths = 0;
+    for (int j = 0; j < D; j++) if (!(processed >> j & 1u) && sh.S.n[j] != 0) open_paths |= 1u << j;
+    const int n_open = __popc(open_paths);
+    for (int q = lane; q < n_fin * n_open; q += 32) {
+      const int ci = q / n_open;
+      int j = 0;
+      { unsigned rem = open_paths; for (int s2 = q - ci * n_open; s2 > 0; s2--) rem &= rem - 1; j = __ffs(rem) - 1; }
+      const int npc = min(sh.S.n[j], PATH_TAIL);
+      double dist = 0;
+      for (int t = 0; t < npc; t++) {
+        const double dx = sh.S.tail[j][t][0] - sh.fin_X[ci][0], dy = sh.S.tail[j][t][1] - sh.fin_X[ci][1], dz = sh.S.tail[j][t][2] - sh.fin_X[ci][2];
+        dist += sqrt(dx * dx + dy * dy + dz * dz);
+      }
+      sh.pdist[ci][j] = dist / (double)npc;
+    }
+    __syncwarp();
+    for (int i = lane; i < n_fin; i += 32) {
+      int bestPath = 0;
+      double bestDist = -1;
+      for (unsigned rem = open_paths; rem; rem &= rem - 1) {
+        const int j = __ffs(rem) - 1;
+        const double dist = sh.pdist[i][j];
+        if (dist < bestDist || bestDist == -1) { bestDist = dist; bestPath = j; }
+      }
+      sh.cp_path[i] = bestPath; sh.cp_err[i] = bestDist;
+    }
+    __syncwarp();
+    if (lane == 0) {  // the stable ascending order of :299-300, walked as :302-321 does
+      unsigned done = processed;
+      unsigned long long taken_lo = 0, taken_hi = 0;
+      for (int step = 0; step < n_fin; step++) {
+        int idx = -1;
+        for (int i = 0; i < n_fin; i++) {
+          if ((i < 64 ? taken_lo >> i : taken_hi >> (i - 64)) & 1ull) continue;
+          if (idx < 0 || sh.cp_err[i] < sh.cp_err[idx]) idx = i;
+        }
+        if (idx < 64) taken_lo |= 1ull << idx; else taken_hi |= 1ull << (idx - 64);
+        int target = -1;
+        if (done >> sh.cp_path[idx] & 1u) {
+          for (int i = 0; i < D; i++) if (sh.S.n[i] == 0) { target = i; break; }
+        } else {
+          target = sh.cp_path[idx];
+        }
+        if (target != -1) { emit(target, f, sh.fin_X[idx], sh.fin_choice[idx], 2); done |= 1u << target; n_phase2++; }
+      }
+    }
+    __syncwarp();
+  }
+  __syncwarp();
+  for (int i = lane; i < (int)(sizeof(LinkState) / sizeof(int)); i += 32) ((int*)st)[i] = ((const int*)&sh.S)[i];
+  for (int o = 16; o > 0; o >>= 1) { solves += __shfl_down_sync(0xffffffffu, solves, o); lm_iters += __shfl_down_sync(0xffffffffu, lm_iters, o); }
+  if (lane == 0) {
+    atomicAdd(&ctr->nodes, nodes); atomicAdd(&ctr->solves, solves); atomicAdd(&ctr->lm_iters, lm_iters);
+    atomicAdd(&ctr->leaves, leaves); atomicAdd(&ctr->phase1, n_phase1); atomicAdd(&ctr->phase2, n_phase2);
+    if (out_of_budget) atomicExch(&ctr->overflow_frontier, 1);
+    if (overflow_final) atomicExch(&ctr->overflow_final, 1);
+  }
+  if (__any_sync(0xffffffffu, bad_input) && lane == 0) atomicExch(&ctr->bad_input, 1);
+}
+
+cudaError_t launch_lazy_link(cudaStream_t s, const DltRig<double>& dlt, const RayRig& ray, const ClsParams& p, int n_seq, const int2* d_seq,
+                             const int32_t* d_offs, const double* d_dets, LinkState* d_state, double* d_paths, int8_t* d_assign,
+                             uint8_t* d_phase, ClsCounters* d_ctr) {
+  cudaError_t err = cudaFuncSetAttribute(lazy_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzShared));
+  if (err != cudaSuccess) return err;
+  lazy_link_kernel<<<n_seq, 32, sizeof(LzShared), s>>>(dlt, ray, p, d_seq, d_offs, d_dets, d_state, d_paths, d_assign, d_phase, d_ctr);
+  return cudaGetLastError();
+}
+
+}  // namespace tri

@@ -140,8 +140,8 @@ struct DltTile64 {
     if constexpr (SMEM_ADDENDS)
       if (tid < 64) reinterpret_cast<double*>(dst)[tid] = rig.P[tid >> 3][tid & 7];
   }
-  template <int NC, int PIX, bool WIDE>
-  static __device__ __forceinline__ void run(const Rig& rig, const unsigned char* sc, const typename RawPix<PIX, 2>::type (&raw)[NC], int,
+  template <int NC, int PIX, bool WIDE, class RS>
+  static __device__ __forceinline__ void run(const Rig& rig, const unsigned char* sc, const RS& raw, int,
                                              double (&X)[2][3], uint32_t (&mask)[2], double (&err)[2], int (&iters)[2]) {
     typename S::Acc acc[2];
     mask[0] = mask[1] = 0;
@@ -243,8 +243,8 @@ struct DltX2TileT {
       }
     }
   }
-  template <int NC, int PIX, bool WIDE>
-  static __device__ __forceinline__ void run(const Rig& rig, const unsigned char* sc, const typename RawPix<PIX, 2>::type (&raw)[NC], int,
+  template <int NC, int PIX, bool WIDE, class RS>
+  static __device__ __forceinline__ void run(const Rig& rig, const unsigned char* sc, const RS& raw, int,
                                              float (&X)[2][3], uint32_t (&mask)[2], double (&err)[2], int (&iters)[2]) {
     float2 M[6] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}, {0, 0}}, v[3] = {{0, 0}, {0, 0}, {0, 0}};
     uint32_t mask0 = 0, mask1 = 0;
@@ -333,8 +333,8 @@ struct StreamProbeTile {
   using Real = float;
   static constexpr int CONST_BYTES = 0;
   static __device__ __forceinline__ void stage_consts(const Rig&, unsigned char*, int) {}
-  template <int NC, int PIX, bool WIDE>
-  static __device__ __forceinline__ void run(const Rig&, const unsigned char*, const typename RawPix<PIX, 2>::type (&raw)[NC], int, float (&X)[2][3],
+  template <int NC, int PIX, bool WIDE, class RS>
+  static __device__ __forceinline__ void run(const Rig&, const unsigned char*, const RS& raw, int, float (&X)[2][3],
                                              uint32_t (&mask)[2], double (&err)[2], int (&iters)[2]) {
     mask[0] = mask[1] = 0;
 #pragma unroll
@@ -377,22 +377,28 @@ cudaError_t launch_dlt(const LaunchCtx& ctx, bool f32, int pixfmt, const DltRig<
     const DltRigX2 x2 = make_x2(rig32);
 #ifdef TRI_TUNING
     if (ctx.debug_stream && pixfmt == PIX_F32) {
-      if (ctx.variant == 1) return launch_streamed<StreamProbeTile, P32, PIX_F32, 2, 3, 2, true>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
-      if (ctx.variant == 2) return launch_streamed<StreamProbeTile, P32, PIX_F32, 2, 4, 2, true>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      if (ctx.variant == 1) return launch_streamed<StreamProbeTile, P32, PIX_F32, 2, 3, 2, 1>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+      if (ctx.variant == 2) return launch_streamed<StreamProbeTile, P32, PIX_F32, 2, 4, 2, 1>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
       return launch_streamed<StreamProbeTile, P32, PIX_F32, 2, 3, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
     }
     if (pixfmt == PIX_F32) {
       switch (ctx.variant) {  // TRI_VARIANT: ring feeders and shapes under A/B measurement (tools/ab_variants.py)
-        case 1: return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 2, 3, true>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        case 2: return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 3, 3, true>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        case 3: return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 3, 2, true>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        case 4: return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 4, 2, true>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        case 5: return launch_streamed<DltX2TileT<true>, P32, PIX_F32, 2, 3, 3, true>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 1: return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 2, 3, 1>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 2: return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 3, 3, 1>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 3: return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 3, 2, 1>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 4: return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 4, 2, 1>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 5: return launch_streamed<DltX2TileT<true>, P32, PIX_F32, 2, 3, 3, 1>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 6: return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 2, 3, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 7: return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 3, 3, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 8: return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 2, 4, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        case 9: return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 3, 4, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
         default: break;
       }
     }
 #endif
-    if (pixfmt == PIX_F32) return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 2, 3>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
+    // float2 pixels: read from the slot camera by camera instead of pulled into registers on arrival -- fewer live registers,
+    // 1.269 -> 1.224 ms per 100 M frames (profiles/r2_dlt_variants.log); the other solves measured slower that way
+    if (pixfmt == PIX_F32) return launch_streamed<DltX2Tile, P32, PIX_F32, 2, 2, 3, 2>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
     if (pixfmt == PIX_F64) return launch_streamed<DltX2Tile, P32, PIX_F64, 2, 2, 3>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
     return launch_streamed<DltX2Tile, P32, PIX_U16, 2, 2, 3>(ctx, x2, rig32, d_xy, n_use, n_frames, cam_stride, out, 0);
   }
@@ -402,11 +408,18 @@ cudaError_t launch_dlt(const LaunchCtx& ctx, bool f32, int pixfmt, const DltRig<
 #ifdef TRI_TUNING
   if (pixfmt == PIX_F32) {
     switch (ctx.variant) {
-      case 1: return launch_streamed<T64, P64, PIX_F32, 2, 2, 2, true>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
-      case 2: return launch_streamed<T64, P64, PIX_F32, 2, 3, 2, true>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 1: return launch_streamed<T64, P64, PIX_F32, 2, 2, 2, 1>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 2: return launch_streamed<T64, P64, PIX_F32, 2, 3, 2, 1>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
       case 3: return launch_streamed<DltTile64<MASK_TABLE>, P64, PIX_F32, 2, 2, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
       case 4: return launch_streamed<DltTile64<MASK_SELECT>, P64, PIX_F32, 2, 2, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
       case 5: return launch_streamed<DltTile64<MASK_SELECT_HI, true>, P64, PIX_F32, 2, 2, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 6: return launch_streamed<T64, P64, PIX_F32, 2, 2, 2, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 7: return launch_streamed<T64, P64, PIX_F32, 2, 3, 2, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 8: return launch_streamed<T64, P64, PIX_F32, 2, 2, 3, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 9: return launch_streamed<PolicyTile<P64, 1>, P64, PIX_F32, 1, 3, 3, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 10: return launch_streamed<PolicyTile<P64, 1>, P64, PIX_F32, 1, 3, 4, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 11: return launch_streamed<PolicyTile<P64, 1>, P64, PIX_F32, 1, 3, 4, 0>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
+      case 12: return launch_streamed<PolicyTile<P64, 1>, P64, PIX_F32, 1, 4, 5, 2>(ctx, rig64, rig64, d_xy, n_use, n_frames, cam_stride, out, 0);
       default: break;
     }
   }

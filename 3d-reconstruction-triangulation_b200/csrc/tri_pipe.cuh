@@ -99,6 +99,16 @@ __device__ __forceinline__ void solve_sym3_x2(const float2 (&M)[6], const float2
   X2 = mul2(fma2(c02, v[0], fma2(c12, v[1], mul2(c22, v[2]))), inv);
 }
 
+// The pixels of one thread's frames, one RawPix per camera: either pulled into registers when the tile arrives (the slot
+// is re-armed at once) or read from the thread's shared-memory slot camera by camera as the solve needs them (LAZY: fewer
+// live registers, so more resident warps; the slot is re-armed after the solve).
+template <typename Raw, int NC, bool LAZY>
+struct RawSrc {
+  Raw regs[LAZY ? 1 : NC];
+  const Raw* slot;  // LAZY: camera c at slot[c * BATCH_THREADS]
+  __device__ __forceinline__ Raw operator[](int c) const { if constexpr (LAZY) return slot[c * BATCH_THREADS]; else return regs[c]; }
+};
+
 // ---- tile interface of the streaming kernels ------------------------------------------------------
 // A tile solver TS turns the raw pixels of FPT consecutive frames (one RawPix per camera) into points:
 //     TS::FPT, TS::Rig (a __grid_constant__ parameter), TS::Real (the arithmetic type of the result)
@@ -116,8 +126,8 @@ struct PolicyTile {
   using Real = typename S::T;
   static constexpr int CONST_BYTES = 0;
   static __device__ __forceinline__ void stage_consts(const Rig&, unsigned char*, int) {}
-  template <int NC, int PIX, bool WIDE>
-  static __device__ __forceinline__ void run(const Rig& rig, const unsigned char*, const typename RawPix<PIX, FPT>::type (&raw)[NC], int opt,
+  template <int NC, int PIX, bool WIDE, class RS>
+  static __device__ __forceinline__ void run(const Rig& rig, const unsigned char*, const RS& raw, int opt,
                                              Real (&X)[FPT][3], uint32_t (&mask)[FPT], double (&err)[FPT], int (&iters)[FPT]) {
     using T = typename S::T;
     typename S::Acc acc[FPT];
@@ -198,7 +208,7 @@ __device__ __forceinline__ void store_wide(const BatchOut& out, int64_t f0, cons
   }
 }
 
-template <class TS, int NC, int PIX, int STAGES, int MINB, bool WIDE>
+template <class TS, int NC, int PIX, int STAGES, int MINB, bool WIDE, bool LAZY = false>
 __global__ void __launch_bounds__(BATCH_THREADS, WIDE ? 1 : MINB)  // the wide instantiation keeps the pixels live for the error pass
 stream_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restrict__ xy, int64_t row_bytes, int64_t n_tiles,
               BatchOut out, int opt, unsigned long long* first_bad, int64_t frame_base) {
@@ -239,17 +249,25 @@ stream_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restri
   for (int k = 0; tile < n_tiles; k++, tile += stride) {
     const int s = k % STAGES;
     cp_async_wait<STAGES - 1>();  // this thread's copies for tile k have landed
-    Raw raw[NC];
+    RawSrc<Raw, NC, LAZY> raw;
+    if constexpr (LAZY) {
+      raw.slot = slots + (size_t)s * NC * BATCH_THREADS + tid;
+    } else {
 #pragma unroll
-    for (int c = 0; c < NC; c++) raw[c] = slots[(s * NC + c) * BATCH_THREADS + tid];
-    if (tile + STAGES * stride < n_tiles) prefetch(s, tile + STAGES * stride);
-    cp_async_commit();
+      for (int c = 0; c < NC; c++) raw.regs[c] = slots[(s * NC + c) * BATCH_THREADS + tid];
+      if (tile + STAGES * stride < n_tiles) prefetch(s, tile + STAGES * stride);
+      cp_async_commit();
+    }
 
     Real X[FPT][3];
     uint32_t mask[FPT];
     double err[FPT];
     int iters[FPT];
     TS::template run<NC, PIX, WIDE>(rig, sc, raw, opt, X, mask, err, iters);
+    if constexpr (LAZY) {  // the slot is free only now
+      if (tile + STAGES * stride < n_tiles) prefetch(s, tile + STAGES * stride);
+      cp_async_commit();
+    }
 
     const int64_t f0 = tile * TILE + (int64_t)tid * FPT;
 #pragma unroll
@@ -333,9 +351,9 @@ tma_kernel(const __grid_constant__ typename TS::Rig rig, const char* __restrict_
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += stride, k++) {
     const int s = k % STAGES;
     mbar_wait(&full[s], (uint32_t)((k / STAGES) & 1));
-    Raw raw[NC];
+    RawSrc<Raw, NC, false> raw;
 #pragma unroll
-    for (int c = 0; c < NC; c++) raw[c] = reinterpret_cast<const Raw*>(smem + s * STAGE + c * ROW)[tid];
+    for (int c = 0; c < NC; c++) raw.regs[c] = reinterpret_cast<const Raw*>(smem + s * STAGE + c * ROW)[tid];
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[s]);  // this warp holds its pixels: one of the eight arrivals that free the stage
 
@@ -383,16 +401,18 @@ static inline bool stream_aligned(const void* xy, int64_t row_bytes, int align, 
            ((uintptr_t)out.mask & 7) || ((uintptr_t)out.err & 15) || ((uintptr_t)out.iters & 7));
 }
 
-template <class TS, int N, int PIX, int STAGES, int MINB, bool WIDE, bool TMA>
+// FEED: 0 = cp.async feeder, pixels to registers on arrival; 1 = the TMA feeder (tuning builds); 2 = cp.async feeder, pixels
+// read from the slot as the solve needs them
+template <class TS, int N, int PIX, int STAGES, int MINB, bool WIDE, int FEED>
 static auto feeder_kernel() {
 #ifdef TRI_TUNING
-  if constexpr (TMA) return tma_kernel<TS, N, PIX, STAGES, MINB, WIDE>;
+  if constexpr (FEED == 1) return tma_kernel<TS, N, PIX, STAGES, MINB, WIDE>;
   else
 #endif
-  return stream_kernel<TS, N, PIX, STAGES, MINB, WIDE>;
+  return stream_kernel<TS, N, PIX, STAGES, MINB, WIDE, FEED == 2>;
 }
 
-template <class TS, int PIX, int STAGES, int MINB, bool WIDE, bool TMA>
+template <class TS, int PIX, int STAGES, int MINB, bool WIDE, int FEED>
 static cudaError_t launch_stream_w(const LaunchCtx& ctx, const typename TS::Rig& rig, const char* xy, int n_use, int64_t n_tiles,
                                    int64_t row_bytes, const BatchOut& out, int opt) {
   constexpr int FPT = TS::FPT;
@@ -400,10 +420,10 @@ static cudaError_t launch_stream_w(const LaunchCtx& ctx, const typename TS::Rig&
   cudaError_t err = cudaSuccess;
 #define TRI_CASE(N)                                                                                                     \
   case N: {                                                                                                             \
-    auto kern = feeder_kernel<TS, N, PIX, STAGES, MINB, WIDE, TMA>();                                                    \
-    constexpr int threads = TMA ? BATCH_THREADS + 32 : BATCH_THREADS;                                                   \
+    auto kern = feeder_kernel<TS, N, PIX, STAGES, MINB, WIDE, FEED>();                                                    \
+    constexpr int threads = FEED == 1 ? BATCH_THREADS + 32 : BATCH_THREADS;                                                  \
     constexpr int bytes = STAGES * N * BATCH_THREADS * (int)sizeof(Raw) + (BATCH_THREADS / 32) * 32 * FPT * 12 +         \
-                          ((TS::CONST_BYTES + 15) & ~15) + (TMA ? 2 * STAGES * 8 : 0);                                  \
+                          ((TS::CONST_BYTES + 15) & ~15) + (FEED == 1 ? 2 * STAGES * 8 : 0);                                  \
     err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);                               \
     if (err != cudaSuccess) return err;                                                                                 \
     int per_sm = 1;                                                                                                     \
@@ -421,7 +441,7 @@ static cudaError_t launch_stream_w(const LaunchCtx& ctx, const typename TS::Rig&
 
 // Launch the streaming kernel on the full tiles of [0, n_frames); *covered = the number of frames it took
 // (0 if the layout does not qualify: unaligned rows or outputs, fewer frames than a tile).
-template <class TS, int PIX, int STAGES, int MINB, bool TMA = false>
+template <class TS, int PIX, int STAGES, int MINB, int FEED = 0>
 static cudaError_t launch_stream(const LaunchCtx& ctx, const typename TS::Rig& rig, const void* d_xy, int n_use, int64_t n_frames,
                                  int64_t cam_stride, const BatchOut& out, int opt, int64_t* covered) {
   *covered = 0;
@@ -431,9 +451,9 @@ static cudaError_t launch_stream(const LaunchCtx& ctx, const typename TS::Rig& r
   const int64_t row_bytes = cam_stride * pix_bytes(PIX);
   const int64_t n_tiles = n_frames / TILE;
   if (n_tiles == 0 || n_use < 2 || n_use > 8) return cudaSuccess;
-  if (!stream_aligned(xy, row_bytes, TMA ? 16 : (int)sizeof(Raw), out)) return cudaSuccess;
-  const cudaError_t err = wants_wide(out) ? launch_stream_w<TS, PIX, STAGES, MINB, true, TMA>(ctx, rig, xy, n_use, n_tiles, row_bytes, out, opt)
-                                          : launch_stream_w<TS, PIX, STAGES, MINB, false, TMA>(ctx, rig, xy, n_use, n_tiles, row_bytes, out, opt);
+  if (!stream_aligned(xy, row_bytes, FEED == 1 ? 16 : (int)sizeof(Raw), out)) return cudaSuccess;
+  const cudaError_t err = wants_wide(out) ? launch_stream_w<TS, PIX, STAGES, MINB, true, FEED>(ctx, rig, xy, n_use, n_tiles, row_bytes, out, opt)
+                                          : launch_stream_w<TS, PIX, STAGES, MINB, false, FEED>(ctx, rig, xy, n_use, n_tiles, row_bytes, out, opt);
   if (err == cudaSuccess) *covered = n_tiles * TILE;
   return err;
 }
@@ -618,7 +638,7 @@ inline BatchOut advance(const BatchOut& o, int64_t frames) {
 
 
 // streaming kernel on the full tiles, the scalar policy kernel on whatever is left (tails, unaligned rows)
-template <class TS, class S, int PIX, int FPT, int STAGES, int MINB, bool TMA = false>
+template <class TS, class S, int PIX, int FPT, int STAGES, int MINB, int FEED = 0>
 static cudaError_t launch_streamed(const LaunchCtx& ctx, const typename TS::Rig& tile_rig, const typename S::Rig& rig,
                                    const void* d_xy, int n_use, int64_t n_frames, int64_t cam_stride, const BatchOut& out, int opt) {
   int64_t covered = 0;
@@ -627,7 +647,7 @@ static cudaError_t launch_streamed(const LaunchCtx& ctx, const typename TS::Rig&
     if (S::CHUNKED && n_use > CHUNK_CAMS)  // 9..32 cameras: camera-chunked pipeline over the scalar policy
       err = launch_chunk<S, PIX, S::CHUNK_FPT, 3, 2>(ctx, rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
     else
-      err = launch_stream<TS, PIX, STAGES, MINB, TMA>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
+      err = launch_stream<TS, PIX, STAGES, MINB, FEED>(ctx, tile_rig, d_xy, n_use, n_frames, cam_stride, out, opt, &covered);
     if (err != cudaSuccess || covered == n_frames) return err;
   }
   LaunchCtx rest = ctx;

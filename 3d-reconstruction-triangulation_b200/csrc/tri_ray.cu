@@ -165,8 +165,8 @@ struct RayTableTile {
   using Real = T_;
   static constexpr int CONST_BYTES = 0;
   static __device__ __forceinline__ void stage_consts(const Rig&, unsigned char*, int) {}
-  template <int NC, int PIX, bool WIDE>
-  static __device__ __forceinline__ void run(const Rig& rig, const unsigned char*, const typename RawPix<PIX, FPT>::type (&raw)[NC], int, T_ (&X)[FPT][3],
+  template <int NC, int PIX, bool WIDE, class RS>
+  static __device__ __forceinline__ void run(const Rig& rig, const unsigned char*, const RS& raw, int, T_ (&X)[FPT][3],
                                              uint32_t (&mask)[FPT], double (&err)[FPT], int (&iters)[FPT]) {
     using T = T_;
     static_assert(NC <= TRI_RAY_TABLE_CAMS, "the mask table covers 8 cameras");
@@ -242,24 +242,17 @@ struct RayX2Tile {
   using Real = float;
   static constexpr int CONST_BYTES = 0;
   static __device__ __forceinline__ void stage_consts(const Rig&, unsigned char*, int) {}
-  template <int NC, int PIX, bool WIDE>
-  static __device__ __forceinline__ void run(const Rig& r, const unsigned char*, const typename RawPix<PIX, 2>::type (&raw)[NC], int, float (&X)[2][3],
+  template <int NC, int PIX, bool WIDE, class RS>
+  static __device__ __forceinline__ void run(const Rig& r, const unsigned char*, const RS& raw, int, float (&X)[2][3],
                                              uint32_t (&mask)[2], double (&err)[2], int (&iters)[2]) {
     const float2 z = make_float2(0.f, 0.f);
     float2 uu[6] = {z, z, z, z, z, z}, cu[3] = {z, z, z};
     uint32_t mask0 = 0, mask1 = 0;
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
+    for (int c = 0; c < NC; c++) {  // one pass over the views: the validity masks build up alongside the sums
       const Views<float, PIX, 2> q = decode<float, PIX, 2>(raw[c]);
       mask0 |= (q.v[0] ? 1u : 0u) << c;
       mask1 |= (q.v[1] ? 1u : 0u) << c;
-    }
-    // sum of n4 ob and of n4 over the valid cameras: one table row per frame, used after the camera loop
-    const float4 k0 = __ldg(reinterpret_cast<const float4*>(r.mask_table + 8 * mask0));
-    const float4 k1 = __ldg(reinterpret_cast<const float4*>(r.mask_table + 8 * mask1));
-#pragma unroll
-    for (int c = 0; c < NC; c++) {
-      const Views<float, PIX, 2> q = decode<float, PIX, 2>(raw[c]);
       const float2 x = make_float2(q.x[0], q.x[1]), y = make_float2(q.y[0], q.y[1]);
       const float2 u0 = fma2(r.U0[c][0], x, fma2(r.U1[c][0], y, r.U2[c][0]));
       const float2 u1 = fma2(r.U0[c][1], x, fma2(r.U1[c][1], y, r.U2[c][1]));
@@ -273,6 +266,9 @@ struct RayX2Tile {
       const float2 t = fma2(s0, r.ob[c][0], fma2(s1, r.ob[c][1], mul2(s2, r.ob[c][2])));
       cu[0] = fma2(u0, t, cu[0]); cu[1] = fma2(u1, t, cu[1]); cu[2] = fma2(u2, t, cu[2]);
     }
+    // sum of n4 ob and of n4 over the valid cameras: one table row per frame (L1-resident, 8 KB)
+    const float4 k0 = __ldg(reinterpret_cast<const float4*>(r.mask_table + 8 * mask0));
+    const float4 k1 = __ldg(reinterpret_cast<const float4*>(r.mask_table + 8 * mask1));
     const float2 cn[3] = {make_float2(k0.x, k1.x), make_float2(k0.y, k1.y), make_float2(k0.z, k1.z)}, tr = make_float2(k0.w, k1.w);
     const float2 M[6] = {add2(tr, neg2(uu[0])), neg2(uu[1]), neg2(uu[2]), add2(tr, neg2(uu[3])), neg2(uu[4]), add2(tr, neg2(uu[5]))};
     const float2 cc[3] = {add2(cn[0], neg2(cu[0])), add2(cn[1], neg2(cu[1])), add2(cn[2], neg2(cu[2]))};
@@ -340,11 +336,17 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
         // 3 stages x 2 CTAs per SM: 1.32 ms per 100 M frames; 2 stages x 3 CTAs (the DLT's choice): 1.47 ms -- with the
         // lighter solve the kernel waits on memory (ncu r1f: long_scoreboard on top), so depth beats occupancy
 #ifdef TRI_TUNING
-        if (ctx.variant == 1) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 2, true>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        if (ctx.variant == 2) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 4, 2, true>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
-        if (ctx.variant == 3) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 3, true>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        if (ctx.variant == 1) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 2, 1>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        if (ctx.variant == 2) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 4, 2, 1>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        if (ctx.variant == 3) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 3, 1>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        if (ctx.variant == 4) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 2, 2>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        if (ctx.variant == 5) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 3, 2>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        if (ctx.variant == 6) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 2, 4, 2>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        if (ctx.variant == 7) return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 4, 3, 2>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
 #endif
-        return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 2>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
+        // one pass over the views, pixels read from the slot as they are needed: 1.32 -> 1.26 ms per 100 M frames
+        // (profiles/r2_dlt_variants.log; with the pixels pulled into registers on arrival the single pass measured 1.37)
+        return launch_streamed<RayX2Tile, P32, PIX_F32, 2, 3, 2, 2>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
       case PIX_F64: return launch_streamed<RayX2Tile, P32, PIX_F64, 2, 3, 2>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
       default: return launch_streamed<RayX2Tile, P32, PIX_U16, 2, 3, 2>(ctx, x2, r32, d_xy, n_use, n_frames, cam_stride, out, 0);
     }
@@ -357,8 +359,13 @@ cudaError_t launch_ray_fold(const LaunchCtx& ctx, bool lm, bool f32, int pixfmt,
   switch (pixfmt) {
     case PIX_F32:
 #ifdef TRI_TUNING
-      if (ctx.variant == 1) return lm ? launch_streamed<LMT, P64, PIX_F32, 2, 2, 2, true>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
-                                      : launch_streamed<CFT, P64, PIX_F32, 2, 3, 2, true>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+      if (ctx.variant == 1) return lm ? launch_streamed<LMT, P64, PIX_F32, 2, 2, 2, 1>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
+                                      : launch_streamed<CFT, P64, PIX_F32, 2, 3, 2, 1>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+      if (ctx.variant == 2) return lm ? launch_streamed<LMT, P64, PIX_F32, 2, 2, 2, 2>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
+                                      : launch_streamed<CFT, P64, PIX_F32, 2, 3, 2, 2>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+      if (ctx.variant == 3) return lm ? launch_streamed<LMT, P64, PIX_F32, 2, 3, 3, 2>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)
+                                      : launch_streamed<CFT, P64, PIX_F32, 2, 3, 3, 2>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
+      if (ctx.variant == 4) return launch_streamed<RayTableTile<double, false, 1>, P64, PIX_F32, 1, 3, 4, 2>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt);
 #endif
       // (4- and 6-stage rings measured the same: these two are FP64-pipe-bound)
       return lm ? launch_streamed<LMT, P64, PIX_F32, 2, 2, 2>(ctx, r64, r64, d_xy, n_use, n_frames, cam_stride, out, opt)

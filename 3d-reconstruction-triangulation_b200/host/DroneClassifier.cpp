@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <iostream>
 #include <stdexcept>
 #include <string>
 
@@ -12,6 +13,10 @@ void DroneClassifier::classifyDrones(const DetectionsContainer& container,
   if (n_cams != (int)triangulator_->getCameras().size())
     throw std::runtime_error("tri_b200: the detections have " + std::to_string(n_cams) + " cameras, the rig has " +
                              std::to_string(triangulator_->getCameras().size()));
+  // the reference announces every frame on stdout, flushed (src/DroneClassifier.cpp:113); the batched engine classifies the
+  // whole sequence in one call, so the lines come first.  setProgress(false) / TRI_B200_QUIET=1 silences them.
+  if (progress_ && !getenv("TRI_B200_QUIET"))
+    for (int frame = 0; frame < n_frames; frame++) std::cout << frame << " / " << n_frames << std::endl;
   std::vector<int32_t> offsets;
   std::vector<double> xy;
   container.toCSR(offsets, xy);

@@ -25,6 +25,7 @@ class DroneClassifier {
   const std::vector<int8_t>& assignments() const { return assign_; }
   const std::vector<uint8_t>& phases() const { return phase_; }
   const tri_classify_stats& stats() const { return stats_; }
+  void setProgress(bool on) { progress_ = on; }  // the per-frame "frame / n" lines of src/DroneClassifier.cpp:113 (on by default)
 
  private:
   Triangulator* triangulator_;
@@ -32,4 +33,5 @@ class DroneClassifier {
   std::vector<int8_t> assign_;
   std::vector<uint8_t> phase_;
   tri_classify_stats stats_{};
+  bool progress_ = true;
 };

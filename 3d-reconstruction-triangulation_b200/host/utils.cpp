@@ -1,12 +1,58 @@
 #include "utils.h"
 
+#include <cstring>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
 #include <string>
 
 namespace {
-// value of attribute `name` inside the tag text `tag` ("" if absent)
+// The document with everything a tag scanner must not look into blanked out (same length, so offsets stay valid):
+// comments <!-- -->, CDATA sections, processing instructions <? ?> and the DOCTYPE declaration.  pugixml, which the
+// reference uses (src/utils.cpp:46-49), skips the same constructs.
+std::string strip_non_markup(std::string doc) {
+  auto blank = [&](const char* open, const char* close) {
+    size_t at = 0;
+    while ((at = doc.find(open, at)) != std::string::npos) {
+      size_t end = doc.find(close, at + strlen(open));
+      end = end == std::string::npos ? doc.size() : end + strlen(close);
+      for (size_t i = at; i < end; i++) if (doc[i] != '\n') doc[i] = ' ';
+      at = end;
+    }
+  };
+  blank("<!--", "-->");
+  blank("<![CDATA[", "]]>");
+  blank("<?", "?>");
+  blank("<!DOCTYPE", ">");
+  return doc;
+}
+// the five predefined entities and numeric character references of an attribute value
+std::string unescape(const std::string& v) {
+  std::string out;
+  for (size_t i = 0; i < v.size(); i++) {
+    if (v[i] != '&') { out += v[i]; continue; }
+    const size_t semi = v.find(';', i);
+    if (semi == std::string::npos) { out += v[i]; continue; }
+    const std::string e = v.substr(i + 1, semi - i - 1);
+    if (e == "amp") out += '&'; else if (e == "lt") out += '<'; else if (e == "gt") out += '>';
+    else if (e == "quot") out += '"'; else if (e == "apos") out += '\'';
+    else if (e.size() > 1 && e[0] == '#') out += (char)(e[1] == 'x' ? std::strtol(e.c_str() + 2, nullptr, 16) : std::strtol(e.c_str() + 1, nullptr, 10));
+    else { out += v[i]; continue; }
+    i = semi;
+  }
+  return out;
+}
+// end of the tag that starts at `at` ('>' outside quoted attribute values), npos if unterminated
+size_t tag_end(const std::string& doc, size_t at) {
+  char quote = 0;
+  for (size_t i = at; i < doc.size(); i++) {
+    if (quote) { if (doc[i] == quote) quote = 0; }
+    else if (doc[i] == '"' || doc[i] == '\'') quote = doc[i];
+    else if (doc[i] == '>') return i;
+  }
+  return std::string::npos;
+}
+// value of attribute `name` inside the tag text `tag` ("" if absent); either quote character
 std::string attribute(const std::string& tag, const std::string& name) {
   size_t at = 0;
   while ((at = tag.find(name, at)) != std::string::npos) {
@@ -18,7 +64,7 @@ std::string attribute(const std::string& tag, const std::string& name) {
       if (q == std::string::npos) return "";
       const size_t end = tag.find(tag[q], q + 1);
       if (end == std::string::npos) return "";
-      return tag.substr(q + 1, end - q - 1);
+      return unescape(tag.substr(q + 1, end - q - 1));
     }
     at += name.size();
   }
@@ -45,13 +91,14 @@ std::vector<const tdr::Camera*> loadCamerasXML(const char* path) {
   if (!in) throw std::runtime_error("Cannot open camera XML file");
   std::stringstream buf;
   buf << in.rdbuf();
-  const std::string doc = buf.str();
+  const std::string doc = strip_non_markup(buf.str());
+  if (doc.find("<Cameras") == std::string::npos && doc.find('<') == std::string::npos) throw std::runtime_error("Cannot open camera XML file");
   std::vector<const tdr::Camera*> cameras;
   size_t at = 0;
   while ((at = doc.find("<Camera", at)) != std::string::npos) {
     const char next = at + 7 < doc.size() ? doc[at + 7] : '\0';
     if (next != ' ' && next != '>' && next != '\t' && next != '\n' && next != '\r') { at += 7; continue; }  // <Cameras>
-    const size_t head_end = doc.find('>', at);
+    const size_t head_end = tag_end(doc, at);
     if (head_end == std::string::npos) break;
     const std::string head = doc.substr(at, head_end - at);
     const bool self_closed = head_end > 0 && doc[head_end - 1] == '/';
@@ -59,9 +106,15 @@ std::vector<const tdr::Camera*> loadCamerasXML(const char* path) {
     if (body_end == std::string::npos) body_end = doc.size();
     const std::string body = doc.substr(head_end, body_end - head_end);
     at = body_end;
-    const size_t cf = body.find("<ControlFrame ");
+    size_t cf = 0;  // the first <ControlFrame ...> (not <ControlFrames>)
+    while ((cf = body.find("<ControlFrame", cf)) != std::string::npos) {
+      const char c2 = cf + 13 < body.size() ? body[cf + 13] : '\0';
+      if (c2 == ' ' || c2 == '\t' || c2 == '\n' || c2 == '\r' || c2 == '/' || c2 == '>') break;
+      cf += 13;
+    }
     if (cf == std::string::npos) continue;
-    const std::string frame = body.substr(cf, body.find('>', cf) - cf);
+    const size_t cf_end = tag_end(body, cf);
+    const std::string frame = body.substr(cf, (cf_end == std::string::npos ? body.size() : cf_end) - cf);
     const int id = std::atoi(attribute(head, "DEVICEID").c_str());
     const double focal = std::strtod(attribute(frame, "FOCAL_LENGTH").c_str(), nullptr);
     int width = 0, height = 0;

@@ -49,6 +49,9 @@ enum tri_flags {
                                      tri_classify*: opt in to it instead of the reference-LM solves (below)          */
   TRI_PIX_F64 = 1u << 4,          /* pixels are double2 (cv::Point2d) instead of float2          */
   TRI_PIX_U16 = 1u << 5,          /* pixels are ushort2; (0xFFFF,0xFFFF) is the missing marker   */
+  TRI_CLS_LAZY = 1u << 7,         /* tri_classify / tri_classify_sequences: the lazy best-first search instead of the candidate
+                                     enumeration -- always used above 16 cameras, where the enumeration (like the reference's
+                                     own, DroneClassifier.cpp:156-198) is out of reach; same results where both can run   */
   TRI_RAY_ANALYTIC_LM = 1u << 6,  /* ray batch: Levenberg-Marquardt with the analytic Jacobian and cv::LMSolver's damping
                                      schedule, register resident (3 iterations; same minimiser as the default)      */
   TRI_DEBUG_STREAM = 1u << 30     /* tuning build only (libtri_b200_tuning.so; TRI_ERR_ARG otherwise): the streaming
@@ -154,7 +157,8 @@ int tri_triangulate_subsets(tri_engine* e, int mode, unsigned flags, int64_t n_i
 int tri_dist_from_ray(tri_engine* e, int64_t n, const int32_t* cam_idx, const double* xy,
                       const double* points, double* out);
 
-/* DroneClassifier::classifyDrones (DroneClassifier.cpp:96-154); HOST buffers.
+/* DroneClassifier::classifyDrones (DroneClassifier.cpp:96-154); HOST buffers.  Up to 16 cameras the candidate combinations
+ * are enumerated frame-parallel and then linked; 17..32 cameras (or TRI_CLS_LAZY) run the lazy best-first search.
  * Detections in CSR form: det_offsets[cam*(n_frames+1)+f] indexes dets_xy pairs ordered
  * [cam][frame][det].  out_paths [n_drones][n_frames][3]; out_assign [n_drones][n_frames][n_cams]
  * combination indices (0 = camera unused, k = detection k-1; -1 = the path got no point in that

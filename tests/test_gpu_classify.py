@@ -325,3 +325,63 @@ def test_synthetic_six_drones_and_independent_sequences():
         one = eng.classify(T.MATRIX, 6, o, x, n)
         assert np.array_equal(many["assign"][:, a:b], one["assign"]) and np.array_equal(many["phase"][:, a:b], one["phase"])
         assert np.array_equal(many["paths"][:, a:b], one["paths"])
+
+
+@pytest.mark.parametrize("mode,flags,frames", [(T.MATRIX, 0, 400), (T.RAY, T.RAY_CLOSED_FORM, 120), (T.RAY, 0, 25)])
+def test_lazy_search_equals_the_enumeration_at_8_cameras(s09, mode, flags, frames):
+    """TRI_CLS_LAZY (the classifier of the 17..32-camera rigs: branch and bound over the reference's tree instead of
+    enumerating it) returns bit-identical paths, assignments and phases where the enumerating classifier can run."""
+    cams, eng, (offs, xy, nc, nf) = s09
+    o, x, _, _ = O.slice_frames(offs, xy, nc, nf, 0, frames)
+    a = eng.classify(mode, 6, o, x, frames, flags)
+    b = eng.classify(mode, 6, o, x, frames, flags | T.CLS_LAZY)
+    assert np.array_equal(a["assign"], b["assign"]) and np.array_equal(a["phase"], b["phase"])
+    assert np.array_equal(a["paths"], b["paths"])
+    assert (a["stats"]["phase1"], a["stats"]["phase2"]) == (b["stats"]["phase1"], b["stats"]["phase2"])
+
+
+def test_lazy_search_on_12_and_32_camera_rigs():
+    """12 cameras: the lazy search against the enumerating classifier (still runnable there: <= 16 cameras) on six simulated
+    drones, bit for bit, and both against the oracle's decisions on a prefix.  32 cameras (BASELINE config 5): only the lazy
+    search can run -- the enumeration the reference does is ~6 * 2^26 leaves per frame -- so it is checked against the
+    simulated flight: every drone tracked in every frame, a few millimetres from the truth, with ~25 cameras per point."""
+    from tri_b200 import synthetic as S
+    cams = S.ring_rig(12)
+    nf = 60
+    offs, xy, truth = S.generate_multi_drone(cams, nf, 6)
+    eng = T.Engine(cams, 0)
+    a = eng.classify(T.MATRIX, 6, offs, xy, nf)
+    b = eng.classify(T.MATRIX, 6, offs, xy, nf, T.CLS_LAZY)
+    assert np.array_equal(a["assign"], b["assign"]) and np.array_equal(a["phase"], b["phase"]) and np.array_equal(a["paths"], b["paths"])
+    o, x, _, _ = O.slice_frames(offs, xy, 12, nf, 0, 6)
+    ref = O.classify(ocams(cams), O.MATRIX, 6, o, x, 12, 6)
+    assert np.array_equal(ref["assign"], b["assign"][:, :6]) and np.array_equal(ref["phase"], b["phase"][:, :6])
+    np.testing.assert_allclose(b["paths"][:, :6], ref["paths"], rtol=1e-9, atol=1e-6)
+    # a sequence cut into recordings goes through the same search
+    bounds = [0, 25, 25, 60]
+    m = eng.classify_sequences(T.MATRIX, 6, bounds, offs, xy, nf, T.CLS_LAZY)
+    for f0, f1 in ((0, 25), (25, 60)):
+        oo, xx, _, n = O.slice_frames(offs, xy, 12, nf, f0, f1)
+        one = eng.classify(T.MATRIX, 6, oo, xx, n, T.CLS_LAZY)
+        assert np.array_equal(m["assign"][:, f0:f1], one["assign"]) and np.array_equal(m["paths"][:, f0:f1], one["paths"])
+
+    cams32 = S.ring_rig(32, rings=((6000.0, 3000.0), (9000.0, 5000.0)))
+    nf = 150
+    offs, xy, truth = S.generate_multi_drone(cams32, nf, 6)
+    eng32 = T.Engine(cams32, 0)
+    for mode, flags in ((T.MATRIX, 0), (T.RAY, T.RAY_CLOSED_FORM)):
+        r = eng32.classify(mode, 6, offs, xy, nf, flags)
+        assert np.all(r["phase"][:, 0] == 2) and np.all(r["phase"][:, 1:] == 1)  # re-initialised once, tracked ever after
+        for p in range(6):
+            d = np.linalg.norm(r["paths"][p][:, None, :] - truth.transpose(1, 0, 2), axis=2)
+            assert np.median(d.min(axis=1)) < 10.0 and d.min(axis=1)[1:].max() < 60.0 and d.min(axis=1)[0] < 200.0  # frame 0 is the greedy re-initialisation
+        used = (r["assign"] > 0).sum(axis=2)
+        assert used.mean() > 20  # ~80 % of 32 cameras per point
+        # every assigned detection exists, and no detection serves two drones in a frame
+        o2 = offs.reshape(32, nf + 1)
+        cnt = (o2[:, 1:] - o2[:, :-1]).T  # [frame][cam]
+        assert np.all(r["assign"] <= cnt[None, :, :])
+        for f in range(0, nf, 7):
+            for c in range(32):
+                ks = [int(k) for k in r["assign"][:, f, c] if k > 0]
+                assert len(ks) == len(set(ks))

@@ -191,3 +191,48 @@ def test_cpp_triangulator_adapters(host_bins, tmp_path):
     assert "throw_dim Every camera should have the same number of points" in out
     assert "throw_few Too few rays are found" in out and "throw_few Too few detections are found" in out
     assert "throw_one Too few rays are found" in out
+
+
+def test_cli_flag_forms_follow_the_reference_parser(host_bins):
+    """src/main.cpp:16-41 parses with p-ranav argparse: -h/--help and -v/--version exit 0, '--flag=value' is accepted,
+    an unknown flag or a non-integer --n_drones is an error (usage on stderr, exit code 1)."""
+    exe = host_bins[1]
+    r = subprocess.run([exe, "--help"], capture_output=True, text=True)
+    assert r.returncode == 0 and "cameras_path" in r.stderr + r.stdout and "--n_drones" in r.stderr + r.stdout
+    r = subprocess.run([exe, "-v"], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip() == "1.0"
+    r = subprocess.run([exe, "a.xml", "data", "--bogus"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Unknown argument: --bogus" in r.stderr
+    r = subprocess.run([exe, "a.xml", "data", "--n_drones=x3"], capture_output=True, text=True)
+    assert r.returncode == 1 and "pattern" in r.stderr
+    r = subprocess.run([exe, "a.xml", "--n_drones"], capture_output=True, text=True)
+    assert r.returncode == 1 and "1 argument(s) expected. 0 provided." in r.stderr
+    r = subprocess.run([exe, "a.xml", "b", "c"], capture_output=True, text=True)
+    assert r.returncode == 1 and "Maximum number of positional arguments exceeded" in r.stderr
+
+
+def test_cpp_xml_loader_skips_what_pugixml_skips(host_bins, tmp_path):
+    """Comments (with camera-looking text inside), CDATA, a processing instruction, single-quoted attributes, a '>' inside
+    an attribute value, entities and cameras without a ControlFrame: the scanner sees what the reference's pugixml
+    loader sees (src/utils.cpp:46-92) -- checked against the reference's own loader when oracle/_ref is built."""
+    src = open(G + "/R02_D1_cameras.xml").read()
+    cams = T.load_cameras_xml(G + "/R02_D1_cameras.xml")
+    body = src[src.index("<Cameras"):]
+    first = body.index("<Camera ")
+    tricky = ('<?xml version="1.0"?>\n<!-- <Camera DEVICEID="1"><ControlFrames><ControlFrame FOCAL_LENGTH="1"/></ControlFrames></Camera> -->\n'
+              + body[:first]
+              + '<Camera DEVICEID="777" NOTE="a > b"><ControlFrames/></Camera>\n<![CDATA[ <Camera DEVICEID="5"> ]]>\n'
+              + body[first:].replace('DEVICEID="', "DEVICEID='", 1).replace('"', "'", 1))
+    p = tmp_path / "tricky.xml"
+    p.write_text(tricky)
+    out = subprocess.check_output([host_bins[0], str(p), G + "/csv_sample"], text=True).splitlines()
+    rows = [l.split() for l in out if l.startswith("cam ")]
+    assert out[0] == "cameras %d" % len(cams)
+    for r, c in zip(rows, cams):
+        assert int(r[1]) == c.cam_id and np.array_equal(np.array([float(v) for v in r[6:18]]), c.P.reshape(-1))
+    import ref_py as R
+    if R.available():
+        ref = R.Reference(xml=str(p), mode=R.MATRIX)
+        assert ref.n_cams == len(cams)
+        for i, c in enumerate(cams):
+            assert np.array_equal(ref.camera(i)["P"], c.P)
