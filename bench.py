@@ -470,10 +470,36 @@ def main():
                                    "points": int(rm["stats"]["phase1"] + rm["stats"]["phase2"]), "candidate_solves": rm["stats"]["solves"],
                                    "enumerate_ms": rm["stats"]["enumerate_us"] / 1e3, "link_ms": rm["stats"]["link_us"] / 1e3},
                 "oracle_parity_first_250_frames": same,
+                "cameras_32": None,
                 "note": "wall clock of the whole call, host CSR detections in, host paths / assignments out"}
             del offs5, xy5, r1, rm
+            # the configuration's own camera count: 32 cameras on two rings.  The enumeration the reference does there is ~6 * 2^26
+            # leaves per frame -- not runnable by the reference, the oracle or the enumerating kernels -- so this is the lazy
+            # best-first search (tri_classify_lazy.cu), bit-identical to the enumeration at 8 and 12 cameras (tests/).
+            cams32 = S.ring_rig(32, rings=((6000.0, 3000.0), (9000.0, 5000.0)))
+            ceng32 = T.Engine(cams32, local)
+            n32, q32, l32 = 2000, 128, 250
+            offs32, xy32, truth32 = S.generate_multi_drone(cams32, q32 * l32, 6, device=dev)
+            o3, x3 = SH5.slice_csr(offs32, xy32, 32, q32 * l32, 0, n32)
+            ceng32.classify(T.MATRIX, 6, o3, x3, n32)
+            t0 = time.perf_counter()
+            r3 = ceng32.classify(T.MATRIX, 6, o3, x3, n32)
+            t_32 = time.perf_counter() - t0
+            b32 = np.arange(0, q32 * l32 + 1, l32, dtype=np.int32)
+            t0 = time.perf_counter()
+            r4 = ceng32.classify_sequences(T.MATRIX, 6, b32, offs32, xy32, q32 * l32)
+            t_32m = time.perf_counter() - t0
+            dmin = [float(np.median(np.linalg.norm(r3["paths"][pp][:, None, :] - truth32[:, :n32].transpose(1, 0, 2), axis=2).min(axis=1))) for pp in range(6)]
+            res["config5_classifier"]["cameras_32"] = {
+                "cameras": 32, "n_drones": 6, "mode": "matrix", "search": "lazy best-first (TRI_CLS_LAZY path, automatic above 16 cameras)",
+                "one_sequence": {"frames": n32, "seconds": t_32, "frames_per_s": n32 / t_32, "points": int(r3["stats"]["phase1"] + r3["stats"]["phase2"]),
+                                 "nodes_visited": r3["stats"]["nodes"], "solves": r3["stats"]["solves"], "link_us_per_frame": r3["stats"]["link_us"] / n32,
+                                 "median_mm_from_simulated_truth_per_path": dmin, "cameras_per_point": float((r3["assign"] > 0).sum(axis=2).mean())},
+                "many_sequences": {"sequences": q32, "frames": q32 * l32, "seconds": t_32m, "frames_per_s": q32 * l32 / t_32m,
+                                   "points": int(r4["stats"]["phase1"] + r4["stats"]["phase2"])}}
+            del offs32, xy32, r3, r4
         except Exception as exc:  # noqa: BLE001
-            res["config5_classifier"] = {"error": repr(exc)}
+            res.setdefault("config5_classifier", {})["error"] = repr(exc)
 
     # the frame-sharded classifier: every rank enumerates its frame range of S09_D6 with the trajectory-exact LM,
     # the linking chain hands the tracking state from rank to rank (one point-to-point message each)

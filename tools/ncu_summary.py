@@ -5,8 +5,9 @@ import io
 import subprocess
 import sys
 
-rep = sys.argv[1]
-raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rep = sys.argv[1]  # an .ncu-rep, or the CSV that `ncu -i file.ncu-rep --page raw --csv` printed on the GPU box
+raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw = raw[raw.index('"ID"'):] if '"ID"' in raw else raw
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
