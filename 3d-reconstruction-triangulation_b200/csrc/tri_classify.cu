@@ -39,7 +39,7 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
                  const int32_t* __restrict__ offs, const double* __restrict__ dets, u64* __restrict__ front,
                  double* __restrict__ tmp_xyz, double* __restrict__ tmp_err, u64* __restrict__ leaf_rec,
                  long long* __restrict__ leaf_off, int* __restrict__ leaf_cnt, int* __restrict__ hdr,
-                 FrameDet* __restrict__ fdet, long long* __restrict__ fdet_off, int* __restrict__ fdet_cnt, ClsCounters* ctr) {
+                 unsigned char* __restrict__ fdet, long long* __restrict__ fdet_off, int* __restrict__ fdet_cnt, ClsCounters* ctr) {
   __shared__ int s_n[CLS_MAX_CAMS], s_pref[CLS_MAX_CAMS + 1], s_hist[CLS_MAX_CAMS + 2];
   __shared__ long long s_doff;
   __shared__ double s_px[CLS_MAX_CAMS][TRI_MAX_DETS], s_py[CLS_MAX_CAMS][TRI_MAX_DETS];
@@ -75,16 +75,23 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
       fdet_cnt[f - p.f0] = n;
     }
     __syncthreads();
-    // the frame's detections with their pixel rays, camera-major: the linking pass gates them against every path
-    for (int i = tid; i < C * TRI_MAX_DETS; i += CLS_THREADS) {
-      const int c = i / TRI_MAX_DETS, d = i % TRI_MAX_DETS;
-      if (d < s_n[c]) {
-        FrameDet fd;
-        ref::make_dir(ray, c, s_px[c][d], s_py[c][d], fd.dir);
-        fd.org[0] = ray.pos[c][0]; fd.org[1] = ray.pos[c][1]; fd.org[2] = ray.pos[c][2];
-        for (int j = 0; j < 3; j++) { fd.dirf[j] = (float)fd.dir[j]; fd.orgf[j] = (float)fd.org[j]; }
-        fd.cam = c; fd.slot = d;
-        fdet[s_doff + s_pref[c] + d] = fd;
+    // the frame's detections with their pixel rays, camera-major, as the block the linking pass stages: n x float4 (origin, dir.x),
+    // n x float4 (dir.y, dir.z, camera), n x 4 doubles (dir): it gates them against every path
+    {
+      const int n = s_pref[C];
+      float4* A = reinterpret_cast<float4*>(fdet + (size_t)s_doff * FDET_BYTES);
+      float4* B = A + n;
+      double* Dd = reinterpret_cast<double*>(B + n);
+      for (int i = tid; i < C * TRI_MAX_DETS; i += CLS_THREADS) {
+        const int c = i / TRI_MAX_DETS, d = i % TRI_MAX_DETS;
+        if (d < s_n[c]) {
+          double dir[3];
+          ref::make_dir(ray, c, s_px[c][d], s_py[c][d], dir);
+          const int k = s_pref[c] + d;
+          A[k] = make_float4((float)ray.pos[c][0], (float)ray.pos[c][1], (float)ray.pos[c][2], (float)dir[0]);
+          B[k] = make_float4((float)dir[1], (float)dir[2], __int_as_float(c), 0.f);
+          Dd[4 * k] = dir[0]; Dd[4 * k + 1] = dir[1]; Dd[4 * k + 2] = dir[2]; Dd[4 * k + 3] = 0;
+        }
       }
     }
     u64 *fin = buf0, *fout = buf1;
@@ -172,18 +179,20 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
             }
             n_tie += tie;
             atomicAdd(&s_hist[zi + 1], 1);
-            u64* rec = leaf_rec + (size_t)(off + rank) * RW;
+            // the frame's block: m masks of W words, then m x (point, combination)
+            u64* mrow = leaf_rec + (size_t)off * RW + (size_t)rank * p.W;
+            u64* prow = leaf_rec + (size_t)off * RW + (size_t)m * p.W + (size_t)rank * 4;
             u64 mk[4] = {0, 0, 0, 0};
             for (int c = 0; c < C; c++) {
               const int k = (int)((ci >> (4 * c)) & 15);
               if (k) { const int bit = s_pref[c] + k - 1; mk[bit >> 6] |= 1ull << (bit & 63); }
             }
             if (!(ei < p.error_)) mk[p.W - 1] |= 1ull << 63;  // poison: a leaf (:185-196) that no acceptance test passes (:209, :243)
-            for (int w = 0; w < p.W; w++) rec[w] = mk[w];
-            rec[p.W] = (u64)__double_as_longlong(t_xyz[3 * i]);
-            rec[p.W + 1] = (u64)__double_as_longlong(t_xyz[3 * i + 1]);
-            rec[p.W + 2] = (u64)__double_as_longlong(t_xyz[3 * i + 2]);
-            rec[p.W + 3] = ci;
+            for (int w = 0; w < p.W; w++) mrow[w] = mk[w];
+            prow[0] = (u64)__double_as_longlong(t_xyz[3 * i]);
+            prow[1] = (u64)__double_as_longlong(t_xyz[3 * i + 1]);
+            prow[2] = (u64)__double_as_longlong(t_xyz[3 * i + 2]);
+            prow[3] = ci;
           }
           if (n_tie) atomicAdd(&ctr->ties, n_tie);
           __syncthreads();
@@ -193,6 +202,7 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
             int* zs = hdr + (size_t)(f - p.f0) * HDR_INTS;
             for (int z = 0; z <= C + 1; z++) { run += s_hist[z]; zs[z] = run; }  // zs[z] = leaves with fewer than z unused cameras
             for (int c = 0; c <= C; c++) zs[HDR_PREF + c] = s_pref[c];
+            *reinterpret_cast<long long*>(zs + HDR_OFF) = off;
           }
         } else if (tid == 0) {
           leaf_off[f - p.f0] = 0; leaf_cnt[f - p.f0] = 0;
@@ -216,24 +226,32 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
 }
 
 // ---- (B) linking -------------------------------------------------------------------------------
-// One CTA of eight warps per sequence, TWO block barriers per frame.  Everything that does not depend on the tracking
-// state was prepared by (A): the leaves in priority order as (detection mask, point, combination) records, the number
-// of leaves per count of unused cameras, the frame's detections with their pixel rays.  A frame's records, detections
-// and header arrive in shared memory as three bulk async copies (cp.async.bulk -> UBLKCP) that complete on an
-// mbarrier, issued one frame ahead into the other buffer.  Per frame:
-//   speculative phase 1, one warp per tracked path, all paths at once:
+// One CTA of sixteen warps per sequence; two block barriers per frame, a third when the frame has a phase 2.  Everything
+// that does not depend on the tracking state was prepared by (A): the leaves in priority order -- their detection masks
+// as one dense array, points + combination words as another --, the number of leaves per count of unused cameras, the
+// frame's detections with their pixel rays.  A frame's leaves, detections and header arrive in shared memory as three
+// bulk async copies (cp.async.bulk -> UBLKCP) that complete on an mbarrier, issued one frame ahead into the other buffer
+// by the last warp (which also reads the frame table two frames ahead, off every other warp's path).  Per frame:
+//   speculative phase 1, all tracked paths at once, LINK_WARPS / paths warps per path:
 //     gate    the MAX_STEP ray gate (:228-236) with lane <-> detection: the ballot of one 32-detection test IS a slice
 //             of the path's gate mask.  The distance runs in single precision first and in the reference's
-//             double-precision operation order only where single precision cannot decide.
+//             double-precision operation order only where single precision cannot decide.  (Each warp of a path
+//             computes the gate for itself: cheaper than handing it over.)
 //     scan    the FIRST leaf (priority order) whose mask lies inside the gate and whose point is within MAX_STEP of the
 //             path's last point (:241-246), ignoring earlier paths' picks; it starts at the first leaf with at least
-//             as many unused cameras as the gate leaves empty and tests 128 leaves per step.
-//   warp 0: confirmation in path order with shuffles (a pick that collides with an earlier one -- 404 of 14 738 on
-//     S09_D6 -- is scanned again with the used mask); phase 2, pickBestCombinations (:200-217), as ONE forward pass over
-//     the list with a running used mask -- literally the reference's pop loop; classifyPaths (:262-332) with the tail
-//     distances one (combination, open path) pair per lane and the ordered assignment by warp-wide minimum extraction.
+//             as many unused cameras as the gate leaves empty; a warp tests 128 leaves per step, the warps of a path
+//             take the 128-leaf blocks in turn and keep the smallest hit with a shared-memory atomicMin.
+//   confirmation, every warp for itself (lane <-> path): if the picks' masks are pairwise disjoint -- one OR-reduction
+//     against one sum of popcounts -- every pick is also the first of the list filtered by the earlier paths' picks
+//     (:119-135).  Otherwise (404 of 14 738 picks on S09_D6) warp 0 walks the paths in order, scans the colliding ones
+//     again with the used mask and publishes the result.
+//   phase 2, pickBestCombinations (:200-217): every warp filters its 128-leaf blocks against the used mask into a
+//     survivor bitmap; warp 0 compacts the survivors (usually a few dozen of ~750 leaves) and runs the reference's pop
+//     loop over them 32 at a time with a running used mask.
+//   classifyPaths (:262-332) on warp 0, lane <-> kept combination: tail distances, nearest open path, then the ordered
+//     assignment by warp-wide minimum extraction (three REDUX operations per step).
 // Round 1 ran this with ~15 block barriers per frame, the pixel rays and the whole phase-2 filter inside the sequential
-// kernel (29 ms for S09_D6's 3000 frames, profiles/r1_link_kernel_lines.txt); now 20 ms and falling (profiles/r2_*).
+// kernel (29 ms for S09_D6's 3000 frames, profiles/r1_link_kernel_lines.txt); the history since is in profiles/r2_link_kernel.log.
 __device__ __forceinline__ uint32_t cls_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cls_mbar_init(u64* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cls_smem_u32(bar)), "r"(count));
@@ -259,8 +277,8 @@ __device__ __forceinline__ void cls_bulk_load(void* smem_dst, const void* gmem_s
                "l"(gmem_src), "r"(bytes), "r"(cls_smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ double dist3(const double* a, const double* b) {  // cv::norm(a - b)
-  const double x = a[0] - b[0], y = a[1] - b[1], z = a[2] - b[2];
+__device__ __forceinline__ double dist3(const double* a, double bx, double by, double bz) {  // cv::norm(a - b)
+  const double x = a[0] - bx, y = a[1] - by, z = a[2] - bz;
   return sqrt(x * x + y * y + z * z);
 }
 // sqrt(s) < MAX_STEP without the square root unless s is within rounding reach of MAX_STEP^2 (sqrt is monotonic and
@@ -277,38 +295,46 @@ struct LinkLayout {
   static constexpr int RW = rec_words(W);
   static constexpr int MAX_LEAVES = W == 2 ? 1664 : 960;  // staged leaves per frame; longer lists are read from global memory
   static constexpr int REC_BYTES = MAX_LEAVES * RW * 8;
-  static constexpr int DET_BYTES = LINK_MAX_DETS * (int)sizeof(FrameDet);
+  static constexpr int DET_BYTES = LINK_MAX_DETS * FDET_BYTES;
   static constexpr int HDR_BYTES = HDR_INTS * 4;
   static constexpr int BUF_BYTES = REC_BYTES + DET_BYTES + HDR_BYTES;
   static constexpr int BYTES = 2 * BUF_BYTES + 16;  // + the two mbarriers
 };
 
-constexpr int LINK_WARPS = 8;
+constexpr int LINK_WARPS = 16;
 constexpr int LINK_THREADS = 32 * LINK_WARPS;
+constexpr int LINK_BLOCKS = 32;  // phase 2 holds the first 32 x 128 leaves of a frame in registers, two blocks per warp (the rest is walked in place)
+constexpr int LINK_NONE = 0x7fffffff;
 
-template <int W>
-__global__ void __launch_bounds__(LINK_THREADS)
+// ALL_STAGED: no frame of the batch has more than MAX_LEAVES leaves (the host knows the longest list), so the body that reads
+// leaves from global memory is not even compiled in -- the kernel is latency-bound on one SM and its instruction footprint counts.
+template <int W, bool ALL_STAGED>
+__global__ void __launch_bounds__(LINK_THREADS, 1)
 link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __restrict__ seq_bounds,
             const u64* __restrict__ leaf_rec, const long long* __restrict__ leaf_off, const int* __restrict__ leaf_cnt,
-            const int* __restrict__ hdr, const FrameDet* __restrict__ fdet, const long long* __restrict__ fdet_off,
+            const int* __restrict__ hdr, const unsigned char* __restrict__ fdet, const long long* __restrict__ fdet_off,
             const int* __restrict__ fdet_cnt, LinkState* state, double* __restrict__ out_paths, int8_t* __restrict__ out_assign,
             uint8_t* __restrict__ out_phase, ClsCounters* ctr) {
   using L_ = LinkLayout<W>;
   constexpr int RW = L_::RW;
   constexpr u64 POISON = 1ull << 63;  // in word W - 1
+  constexpr unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char link_dyn[];
   __shared__ LinkState S;
-  __shared__ float s_lastf[TRI_MAX_DRONES][4];     // single-precision copy of each path's last point
+  __shared__ float s_lastf[TRI_MAX_DRONES][4];        // single-precision copy of each path's last point
   __shared__ unsigned s_gate[TRI_MAX_DRONES][2 * W];  // 32-bit slices of each tracked path's gate mask
-  __shared__ int s_spec[TRI_MAX_DRONES];           // each tracked path's speculative pick (leaf index or -1)
-  __shared__ int s_fin_idx[LINK_MAX_FINAL], s_cp_path[LINK_MAX_FINAL];
-  __shared__ double s_cp_err[LINK_MAX_FINAL];
-  __shared__ double s_pdist[LINK_MAX_FINAL][TRI_MAX_DRONES];
+  __shared__ int s_spec[2][TRI_MAX_DRONES];           // each tracked path's speculative pick (leaf index), by frame parity
+  __shared__ u64 s_used[W];                           // a frame with colliding picks: what warp 0 confirmed
+  __shared__ unsigned s_processed;
+  __shared__ int s_win[3];                            // phase 2: the first leaf still in the list, by round mod 3
+  __shared__ int s_fin_idx[LINK_MAX_FINAL];
   u64* full = reinterpret_cast<u64*>(link_dyn + 2 * L_::BUF_BYTES);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, C = p.n_cams, D = p.n_drones;
   const int fa = seq_bounds ? seq_bounds[blockIdx.x].x : p.f0, fb = seq_bounds ? seq_bounds[blockIdx.x].y : p.f1;
   LinkState* st = state + blockIdx.x;
   for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += LINK_THREADS) ((int*)&S)[i] = ((const int*)st)[i];
+  if (tid < 2 * TRI_MAX_DRONES) (&s_spec[0][0])[tid] = LINK_NONE;
+  if (tid < 3) s_win[tid] = LINK_NONE;
   if (tid == 0) {
     cls_mbar_init(&full[0], 1); cls_mbar_init(&full[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -321,314 +347,407 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __restr
   u64 n_phase1 = 0, n_phase2 = 0;  // thread 0
   bool overflow_final = false;
 #ifdef TRI_TUNING
-  u64 prof_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  u64 prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   long long prof_t = clock64();
 #endif
 
-  // stage frame f's records / detections / header into buffer b (thread 0)
-  auto stage = [&](int b, int f, int L, long long off, int nd, long long doff) {
-    unsigned char* base = link_dyn + (size_t)b * L_::BUF_BYTES;
-    const uint32_t rec_bytes = L <= L_::MAX_LEAVES ? (uint32_t)L * RW * 8 : 0, det_bytes = (uint32_t)nd * (uint32_t)sizeof(FrameDet);
-    cls_mbar_expect_tx(&full[b], rec_bytes + det_bytes + L_::HDR_BYTES);
-    if (rec_bytes) cls_bulk_load(base, leaf_rec + (size_t)off * RW, rec_bytes, &full[b]);
-    if (det_bytes) cls_bulk_load(base + L_::REC_BYTES, fdet + doff, det_bytes, &full[b]);
-    cls_bulk_load(base + L_::REC_BYTES + L_::DET_BYTES, hdr + (size_t)(f - p.f0) * HDR_INTS, L_::HDR_BYTES, &full[b]);
-  };
-  auto emit = [&](int path, int f, const u64* r, int phase) {  // one thread: push leaf r's point to a path
-    const double x = __longlong_as_double((long long)r[W]), y = __longlong_as_double((long long)r[W + 1]), z = __longlong_as_double((long long)r[W + 2]);
-    const u64 comb = r[W + 3];
-    const int n = S.n[path];
-    double(*t)[3] = S.tail[path];
-    if (n >= PATH_TAIL) {
-      for (int k = 0; k < PATH_TAIL - 1; k++) for (int j = 0; j < 3; j++) t[k][j] = t[k + 1][j];
-      t[PATH_TAIL - 1][0] = x; t[PATH_TAIL - 1][1] = y; t[PATH_TAIL - 1][2] = z;
-    } else {
-      t[n][0] = x; t[n][1] = y; t[n][2] = z;
-    }
-    s_lastf[path][0] = (float)x; s_lastf[path][1] = (float)y; s_lastf[path][2] = (float)z;
-    if (n < 0x3fffffff) S.n[path] = n + 1;
-    double* o = out_paths + ((size_t)path * p.n_frames + f) * 3;
-    o[0] = x; o[1] = y; o[2] = z;
-    if (out_assign) {
-      int8_t* dst = out_assign + ((size_t)path * p.n_frames + f) * C;
-      if (C == 8) {  // the 8 nibbles spread to 8 bytes, one store (rows of 8 bytes are 8-byte aligned)
-        u64 v = comb & 0xffffffffull;
-        v = (v | (v << 16)) & 0x0000ffff0000ffffull;
-        v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
-        v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
-        *reinterpret_cast<u64*>(dst) = v;
-      } else {
-        for (int c = 0; c < C; c++) dst[c] = (int8_t)((comb >> (4 * c)) & 15);
-      }
-    }
-    if (out_phase) out_phase[(size_t)path * p.n_frames + f] = (uint8_t)phase;
-  };
-  // The first leaf (priority order) from index `start` on whose mask lies inside the gate g, misses `used`, and whose point is
-  // within MAX_STEP of (lx, ly, lz): what the reference's priority_queue pops first that passes :241-246.  One warp, 128
-  // leaves per step; the distance runs only for the few leaves inside the gate.
-  auto scan = [&](const u64* rec, int L, int start, const u64 (&g)[W], const u64 (&used)[W], double lx, double ly, double lz) {
-    int pick = -1;
-    for (int i0 = start & ~31; i0 < L && pick < 0; i0 += 128) {
-      unsigned cand[4];
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int i = i0 + 32 * u + lane;
-        bool ok = i < L;
-        const u64* r = rec + (size_t)(ok ? i : 0) * RW;
-#pragma unroll
-        for (int w = 0; w < W; w++) { const u64 m = r[w]; ok = ok && !(m & ~g[w]) && !(m & used[w]); }
-        cand[u] = __ballot_sync(0xffffffffu, ok);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; u++) {
-        if (cand[u] && pick < 0) {  // cv::norm(c.point - pos) < MAX_STEP, :244
-          bool ok = (cand[u] >> lane) & 1u;
-          if (ok) {
-            const u64* r = rec + (size_t)(i0 + 32 * u + lane) * RW;
-            const double x = __longlong_as_double((long long)r[W]) - lx, y = __longlong_as_double((long long)r[W + 1]) - ly,
-                         z = __longlong_as_double((long long)r[W + 2]) - lz;
-            ok = sqrt_below_step(x * x + y * y + z * z);
-          }
-          const unsigned hit = __ballot_sync(0xffffffffu, ok);
-          if (hit) pick = i0 + 32 * u + __ffs(hit) - 1;
-        }
-      }
-    }
-    return pick;
-  };
-
-  // frame metadata runs two frames ahead in registers, the staged copy one frame ahead
+  // ---- the stager: lane 0 of the last warp.  Frame table two frames ahead in registers, the staged copy one frame ahead ----
+  const bool stager = tid == LINK_THREADS - 32;
   const int nf = fb - fa;
+  int L_n1 = 0, nd_n1 = 0, L_n2 = 0, nd_n2 = 0;
+  long long off_n1 = 0, doff_n1 = 0, off_n2 = 0, doff_n2 = 0;
   auto meta = [&](int k, int& L, long long& off, int& nd, long long& doff) {
     L = 0; off = 0; nd = 0; doff = 0;
     if (k < nf) { const int g = fa + k - p.f0; L = leaf_cnt[g]; off = leaf_off[g]; nd = fdet_cnt[g]; doff = fdet_off[g]; }
   };
-  int L_n1, nd_n1, L_n2, nd_n2;
-  long long off_n1, doff_n1, off_n2, doff_n2;
-  meta(0, L_n1, off_n1, nd_n1, doff_n1);
-  meta(1, L_n2, off_n2, nd_n2, doff_n2);
-  if (tid == 0 && nf > 0) stage(0, fa, L_n1, off_n1, nd_n1, doff_n1);
+  auto stage = [&](int b, int f, int L, long long off, int nd, long long doff) {
+    unsigned char* base = link_dyn + (size_t)b * L_::BUF_BYTES;
+    const uint32_t rec_bytes = L <= L_::MAX_LEAVES ? (uint32_t)L * RW * 8 : 0, det_bytes = (uint32_t)nd * FDET_BYTES;
+    cls_mbar_expect_tx(&full[b], rec_bytes + det_bytes + L_::HDR_BYTES);
+    if (rec_bytes) cls_bulk_load(base, leaf_rec + (size_t)off * RW, rec_bytes, &full[b]);
+    if (det_bytes) cls_bulk_load(base + L_::REC_BYTES, fdet + (size_t)doff * FDET_BYTES, det_bytes, &full[b]);
+    cls_bulk_load(base + L_::REC_BYTES + L_::DET_BYTES, hdr + (size_t)(f - p.f0) * HDR_INTS, L_::HDR_BYTES, &full[b]);
+  };
+  if (stager) {
+    meta(0, L_n1, off_n1, nd_n1, doff_n1);
+    meta(1, L_n2, off_n2, nd_n2, doff_n2);
+    if (nf > 0) stage(0, fa, L_n1, off_n1, nd_n1, doff_n1);
+  }
 
-  for (int k = 0; k < nf; k++) {
+  // which warp works on which path: recomputed only when the set of tracked paths changes
+  unsigned map_mask = FULL;
+  int map_nseg = 0, map_seg = 0, map_np = -1;
+
+  // One frame.  `staged` says the leaves are in shared memory (a compile-time fact, so that they are read with LDS
+  // instead of generic loads); a frame with more than MAX_LEAVES leaves reads them from global memory.
+  auto frame = [&](auto staged, const int k, const int L) {
     const int f = fa + k, b = k & 1;
-    const int L = L_n1, nd = nd_n1;
-    const long long off = off_n1;
-    L_n1 = L_n2; off_n1 = off_n2; nd_n1 = nd_n2; doff_n1 = doff_n2;
-    __syncthreads();  // barrier 1 of 2: frame k - 1 is linked (state, its buffer free)
-    if (tid == 0 && k + 1 < nf) stage(b ^ 1, f + 1, L_n1, off_n1, nd_n1, doff_n1);
-    meta(k + 2, L_n2, off_n2, nd_n2, doff_n2);
-    CLS_PROF(0);
-    cls_mbar_wait(&full[b], (uint32_t)((k >> 1) & 1));
-    CLS_PROF(1);
     const unsigned char* base = link_dyn + (size_t)b * L_::BUF_BYTES;
-    const u64* rec = L <= L_::MAX_LEAVES ? reinterpret_cast<const u64*>(base) : leaf_rec + (size_t)off * RW;
-    const FrameDet* dets = reinterpret_cast<const FrameDet*>(base + L_::REC_BYTES);
     const int* zs = reinterpret_cast<const int*>(base + L_::REC_BYTES + L_::DET_BYTES);
+    const int nd = zs[HDR_PREF + C];
+    const u64* msk = decltype(staged)::value ? reinterpret_cast<const u64*>(base)
+                                             : leaf_rec + (size_t)(*reinterpret_cast<const long long*>(zs + HDR_OFF)) * RW;
+    const u64* pts = msk + (size_t)L * W;
+    const float4* detA = reinterpret_cast<const float4*>(base + L_::REC_BYTES);
+    const float4* detB = detA + nd;
+    const double* detD = reinterpret_cast<const double*>(detB + nd);
+    int* spec = s_spec[b];
+
+    // The first leaf (priority order) from index `start` on whose mask lies inside the gate g, misses `used`, and whose point
+    // is within MAX_STEP of (lx, ly, lz): what the reference's priority_queue pops first that passes :241-246.  This warp
+    // takes the 128-leaf blocks seg, seg + nseg, ...; `best` (shared, or nullptr) holds the smallest hit of the other warps.
+    auto scan = [&](int start, int seg, int nseg, const u64 (&g)[W], const u64 (&used)[W], double lx, double ly, double lz, const int* best) {
+      int pick = LINK_NONE;
+      for (int i0 = (start & ~31) + 128 * seg; i0 < L; i0 += 128 * nseg) {
+        if (best && *reinterpret_cast<const volatile int*>(best) < i0) break;  // an earlier block already has one
+        unsigned cand[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int i = i0 + 32 * u + lane;
+          bool ok = i < L;
+          const u64* r = msk + (size_t)(ok ? i : 0) * W;
+#pragma unroll
+          for (int w = 0; w < W; w += 2) {
+            const ulonglong2 m = *reinterpret_cast<const ulonglong2*>(r + w);
+            ok = ok && !(m.x & ~g[w]) && !(m.x & used[w]) && !(m.y & ~g[w + 1]) && !(m.y & used[w + 1]);
+          }
+          cand[u] = __ballot_sync(FULL, ok);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (cand[u] && pick == LINK_NONE) {  // cv::norm(c.point - pos) < MAX_STEP, :244
+            bool ok = (cand[u] >> lane) & 1u;
+            if (ok) {
+              const u64* r = pts + (size_t)(i0 + 32 * u + lane) * 4;
+              const double x = __longlong_as_double((long long)r[0]) - lx, y = __longlong_as_double((long long)r[1]) - ly,
+                           z = __longlong_as_double((long long)r[2]) - lz;
+              ok = sqrt_below_step(x * x + y * y + z * z);
+            }
+            const unsigned hit = __ballot_sync(FULL, ok);
+            if (hit) pick = i0 + 32 * u + __ffs(hit) - 1;
+          }
+        }
+        if (pick != LINK_NONE) break;
+      }
+      return pick;
+    };
+    auto emit = [&](int path, int leaf, int phase) {  // one thread: push a leaf's point to a path
+      const u64* r = pts + (size_t)leaf * 4;
+      const double x = __longlong_as_double((long long)r[0]), y = __longlong_as_double((long long)r[1]), z = __longlong_as_double((long long)r[2]);
+      const u64 comb = r[3];
+      const int n = S.n[path];
+      double(*t)[3] = S.tail[path];
+      if (n >= PATH_TAIL) {
+        for (int q = 0; q < PATH_TAIL - 1; q++) for (int j = 0; j < 3; j++) t[q][j] = t[q + 1][j];
+        t[PATH_TAIL - 1][0] = x; t[PATH_TAIL - 1][1] = y; t[PATH_TAIL - 1][2] = z;
+      } else {
+        t[n][0] = x; t[n][1] = y; t[n][2] = z;
+      }
+      s_lastf[path][0] = (float)x; s_lastf[path][1] = (float)y; s_lastf[path][2] = (float)z;
+      if (n < 0x3fffffff) S.n[path] = n + 1;
+      double* o = out_paths + ((size_t)path * p.n_frames + f) * 3;
+      o[0] = x; o[1] = y; o[2] = z;
+      if (out_assign) {
+        int8_t* dst = out_assign + ((size_t)path * p.n_frames + f) * C;
+        if (C == 8) {  // the 8 nibbles spread to 8 bytes, one store (rows of 8 bytes are 8-byte aligned)
+          u64 v = comb & 0xffffffffull;
+          v = (v | (v << 16)) & 0x0000ffff0000ffffull;
+          v = (v | (v << 8)) & 0x00ff00ff00ff00ffull;
+          v = (v | (v << 4)) & 0x0f0f0f0f0f0f0f0full;
+          *reinterpret_cast<u64*>(dst) = v;
+        } else {
+          for (int c = 0; c < C; c++) dst[c] = (int8_t)((comb >> (4 * c)) & 15);
+        }
+      }
+      if (out_phase) out_phase[(size_t)path * p.n_frames + f] = (uint8_t)phase;
+    };
 
     // ---- which paths track (:121-123): every warp computes the same list ----
     bool act = false;
+    int my_n = 0;
     if (lane < D) {
-      const int n = S.n[lane];
-      const double* last = S.tail[lane][min(max(n, 1), PATH_TAIL) - 1];
-      act = n != 0 && !(last[0] == 0 && last[1] == 0 && last[2] == 0);
+      my_n = S.n[lane];
+      const double* last = S.tail[lane][min(max(my_n, 1), PATH_TAIL) - 1];
+      act = my_n != 0 && !(last[0] == 0 && last[1] == 0 && last[2] == 0);
     }
-    const unsigned act_mask = __ballot_sync(0xffffffffu, act);
+    const unsigned act_mask = __ballot_sync(FULL, act);
     const int n_act = __popc(act_mask);
-    // this lane's camera (lane < C): the bits of its detections, to count the cameras a gate touches
-    u64 cam_bits[W];
-    {
-      const int b0 = lane < C ? zs[HDR_PREF + lane] : 0, b1 = lane < C ? zs[HDR_PREF + lane + 1] : 0;
-#pragma unroll
-      for (int w = 0; w < W; w++) {
-        const int lo = max(b0 - 64 * w, 0), hi = min(b1 - 64 * w, 64);
-        cam_bits[w] = hi > lo ? ((hi == 64 ? ~0ull : ((1ull << hi) - 1)) & ~((1ull << lo) - 1)) : 0ull;
+
+    // ---- speculative phase 1: path ai = warp mod n_act, block phase seg = warp div n_act of nseg (warps beyond nseg * n_act rest) ----
+    if (act_mask != map_mask) {
+      map_mask = act_mask; map_nseg = 0; map_seg = 0; map_np = -1;
+      if (n_act > 0) {
+        for (int t = n_act; t <= LINK_WARPS; t += n_act) map_nseg++;  // n_act <= TRI_MAX_DRONES = LINK_WARPS
+        int ai = warp;
+        while (ai >= n_act) { ai -= n_act; map_seg++; }
+        if (map_seg < map_nseg) { unsigned rem = act_mask; for (int q = 0; q < ai; q++) rem &= rem - 1; map_np = __ffs(rem) - 1; }
       }
     }
-    const int n_slices = (nd + 31) >> 5;
-
-    // ---- speculative phase 1, one warp per tracked path (paths beyond the warp count take turns) ----
-    // The ray gate (:228-236) with lane <-> detection: the ballot of one 32-detection test IS a slice of the gate mask.  The
-    // distance runs in single precision first and in the reference's double-precision operation order only where single
-    // precision cannot decide.  Then the scan for the path's first admissible leaf, IGNORING the picks of earlier paths.
-    for (int ai = warp; ai < n_act; ai += LINK_WARPS) {
-      int np = 0;
-      { unsigned rem = act_mask; for (int q = 0; q < ai; q++) rem &= rem - 1; np = __ffs(rem) - 1; }
-      const float lfx = s_lastf[np][0], lfy = s_lastf[np][1], lfz = s_lastf[np][2];
-      const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
-      unsigned slice[2 * W];
-#pragma unroll
-      for (int t = 0; t < 2 * W; t++) {
-        slice[t] = 0;
-        if (t < n_slices) {
-          const int di = 32 * t + lane;
-          const bool have = di < nd;
-          const FrameDet& fd = dets[have ? di : 0];
-          const float wx = lfx - fd.orgf[0], wy = lfy - fd.orgf[1], wz = lfz - fd.orgf[2];
-          const float cx = fd.dirf[1] * wz - fd.dirf[2] * wy, cy = fd.dirf[2] * wx - fd.dirf[0] * wz, cz = fd.dirf[0] * wy - fd.dirf[1] * wx;
-          const float sf = cx * cx + cy * cy + cz * cz;
-          bool gated = sf < (float)(MAX_STEP * MAX_STEP);
-          // single precision decides unless sf is within its own error of the threshold: |error of a cross-product component|
-          // <= ~6e-7 (|w|_1 |d|_1), and near the threshold d sf = 2 sqrt(sf) d c ~ 700 d c  (taken 3x wider)
-          const float tol = 4.f + 1.2e-3f * (fabsf(wx) + fabsf(wy) + fabsf(wz)) * (fabsf(fd.dirf[0]) + fabsf(fd.dirf[1]) + fabsf(fd.dirf[2]));
-          if (have && fabsf(sf - (float)(MAX_STEP * MAX_STEP)) < tol) {
-            const double ex = last[0] - fd.org[0], ey = last[1] - fd.org[1], ez = last[2] - fd.org[2];  // distToRay, Triangulator.cpp:3-9
-            const double fx = fd.dir[1] * ez - fd.dir[2] * ey, fy = fd.dir[2] * ex - fd.dir[0] * ez, fz = fd.dir[0] * ey - fd.dir[1] * ex;
-            gated = sqrt_below_step(fx * fx + fy * fy + fz * fz);
-          }
-          slice[t] = __ballot_sync(0xffffffffu, have && gated);
-        }
-      }
-      u64 g[W], none[W];
-      bool touched = false;
-#pragma unroll
-      for (int w = 0; w < W; w++) { g[w] = ((u64)slice[2 * w + 1] << 32) | slice[2 * w]; none[w] = w == W - 1 ? POISON : 0ull; touched = touched || (g[w] & cam_bits[w]); }
-      const int cams_in_gate = __popc(__ballot_sync(0xffffffffu, touched));
-      int pick = -1;
-      if (cams_in_gate >= MIN_CAMERAS)  // else fillCombinationQueue on the gated container yields nothing
-        pick = scan(rec, L, zs[C - cams_in_gate], g, none, last[0], last[1], last[2]);  // leaves with fewer unused cameras cannot lie inside the gate
-      if (lane == 0) {
-        s_spec[np] = cams_in_gate >= MIN_CAMERAS ? pick : -2;  // -2: nothing gated, no rescan needed
-#pragma unroll
-        for (int t = 0; t < 2 * W; t++) s_gate[np][t] = slice[t];
-      }
-    }
-    CLS_PROF(2);
-    __syncthreads();  // barrier 2 of 2: the speculative picks are in
-    if (warp != 0) continue;
-
-    // ---- warp 0: confirm the picks in path order (:119-135) ----
-    // A pick that collides with nothing confirmed before it is also the first of the filtered list; otherwise (rare) the
-    // path is scanned again with the used mask.  Lane np holds path np's pick.
-    u64 used[W];
-#pragma unroll
-    for (int w = 0; w < W; w++) used[w] = w == W - 1 ? POISON : 0ull;
-    unsigned processed = 0;
     {
-      int cand = (lane < D && ((act_mask >> lane) & 1u)) ? s_spec[lane] : -2;
-      u64 mk[W];
+      const int np = map_np, seg = map_seg, nseg = map_nseg;
+      if (np >= 0) {
+        const int n_slices = (nd + 31) >> 5;
+        const float lfx = s_lastf[np][0], lfy = s_lastf[np][1], lfz = s_lastf[np][2];
+        const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
+        unsigned slice[2 * W], cam_set = 0;
 #pragma unroll
-      for (int w = 0; w < W; w++) mk[w] = cand >= 0 ? rec[(size_t)cand * RW + w] : 0ull;
-      for (unsigned rem = act_mask; rem; rem &= rem - 1) {
-        const int np = __ffs(rem) - 1;
-        int c_np = __shfl_sync(0xffffffffu, cand, np);
-        if (c_np < 0) continue;
-        bool clash = false;
-#pragma unroll
-        for (int w = 0; w < W; w++) clash = clash || (__shfl_sync(0xffffffffu, mk[w], np) & used[w]);
-        if (clash) {  // walk the list again with the used filter
-          u64 g[W];
-#pragma unroll
-          for (int w = 0; w < W; w++) g[w] = ((u64)s_gate[np][2 * w + 1] << 32) | s_gate[np][2 * w];
-          const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
-          c_np = scan(rec, L, c_np, g, used, last[0], last[1], last[2]);  // nothing before the unfiltered pick can pass
-          if (lane == np) {
-            cand = c_np;
-#pragma unroll
-            for (int w = 0; w < W; w++) mk[w] = c_np >= 0 ? rec[(size_t)c_np * RW + w] : 0ull;
+        for (int t = 0; t < 2 * W; t++) {
+          slice[t] = 0;
+          if (t < n_slices) {
+            const int di = 32 * t + lane;
+            const bool have = di < nd;
+            const float4 A = detA[have ? di : 0], B = detB[have ? di : 0];  // A = origin, dir.x; B = dir.y, dir.z, camera
+            const float wx = lfx - A.x, wy = lfy - A.y, wz = lfz - A.z;
+            const float cx = B.x * wz - B.y * wy, cy = B.y * wx - A.w * wz, cz = A.w * wy - B.x * wx;
+            const float sf = cx * cx + cy * cy + cz * cz;
+            bool gated = sf < (float)(MAX_STEP * MAX_STEP);
+            // single precision decides unless sf is within its own error of the threshold: |error of a cross-product component|
+            // <= ~6e-7 (|w|_1 |d|_1), and near the threshold d sf = 2 sqrt(sf) d c ~ 700 d c  (taken 3x wider)
+            const float tol = 4.f + 2.1e-3f * (fabsf(wx) + fabsf(wy) + fabsf(wz));  // |d|_1 <= sqrt(3)
+            if (have && fabsf(sf - (float)(MAX_STEP * MAX_STEP)) < tol) {
+              const double* dd = detD + 4 * di;
+              const double* org = ray.pos[__float_as_int(B.z)];
+              const double ex = last[0] - org[0], ey = last[1] - org[1], ez = last[2] - org[2];  // distToRay, Triangulator.cpp:3-9
+              const double fx = dd[1] * ez - dd[2] * ey, fy = dd[2] * ex - dd[0] * ez, fz = dd[0] * ey - dd[1] * ex;
+              gated = sqrt_below_step(fx * fx + fy * fy + fz * fz);
+            }
+            slice[t] = __ballot_sync(FULL, have && gated);
+            if (have && gated) cam_set |= 1u << __float_as_int(B.z);
           }
-          if (c_np < 0) continue;
         }
+        u64 g[W], none[W];
 #pragma unroll
-        for (int w = 0; w < W; w++) used[w] |= __shfl_sync(0xffffffffu, mk[w], np);
-        processed |= 1u << np;
+        for (int w = 0; w < W; w++) { g[w] = ((u64)slice[2 * w + 1] << 32) | slice[2 * w]; none[w] = w == W - 1 ? POISON : 0ull; }
+        const int cams_in_gate = __popc(__reduce_or_sync(FULL, cam_set));  // cameras with a detection inside the gate
+        if (seg == 0 && lane < 2 * W) {
+          unsigned v = 0;
+#pragma unroll
+          for (int t = 0; t < 2 * W; t++) v = lane == t ? slice[t] : v;
+          s_gate[np][lane] = v;
+        }
+        CLS_PROF(2);
+        if (cams_in_gate >= MIN_CAMERAS) {  // else fillCombinationQueue on the gated container yields nothing
+          // leaves with fewer unused cameras than the gate leaves empty cannot lie inside it
+          const int pick = scan(zs[C - cams_in_gate], seg, nseg, g, none, last[0], last[1], last[2], nseg > 1 ? &spec[np] : nullptr);
+          if (lane == 0 && pick != LINK_NONE) atomicMin(&spec[np], pick);
+        }
       }
-      if ((processed >> lane) & 1u) emit(lane, f, rec + (size_t)cand * RW, 1);  // all confirmed paths at once, one lane per path
-      if (lane == 0) n_phase1 += __popc(processed);
-      __syncwarp();
     }
     CLS_PROF(3);
-    if (__popc(processed) == D) continue;  // :137
+    __syncthreads();  // barrier 2: the speculative picks are in
+    CLS_PROF(4);
 
-    // ---- phase 2: pickBestCombinations (:200-217), one forward pass with a running used mask, 128 leaves per step ----
-    int n_fin = 0;
-    for (int i0 = 0; i0 < L; i0 += 128) {
-      u64 m[4][W];
+    // ---- confirm the picks (:119-135), lane <-> path, every warp for itself ----
+    u64 used[W];
+    unsigned processed;
+    int cand = (lane < D && ((act_mask >> lane) & 1u)) ? spec[lane] : LINK_NONE;
+    {
+      u64 mk[W];
+      unsigned bits = 0, any = 0;
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        const int i = i0 + 32 * u + lane;
-#pragma unroll
-        for (int w = 0; w < W; w++) m[u][w] = i < L ? rec[(size_t)i * RW + w] : ~0ull;
+      for (int w = 0; w < W; w++) {
+        mk[w] = cand != LINK_NONE ? msk[(size_t)cand * W + w] : 0ull;
+        bits += __popcll(mk[w]);
+        const unsigned lo = __reduce_or_sync(FULL, (unsigned)mk[w]), hi = __reduce_or_sync(FULL, (unsigned)(mk[w] >> 32));
+        used[w] = ((u64)hi << 32) | lo;
+        any += __popc(lo) + __popc(hi);
       }
+      used[W - 1] |= POISON;
+      processed = __ballot_sync(FULL, cand != LINK_NONE);
+      if (__reduce_add_sync(FULL, bits) != any) {  // two picks share a detection: walk the paths in order (warp 0), rare
+        if (warp == 0) {
 #pragma unroll
-      for (int u = 0; u < 4; u++) {
-        bool ok = true;
+          for (int w = 0; w < W; w++) used[w] = w == W - 1 ? POISON : 0ull;
+          processed = 0;
+          for (unsigned rem = act_mask; rem; rem &= rem - 1) {
+            const int np = __ffs(rem) - 1;
+            int c_np = __shfl_sync(FULL, cand, np);
+            if (c_np == LINK_NONE) continue;
+            bool clash = false;
 #pragma unroll
-        for (int w = 0; w < W; w++) ok = ok && !(m[u][w] & used[w]);
-        unsigned hit = __ballot_sync(0xffffffffu, ok);
-        while (hit) {
-          const int j = __ffs(hit) - 1;
-          bool clash = false;
+            for (int w = 0; w < W; w++) clash = clash || (__shfl_sync(FULL, mk[w], np) & used[w]);
+            if (clash) {  // walk the list again with the used filter; nothing before the unfiltered pick can pass
+              u64 g[W];
 #pragma unroll
-          for (int w = 0; w < W; w++) {
-            const u64 mj = __shfl_sync(0xffffffffu, m[u][w], j);
-            used[w] |= mj;
-            clash = clash || (m[u][w] & mj);
+              for (int w = 0; w < W; w++) g[w] = ((u64)s_gate[np][2 * w + 1] << 32) | s_gate[np][2 * w];
+              const double* last = S.tail[np][min(S.n[np], PATH_TAIL) - 1];
+              c_np = scan(c_np, 0, 1, g, used, last[0], last[1], last[2], nullptr);
+              if (lane == np) {
+                cand = c_np;
+#pragma unroll
+                for (int w = 0; w < W; w++) mk[w] = c_np != LINK_NONE ? msk[(size_t)c_np * W + w] : 0ull;
+              }
+              if (c_np == LINK_NONE) continue;
+            }
+#pragma unroll
+            for (int w = 0; w < W; w++) used[w] |= __shfl_sync(FULL, mk[w], np);
+            processed |= 1u << np;
           }
-          if (n_fin < LINK_MAX_FINAL) { if (lane == 0) s_fin_idx[n_fin] = i0 + 32 * u + j; n_fin++; }
-          else overflow_final = true;
-          ok = ok && !clash;  // lane j clashes with itself
-          hit = __ballot_sync(0xffffffffu, ok);
+          if (lane == 0) {
+#pragma unroll
+            for (int w = 0; w < W; w++) s_used[w] = used[w];
+            s_processed = processed;
+          }
+        }
+        __syncthreads();  // (only in such frames)
+#pragma unroll
+        for (int w = 0; w < W; w++) used[w] = s_used[w];
+        processed = s_processed;
+      }
+    }
+    CLS_PROF(8);
+    if (warp == 0) {
+      if ((processed >> lane) & 1u) emit(lane, cand, 1);  // all confirmed paths at once, one lane per path
+      if (lane == 0) n_phase1 += __popc(processed);
+    }
+    CLS_PROF(5);
+    if (__popc(processed) == D) return;  // :137
+
+    // ---- phase 2: pickBestCombinations (:200-217), the reference's pop loop in parallel.  Every warp keeps the masks of
+    // its 128-leaf blocks in registers (block = warp + 16 j); a round finds the first leaf of the whole list that misses
+    // the used mask (REDUX.MIN in the warp, atomicMin across the warps, one block barrier), adds its mask to the used
+    // mask and strikes the leaves it collides with; the loop ends with the round that finds nothing. ----
+    int n_fin = 0;
+    {
+      constexpr int NB = LINK_BLOCKS / LINK_WARPS;
+      u64 m[NB][4][W];
+      unsigned ok = 0;  // bit 4 j + u: leaf 128 (warp + 16 j) + 32 u + lane is still in the list
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+        const int i0 = 128 * (warp + LINK_WARPS * j);
+        if (i0 < L) {
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int i = i0 + 32 * u + lane;
+            bool o = i < L;
+            const u64* r = msk + (size_t)(o ? i : 0) * W;
+#pragma unroll
+            for (int w = 0; w < W; w += 2) {
+              const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(r + w);
+              m[j][u][w] = v.x; m[j][u][w + 1] = v.y;
+              o = o && !(v.x & used[w]) && !(v.y & used[w + 1]);
+            }
+            ok |= (unsigned)o << (4 * j + u);
+          }
+        }
+      }
+      for (int round = 0;; round++) {
+        int* win = &s_win[round % 3];
+        unsigned mine = (unsigned)LINK_NONE;  // this lane's first leaf still in the list (blocks and words in rising order)
+#pragma unroll
+        for (int j = NB - 1; j >= 0; j--)
+#pragma unroll
+          for (int u = 3; u >= 0; u--) mine = (ok >> (4 * j + u) & 1u) ? (unsigned)(128 * (warp + LINK_WARPS * j) + 32 * u + lane) : mine;
+        const unsigned first = __reduce_min_sync(FULL, mine);
+        if (lane == 0 && first != (unsigned)LINK_NONE) atomicMin(win, (int)first);
+        __syncthreads();
+        const int pick = *reinterpret_cast<volatile int*>(win);
+        if (tid == 0) s_win[(round + 2) % 3] = LINK_NONE;  // read last in round - 1, used next in round + 2
+        if (pick == LINK_NONE) break;
+        u64 mj[W];
+#pragma unroll
+        for (int w = 0; w < W; w++) { mj[w] = msk[(size_t)pick * W + w]; used[w] |= mj[w]; }
+#pragma unroll
+        for (int j = 0; j < NB; j++)
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            bool clash = false;
+#pragma unroll
+            for (int w = 0; w < W; w++) clash = clash || (m[j][u][w] & mj[w]);
+            if (clash) ok &= ~(1u << (4 * j + u));  // (the pick collides with itself)
+          }
+        if (n_fin < LINK_MAX_FINAL) { if (tid == 0) s_fin_idx[n_fin] = pick; n_fin++; }
+        else overflow_final = true;
+      }
+    }
+    if (warp != 0) return;
+    // (leaves beyond the blocks held in registers: walked in place, 32 at a time)
+    for (int i0 = 128 * LINK_BLOCKS; i0 < L; i0 += 32) {
+      const int li = i0 + lane < L ? i0 + lane : -1;
+      u64 m[W];
+      bool o = li >= 0;
+#pragma unroll
+      for (int w = 0; w < W; w++) { m[w] = o ? msk[(size_t)li * W + w] : 0ull; }
+#pragma unroll
+      for (int w = 0; w < W; w++) o = o && !(m[w] & used[w]);
+      unsigned hit = __ballot_sync(FULL, o);
+      while (hit) {
+        const int j = __ffs(hit) - 1;
+        bool clash = false;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+          const u64 mj = __shfl_sync(FULL, m[w], j);
+          used[w] |= mj;
+          clash = clash || (m[w] & mj);
+        }
+        if (n_fin < LINK_MAX_FINAL) { if (lane == 0) s_fin_idx[n_fin] = i0 + j; n_fin++; }
+        else overflow_final = true;
+        o = o && !clash;  // lane j clashes with itself
+        hit = __ballot_sync(FULL, o);
+      }
+    }
+    __syncwarp();
+    CLS_PROF(6);
+
+    // ---- classifyPaths (:262-332), lane <-> kept combination (four rounds of 32 at most) ----
+    const unsigned nonempty = __ballot_sync(FULL, lane < D && S.n[lane] != 0);  // S.n after phase 1's pushes
+    const unsigned d_mask = D >= 32 ? FULL : ((1u << D) - 1);
+    const unsigned open_paths = nonempty & ~processed;  // not processed and not empty: the only ones :269-297 measures
+    const int one_open = (n_fin == 1 && __popc(open_paths) == 1) ? __ffs(open_paths) - 1 : -1;
+    double e[LINK_MAX_FINAL / 32];
+    int bp[LINK_MAX_FINAL / 32];
+#pragma unroll
+    for (int q = 0; q < LINK_MAX_FINAL / 32; q++) {
+      e[q] = -1; bp[q] = 0;
+      const int i = lane + 32 * q;
+      if (i < n_fin && one_open >= 0) bp[q] = one_open;  // a single kept combination and a single open path: nothing to measure or to order
+      else if (i < n_fin) {  // :269-297 (the processed set does not change until the assignment loop)
+        const u64* r = pts + (size_t)s_fin_idx[i] * 4;
+        const double px = __longlong_as_double((long long)r[0]), py = __longlong_as_double((long long)r[1]), pz = __longlong_as_double((long long)r[2]);
+        for (unsigned rem = open_paths; rem; rem &= rem - 1) {
+          const int j = __ffs(rem) - 1;
+          const int npc = min(S.n[j], PATH_TAIL);
+          double dist = 0;
+          for (int t = 0; t < npc; t++) dist += dist3(S.tail[j][t], px, py, pz);
+          dist = dist / (double)npc;
+          if (dist < e[q] || e[q] == -1) { e[q] = dist; bp[q] = j; }
         }
       }
     }
-    __syncwarp();
-    CLS_PROF(4);
-
-    // ---- classifyPaths (:262-332): tail distances one (combination, open path) pair per lane, then per combination its
-    // nearest open path (lane <-> combination), the insertion sort and the assignment on lane 0 ----
-    unsigned open_paths = 0;  // not processed and not empty: the only ones :269-297 measures
-    for (int j = 0; j < D; j++) if (!(processed >> j & 1u) && S.n[j] != 0) open_paths |= 1u << j;
-    const int n_open = __popc(open_paths);
-    for (int q = lane; q < n_fin * n_open; q += 32) {
-      const int ci = q / n_open;
-      int j = 0;
-      { unsigned rem = open_paths; for (int s2 = q - ci * n_open; s2 > 0; s2--) rem &= rem - 1; j = __ffs(rem) - 1; }
-      const int npc = min(S.n[j], PATH_TAIL);
-      const u64* r = rec + (size_t)s_fin_idx[ci] * RW;
-      const double pt[3] = {__longlong_as_double((long long)r[W]), __longlong_as_double((long long)r[W + 1]), __longlong_as_double((long long)r[W + 2])};
-      double dist = 0;
-      for (int t = 0; t < npc; t++) dist += dist3(S.tail[j][t], pt);
-      s_pdist[ci][j] = dist / (double)npc;
-    }
-    __syncwarp();
-    for (int i = lane; i < n_fin; i += 32) {  // :269-297 (the processed set does not change until the assignment loop)
-      int bestPath = 0;
-      double bestDist = -1;
-      for (unsigned rem = open_paths; rem; rem &= rem - 1) {
-        const int j = __ffs(rem) - 1;
-        const double dist = s_pdist[i][j];
-        if (dist < bestDist || bestDist == -1) { bestDist = dist; bestPath = j; }
-      }
-      s_cp_path[i] = bestPath; s_cp_err[i] = bestDist;
-    }
-    __syncwarp();
     // The reference sorts the (combination, nearest path, distance) triples by distance -- std::sort(greater<>) of <= 16
     // elements is libstdc++'s insertion sort: stable, ascending -- and walks them in that order (:299-321).  A triple only
     // acts while an open or an empty path is left, so instead of sorting, the warp extracts the next triple (smallest
-    // distance, then smallest index) with shuffles and stops as soon as no path can take a point any more.
+    // distance, then smallest index) and stops as soon as no path can take a point any more.  Distances are >= 0 (or all
+    // -1 when no path is open), so their bit patterns order like the values: the minimum is two 32-bit REDUX.MIN.
     {
       unsigned done = processed;
-      unsigned empty_paths = 0;
-      for (int i = 0; i < D; i++) if (S.n[i] == 0) empty_paths |= 1u << i;
-      unsigned long long taken = 0;  // bit q: triple lane + 32 q of this lane is consumed (n_fin <= 128)
+      unsigned empty_paths = d_mask & ~nonempty;
+      unsigned taken = 0;  // bit q: this lane's triple lane + 32 q is consumed
       for (int step = 0; step < n_fin; step++) {
         if (!(open_paths & ~done) && !empty_paths) break;  // every remaining triple would find its path taken and no empty one
-        double e = 0;
-        int idx = 0x7fffffff;
-        for (int q = 0, i = lane; i < n_fin; q++, i += 32)
-          if (!(taken >> q & 1ull) && (idx == 0x7fffffff || s_cp_err[i] < e)) { e = s_cp_err[i]; idx = i; }
-        for (int o = 16; o > 0; o >>= 1) {
-          const double e2 = __shfl_xor_sync(0xffffffffu, e, o);
-          const int i2 = __shfl_xor_sync(0xffffffffu, idx, o);
-          if (i2 != 0x7fffffff && (idx == 0x7fffffff || e2 < e || (e2 == e && i2 < idx))) { e = e2; idx = i2; }
+        u64 key = ~0ull;
+        int idx = LINK_NONE;
+#pragma unroll
+        for (int q = 0; q < LINK_MAX_FINAL / 32; q++) {
+          const int i = lane + 32 * q;
+          const u64 kq = (u64)__double_as_longlong(e[q]);
+          if (i < n_fin && !(taken >> q & 1u) && (idx == LINK_NONE || kq < key)) { key = kq; idx = i; }
         }
-        if ((idx & 31) == lane) taken |= 1ull << (idx >> 5);
-        const int pth = s_cp_path[idx];
+        const unsigned hi = (unsigned)(key >> 32), mh = __reduce_min_sync(FULL, hi);
+        const unsigned lo = hi == mh ? (unsigned)key : 0xffffffffu, ml = __reduce_min_sync(FULL, lo);
+        const unsigned mine = (hi == mh && lo == ml) ? (unsigned)idx : (unsigned)LINK_NONE;
+        const int win = (int)__reduce_min_sync(FULL, mine);
+        const int wq = win >> 5;
+        if ((win & 31) == lane) taken |= 1u << wq;
+        int pth_l = bp[0];
+#pragma unroll
+        for (int q = 1; q < LINK_MAX_FINAL / 32; q++) pth_l = wq == q ? bp[q] : pth_l;
+        const int pth = __shfl_sync(FULL, pth_l, win & 31);
         int target = -1;
         if (done >> pth & 1u) { if (empty_paths) target = __ffs(empty_paths) - 1; }  // the first empty path (:305-311)
         else target = pth;
         if (target != -1) {
-          if (lane == 0) { emit(target, f, rec + (size_t)s_fin_idx[idx] * RW, 2); n_phase2++; }
+          if (lane == 0) { emit(target, s_fin_idx[win], 2); n_phase2++; }
           done |= 1u << target;
           empty_paths &= ~(1u << target);
           __syncwarp();
@@ -636,12 +755,34 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __restr
       }
     }
     __syncwarp();
-    CLS_PROF(5);
+    CLS_PROF(7);
+  };
+
+  for (int k = 0; k < nf; k++) {
+    const int b = k & 1;
+    __syncthreads();  // barrier 1: frame k - 1 is linked (state, its buffer free)
+    CLS_PROF(9);
+    if (stager) {
+      L_n1 = L_n2; off_n1 = off_n2; nd_n1 = nd_n2; doff_n1 = doff_n2;
+      if (k + 1 < nf) stage(b ^ 1, fa + k + 1, L_n1, off_n1, nd_n1, doff_n1);
+      meta(k + 2, L_n2, off_n2, nd_n2, doff_n2);
+    }
+    if (warp == 0 && lane < D) s_spec[b ^ 1][lane] = LINK_NONE;  // last read in frame k - 1, next written in frame k + 1
+    CLS_PROF(0);
+    cls_mbar_wait(&full[b], (uint32_t)((k >> 1) & 1));
+    CLS_PROF(1);
+    const int L = reinterpret_cast<const int*>(link_dyn + (size_t)b * L_::BUF_BYTES + L_::REC_BYTES + L_::DET_BYTES)[C + 1];
+    if constexpr (ALL_STAGED) {
+      frame(std::true_type{}, k, L);
+    } else {
+      if (L <= L_::MAX_LEAVES) frame(std::true_type{}, k, L);
+      else frame(std::false_type{}, k, L);
+    }
   }
   __syncthreads();
   for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += LINK_THREADS) ((int*)st)[i] = ((const int*)&S)[i];
 #ifdef TRI_TUNING
-  if (tid == 0) for (int q = 0; q < 8; q++) atomicAdd(&ctr->prof[q], prof_acc[q]);
+  if (tid == 0) for (int q = 0; q < 12; q++) atomicAdd(&ctr->prof[q], prof_acc[q]);
 #endif
   if (tid == 0) {
     atomicAdd(&ctr->phase1, n_phase1); atomicAdd(&ctr->phase2, n_phase2);
@@ -666,16 +807,45 @@ struct DevBuf {
   template <typename T> T* as() { return static_cast<T*>(p); }
 };
 
+// What (A) hands to (B) for one batch of frames.  Two sets: (A) fills one while (B) reads the other.
+struct LinkInput {
+  DevBuf lrec, loff, lcnt, hdr, fdet, fdoff, fdcnt;
+  cudaEvent_t begin = nullptr, end = nullptr;  // of the linking pass that reads this set
+  bool linking = false;                        // a linking pass on this set has been launched and not yet collected
+  ~LinkInput() { if (begin) cudaEventDestroy(begin); if (end) cudaEventDestroy(end); }
+};
+
 struct ClsWork {
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  cudaStream_t link_stream = nullptr;    // (B) runs here, next to the enumeration of the following batch on the engine's stream
   double enumerate_ms = 0, link_ms = 0;  // of the call in progress
-  ~ClsWork() { for (cudaEvent_t v : ev) if (v) cudaEventDestroy(v); }
+  ~ClsWork() {
+    for (cudaEvent_t v : ev) if (v) cudaEventDestroy(v);
+    if (link_stream) cudaStreamDestroy(link_stream);
+  }
   cudaError_t events() {
     for (cudaEvent_t& v : ev)
       if (!v) { cudaError_t err = cudaEventCreate(&v); if (err != cudaSuccess) return err; }
+    for (LinkInput& in : in)
+      for (cudaEvent_t* v : {&in.begin, &in.end})
+        if (!*v) { cudaError_t err = cudaEventCreate(v); if (err != cudaSuccess) return err; }
+    if (!link_stream) { cudaError_t err = cudaStreamCreateWithFlags(&link_stream, cudaStreamNonBlocking); if (err != cudaSuccess) return err; }
     return cudaSuccess;
   }
-  DevBuf offs, dets, paths, assign, phase, state, ctr, front, txyz, terr, lrec, loff, lcnt, hdr, fdet, fdoff, fdcnt, seq;
+  // the linking pass on set k has finished (wait for it if need be): its time is added to link_ms, the set is free again
+  cudaError_t collect(int k) {
+    LinkInput& I = in[k];
+    if (!I.linking) return cudaSuccess;
+    I.linking = false;
+    cudaError_t err = cudaEventSynchronize(I.end);
+    if (err != cudaSuccess) return err;
+    float ms = 0;
+    if ((err = cudaEventElapsedTime(&ms, I.begin, I.end)) != cudaSuccess) return err;
+    link_ms += ms;
+    return cudaSuccess;
+  }
+  DevBuf offs, dets, paths, assign, phase, state, ctr, ctr_link, front, txyz, terr, seq;
+  LinkInput in[2];
   // tri_classify_begin / tri_classify_finish: the enumerated shard waiting for its linking pass
   bool pending = false;
   ClsParams job;
@@ -749,28 +919,30 @@ int cls_grid(const tri_engine* e, int frames) {
 }
 
 // (A) on frames [p.f0, p.f1) with the work buffers sized by (cap, leaf_cap); *h = the counters after the launch
-int cls_enumerate(tri_engine* e, ClsWork& W, ClsParams& p, int cap, long long leaf_cap, int64_t n_det_batch, ClsCounters* h) {
+int cls_enumerate(tri_engine* e, ClsWork& W, int k, ClsParams& p, int cap, long long leaf_cap, int64_t n_det_batch, ClsCounters* h) {
   cudaStream_t s = e->stream;
   const int frames = p.f1 - p.f0, grid = cls_grid(e, frames);
   TRI_CUDA(W.front.alloc(sizeof(u64) * 2 * (size_t)cap * grid));
   TRI_CUDA(W.txyz.alloc(sizeof(double) * 3 * (size_t)cap * grid));
   TRI_CUDA(W.terr.alloc(sizeof(double) * (size_t)cap * grid));
-  TRI_CUDA(W.lrec.alloc(sizeof(u64) * rec_words(p.W) * (size_t)leaf_cap));
-  TRI_CUDA(W.loff.alloc(sizeof(long long) * frames));
-  TRI_CUDA(W.lcnt.alloc(sizeof(int) * frames));
-  TRI_CUDA(W.hdr.alloc(sizeof(int) * HDR_INTS * (size_t)frames));
-  TRI_CUDA(W.fdet.alloc(sizeof(FrameDet) * (size_t)std::max<int64_t>(n_det_batch, 1)));
-  TRI_CUDA(W.fdoff.alloc(sizeof(long long) * frames));
-  TRI_CUDA(W.fdcnt.alloc(sizeof(int) * frames));
+  TRI_CUDA(W.events());
+  TRI_CUDA(W.collect(k));  // the linking pass that read this set before
+  LinkInput& I = W.in[k];
+  TRI_CUDA(I.lrec.alloc(sizeof(u64) * rec_words(p.W) * (size_t)leaf_cap));
+  TRI_CUDA(I.loff.alloc(sizeof(long long) * frames));
+  TRI_CUDA(I.lcnt.alloc(sizeof(int) * frames));
+  TRI_CUDA(I.hdr.alloc(sizeof(int) * HDR_INTS * (size_t)frames));
+  TRI_CUDA(I.fdet.alloc((size_t)FDET_BYTES * (size_t)std::max<int64_t>(n_det_batch, 1)));
+  TRI_CUDA(I.fdoff.alloc(sizeof(long long) * frames));
+  TRI_CUDA(I.fdcnt.alloc(sizeof(int) * frames));
   p.cap = cap; p.leaf_cap = leaf_cap;
   ClsCounters* ctr = W.ctr.as<ClsCounters>();
   TRI_CUDA(cudaMemsetAsync(&ctr->leaf_total, 0, 2 * sizeof(u64), s));  // leaf_total, fdet_total: offsets within this batch
-  TRI_CUDA(W.events());
   TRI_CUDA(cudaEventRecord(W.ev[0], s));
   enumerate_kernel<<<grid, CLS_THREADS, 0, s>>>(e->rig64, e->ray, p, W.offs.as<int32_t>(), W.dets.as<double>(), W.front.as<u64>(),
-                                                 W.txyz.as<double>(), W.terr.as<double>(), W.lrec.as<u64>(), W.loff.as<long long>(),
-                                                 W.lcnt.as<int>(), W.hdr.as<int>(), W.fdet.as<FrameDet>(), W.fdoff.as<long long>(),
-                                                 W.fdcnt.as<int>(), ctr);
+                                                 W.txyz.as<double>(), W.terr.as<double>(), I.lrec.as<u64>(), I.loff.as<long long>(),
+                                                 I.lcnt.as<int>(), I.hdr.as<int>(), I.fdet.as<unsigned char>(), I.fdoff.as<long long>(),
+                                                 I.fdcnt.as<int>(), ctr);
   e->launches++;
   TRI_CUDA(cudaGetLastError());
   TRI_CUDA(cudaEventRecord(W.ev[1], s));
@@ -782,27 +954,26 @@ int cls_enumerate(tri_engine* e, ClsWork& W, ClsParams& p, int cap, long long le
   return TRI_OK;
 }
 
-// (B) on the batch last enumerated: one warp per sequence (seq == nullptr: the single sequence [p.f0, p.f1))
-int cls_link(tri_engine* e, ClsWork& W, const ClsParams& p, int n_seq, const int2* d_seq, int first_seq, bool want_assign, bool want_phase) {
-  cudaStream_t s = e->stream;
+// (B) on the batch enumerated into set k: one CTA per sequence (seq == nullptr: the single sequence [p.f0, p.f1)), launched on the
+// link stream -- the caller goes on to enumerate the next batch into the other set; W.collect(k) waits for this pass.
+int cls_link(tri_engine* e, ClsWork& W, int k, const ClsParams& p, int n_seq, const int2* d_seq, int first_seq, bool want_assign, bool want_phase, int max_leaves) {
+  cudaStream_t s = W.link_stream;
+  LinkInput& I = W.in[k];
   auto go = [&](auto kern, int bytes) -> int {
     TRI_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
-    TRI_CUDA(W.events());
-    TRI_CUDA(cudaEventRecord(W.ev[1], s));
-    kern<<<n_seq, LINK_THREADS, bytes, s>>>(e->ray, p, d_seq, W.lrec.as<u64>(), W.loff.as<long long>(), W.lcnt.as<int>(), W.hdr.as<int>(),
-                                  W.fdet.as<FrameDet>(), W.fdoff.as<long long>(), W.fdcnt.as<int>(), W.state.as<LinkState>() + first_seq,
+    TRI_CUDA(cudaEventRecord(I.begin, s));
+    kern<<<n_seq, LINK_THREADS, bytes, s>>>(e->ray, p, d_seq, I.lrec.as<u64>(), I.loff.as<long long>(), I.lcnt.as<int>(), I.hdr.as<int>(),
+                                  I.fdet.as<unsigned char>(), I.fdoff.as<long long>(), I.fdcnt.as<int>(), W.state.as<LinkState>() + first_seq,
                                   W.paths.as<double>(), want_assign ? W.assign.as<int8_t>() : nullptr,
-                                  want_phase ? W.phase.as<uint8_t>() : nullptr, W.ctr.as<ClsCounters>());
+                                  want_phase ? W.phase.as<uint8_t>() : nullptr, W.ctr_link.as<ClsCounters>());
     e->launches++;
     TRI_CUDA(cudaGetLastError());
-    TRI_CUDA(cudaEventRecord(W.ev[2], s));
-    TRI_CUDA(cudaEventSynchronize(W.ev[2]));  // the next batch's enumeration reuses the buffers this pass reads
-    float ms = 0;
-    TRI_CUDA(cudaEventElapsedTime(&ms, W.ev[1], W.ev[2]));
-    W.link_ms += ms;
+    TRI_CUDA(cudaEventRecord(I.end, s));
+    I.linking = true;
     return TRI_OK;
   };
-  return p.W == 2 ? go(link_kernel<2>, LinkLayout<2>::BYTES) : go(link_kernel<4>, LinkLayout<4>::BYTES);
+  if (p.W == 2) return max_leaves <= LinkLayout<2>::MAX_LEAVES ? go(link_kernel<2, true>, LinkLayout<2>::BYTES) : go(link_kernel<2, false>, LinkLayout<2>::BYTES);
+  return max_leaves <= LinkLayout<4>::MAX_LEAVES ? go(link_kernel<4, true>, LinkLayout<4>::BYTES) : go(link_kernel<4, false>, LinkLayout<4>::BYTES);
 }
 
 int64_t dets_in_frames(const int32_t* det_offsets, int C, int n_frames, int f0, int f1) {
@@ -836,6 +1007,8 @@ int cls_run(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t
   if (!e->cls_work) { e->cls_work = new ClsWork(); e->cls_work_free = free_cls_work; }
   ClsWork& W = *static_cast<ClsWork*>(e->cls_work);
   W.pending = false;
+  TRI_CUDA(W.collect(0));  // (a linking pass left behind by a call that failed half-way)
+  TRI_CUDA(W.collect(1));
   W.enumerate_ms = W.link_ms = 0;
   const size_t n_offs = (size_t)C * (n_frames + 1);
   const size_t sz_paths = sizeof(double) * 3 * n_drones * (size_t)n_frames, sz_assign = (size_t)n_drones * n_frames * C,
@@ -848,8 +1021,10 @@ int cls_run(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t
   TRI_CUDA(W.phase.alloc(sz_phase));
   TRI_CUDA(W.state.alloc(sizeof(LinkState) * (size_t)std::max(n_seq, 1)));
   TRI_CUDA(W.ctr.alloc(sizeof(ClsCounters)));
+  TRI_CUDA(W.ctr_link.alloc(sizeof(ClsCounters)));
   TRI_CUDA(cudaMemcpyAsync(W.offs.p, det_offsets, sizeof(int32_t) * n_offs, cudaMemcpyHostToDevice, s));
   if (n_det) TRI_CUDA(cudaMemcpyAsync(W.dets.p, dets_xy, sizeof(double) * 2 * n_det, cudaMemcpyHostToDevice, s));
+  TRI_CUDA(cudaMemsetAsync(W.ctr_link.p, 0, sizeof(ClsCounters), s));
   TRI_CUDA(cudaMemsetAsync(W.paths.p, 0, sz_paths, s));
   TRI_CUDA(cudaMemsetAsync(W.assign.p, 0xff, sz_assign, s));
   TRI_CUDA(cudaMemsetAsync(W.phase.p, 0, sz_phase, s));
@@ -890,14 +1065,17 @@ int cls_run(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t
     return TRI_OK;
   }
 
-  // Work is cut into batches of frames: (A) enumerates a batch, (B) links it.  One sequence: 8192 frames per batch, the
-  // state carried from batch to batch.  Many sequences: whole sequences per batch (about 128 k frames), one CTA each.
+  // Work is cut into batches of frames: (A) enumerates a batch, (B) links it -- on its own stream, while (A) already works on the
+  // next batch into the other set of buffers (everything this stream has queued so far is complete by then: cls_enumerate ends
+  // with a synchronisation).  One sequence: 8192 frames per batch, the state carried from batch to batch.  Many sequences:
+  // whole sequences per batch (about 128 k frames), one CTA each.
   int batch = std::min(n_frames, 8192);
   int cap = 1 << 14;
   long long leaf_cap = 4ll << 20;
   ClsCounters h{};
   int max_frontier = 0;
   int q0 = 0;  // first sequence of the batch (multi)
+  int set = 0;  // the buffers this batch is enumerated into
   for (int f0 = 0; f0 < n_frames;) {
     int f1 = std::min(n_frames, f0 + batch), q1 = q0;
     if (multi) {
@@ -911,7 +1089,7 @@ int cls_run(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t
     ClsCounters before;
     TRI_CUDA(cudaMemcpyAsync(&before, W.ctr.p, sizeof(before), cudaMemcpyDeviceToHost, s));
     TRI_CUDA(cudaStreamSynchronize(s));
-    if ((st = cls_enumerate(e, W, p, cap, leaf_cap, dets_in_frames(det_offsets, C, n_frames, f0, f1), &h)) != TRI_OK) return st;
+    if ((st = cls_enumerate(e, W, set, p, cap, leaf_cap, dets_in_frames(det_offsets, C, n_frames, f0, f1), &h)) != TRI_OK) return st;
     if (h.bad_input) return fail(TRI_ERR_ARG, "malformed detection offsets");
     if (h.overflow_frontier || h.overflow_leaves) {
       // grow the work buffers (or shrink the batch) and redo this batch; the statistics of the aborted attempt are rolled back
@@ -923,20 +1101,27 @@ int cls_run(tri_engine* e, int mode, unsigned flags, int n_drones, const int32_t
       continue;
     }
     max_frontier = std::max(max_frontier, h.max_frontier);
-    if ((st = cls_link(e, W, p, multi ? q1 - q0 : 1, multi ? W.seq.as<int2>() + q0 : nullptr, multi ? q0 : 0, out_assign != nullptr, out_phase != nullptr)) != TRI_OK) return st;
+    if ((st = cls_link(e, W, set, p, multi ? q1 - q0 : 1, multi ? W.seq.as<int2>() + q0 : nullptr, multi ? q0 : 0, out_assign != nullptr, out_phase != nullptr, h.max_frontier)) != TRI_OK) return st;
+    set ^= 1;
     f0 = f1;
     q0 = q1;
   }
+  TRI_CUDA(W.collect(0));
+  TRI_CUDA(W.collect(1));
+  ClsCounters hl{};
   TRI_CUDA(cudaMemcpyAsync(out_paths, W.paths.p, sz_paths, cudaMemcpyDeviceToHost, s));
   if (out_assign) TRI_CUDA(cudaMemcpyAsync(out_assign, W.assign.p, sz_assign, cudaMemcpyDeviceToHost, s));
   if (out_phase) TRI_CUDA(cudaMemcpyAsync(out_phase, W.phase.p, sz_phase, cudaMemcpyDeviceToHost, s));
   TRI_CUDA(cudaMemcpyAsync(&h, W.ctr.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  TRI_CUDA(cudaMemcpyAsync(&hl, W.ctr_link.p, sizeof(hl), cudaMemcpyDeviceToHost, s));
   TRI_CUDA(cudaStreamSynchronize(s));
-  if (h.overflow_final) return fail(TRI_ERR_CAPACITY, "more than 128 disjoint combinations kept in one frame");
+  if (hl.overflow_final) return fail(TRI_ERR_CAPACITY, "more than 128 disjoint combinations kept in one frame");
+  h.phase1 = hl.phase1; h.phase2 = hl.phase2;
 #ifdef TRI_TUNING
+  for (int q = 0; q < 12; q++) h.prof[q] = hl.prof[q];
   if (getenv("TRI_CLS_PROFILE"))
-    fprintf(stderr, "link cycles: top %llu | wait %llu | gates %llu | phase1 %llu | phase2 %llu | classifyPaths %llu\n", h.prof[0], h.prof[1],
-            h.prof[2], h.prof[3], h.prof[4], h.prof[5]);
+    fprintf(stderr, "link cycles: barrier1 %llu | top %llu | wait %llu | gate %llu | scan %llu | barrier2 %llu | confirm %llu | emit %llu | phase2 %llu | classifyPaths %llu\n",
+            h.prof[9], h.prof[0], h.prof[1], h.prof[2], h.prof[3], h.prof[4], h.prof[8], h.prof[5], h.prof[6], h.prof[7]);
 #endif
   cls_stats(stats, h, max_frontier, W);
   return TRI_OK;
@@ -996,7 +1181,7 @@ extern "C" int tri_classify_begin(tri_engine* e, int mode, unsigned flags, int n
   for (;;) {  // the whole shard's candidates stay resident: on overflow grow the buffers and enumerate again
     TRI_CUDA(cudaMemsetAsync(W.ctr.p, 0, sizeof(ClsCounters), s));
     ClsCounters h{};
-    if ((st = cls_enumerate(e, W, p, cap, leaf_cap, n_det, &h)) != TRI_OK) return st;
+    if ((st = cls_enumerate(e, W, 0, p, cap, leaf_cap, n_det, &h)) != TRI_OK) return st;
     if (h.bad_input) return fail(TRI_ERR_ARG, "malformed detection offsets");
     if (h.overflow_frontier) { if (cap >= (1 << 22)) return fail(TRI_ERR_CAPACITY, "combination frontier exceeds 4M nodes in one frame"); cap *= 4; continue; }
     if (h.overflow_leaves) { if (leaf_cap >= (1ll << 30)) return fail(TRI_ERR_CAPACITY, "candidate list exceeds device buffer"); leaf_cap *= 4; continue; }
@@ -1030,21 +1215,27 @@ extern "C" int tri_classify_finish(tri_engine* e, const void* state_in, void* st
   TRI_CUDA(W.assign.alloc(sz_assign));
   TRI_CUDA(W.phase.alloc(sz_phase));
   TRI_CUDA(W.state.alloc(sizeof(LinkState)));
+  TRI_CUDA(W.ctr_link.alloc(sizeof(ClsCounters)));
+  TRI_CUDA(cudaMemsetAsync(W.ctr_link.p, 0, sizeof(ClsCounters), s));
   TRI_CUDA(cudaMemsetAsync(W.paths.p, 0, sz_paths, s));
   TRI_CUDA(cudaMemsetAsync(W.assign.p, 0xff, sz_assign, s));
   TRI_CUDA(cudaMemsetAsync(W.phase.p, 0, sz_phase, s));
   if (state_in) TRI_CUDA(cudaMemcpyAsync(W.state.p, state_in, sizeof(LinkState), cudaMemcpyHostToDevice, s));
   else TRI_CUDA(cudaMemsetAsync(W.state.p, 0, sizeof(LinkState), s));
-  int st = cls_link(e, W, p, 1, nullptr, 0, out_assign != nullptr, out_phase != nullptr);
+  TRI_CUDA(cudaStreamSynchronize(s));  // the linking pass runs on its own stream
+  int st = cls_link(e, W, 0, p, 1, nullptr, 0, out_assign != nullptr, out_phase != nullptr, W.job_max_frontier);
   if (st != TRI_OK) return st;
-  ClsCounters h{};
+  TRI_CUDA(W.collect(0));
+  ClsCounters h{}, hl{};
   TRI_CUDA(cudaMemcpyAsync(out_paths, W.paths.p, sz_paths, cudaMemcpyDeviceToHost, s));
   if (out_assign) TRI_CUDA(cudaMemcpyAsync(out_assign, W.assign.p, sz_assign, cudaMemcpyDeviceToHost, s));
   if (out_phase) TRI_CUDA(cudaMemcpyAsync(out_phase, W.phase.p, sz_phase, cudaMemcpyDeviceToHost, s));
   if (state_out) TRI_CUDA(cudaMemcpyAsync(state_out, W.state.p, sizeof(LinkState), cudaMemcpyDeviceToHost, s));
   TRI_CUDA(cudaMemcpyAsync(&h, W.ctr.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+  TRI_CUDA(cudaMemcpyAsync(&hl, W.ctr_link.p, sizeof(hl), cudaMemcpyDeviceToHost, s));
   TRI_CUDA(cudaStreamSynchronize(s));
-  if (h.overflow_final) return fail(TRI_ERR_CAPACITY, "more than 128 disjoint combinations kept in one frame");
+  if (hl.overflow_final) return fail(TRI_ERR_CAPACITY, "more than 128 disjoint combinations kept in one frame");
+  h.phase1 = hl.phase1; h.phase2 = hl.phase2;
   cls_stats(stats, h, W.job_max_frontier, W);
   return TRI_OK;
 }

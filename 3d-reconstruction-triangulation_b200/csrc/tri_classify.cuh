@@ -25,16 +25,18 @@ constexpr int MIN_CAMERAS = 2, PATH_TAIL = 3;
 //             bit of the last word is a poison bit: set on a leaf whose error is not < error_ (it can never be
 //             accepted, :209, :243) and in every "used" mask.
 //   xyz[3]    the triangulated point, comb = the 4-bit-per-camera combination word (for the assignment output)
-// W = 2 (<= 8 cameras, 48-byte records) or 4 (<= 16 cameras, 80-byte records: both strides are conflict-free for the
-// 16-byte shared-memory loads of a warp).
-__host__ __device__ constexpr int rec_words(int W) { return W == 2 ? 6 : 10; }
-constexpr int HDR_INTS = 40;   // per frame: [0 .. C+1] zstart[z] = leaves with fewer than z unused cameras; [20 .. 20+C] pref[c]
+// A frame's leaves are one block: the masks of all leaves ([L][W], dense: a warp tests 32 leaves with conflict-free 16-byte
+// shared-memory loads), then [L][4] = point, combination.  W = 2 (<= 8 cameras) or 4 (<= 16 cameras).
+__host__ __device__ constexpr int rec_words(int W) { return W + 4; }
+// per frame: [0 .. C+1] zstart[z] = leaves with fewer than z unused cameras (so [C+1] = all leaves); [20 .. 20+C] pref[c]
+// (so [20+C] = detections); [38..39] the frame's offset into the leaf array (a long long)
+constexpr int HDR_INTS = 40;
 constexpr int HDR_PREF = 20;
-struct __align__(16) FrameDet {  // a detection of the frame with its pixel ray (Triangulator.cpp:27-55); 80 B, a conflict-free stride
-  double dir[3], org[3];
-  float dirf[3], orgf[3];  // single-precision copies for the gate's fast path
-  int cam, slot;
-};
+constexpr int HDR_OFF = 38;
+// A frame's n detections with their pixel rays (Triangulator.cpp:27-55) are one block of n * FDET_BYTES bytes:
+// n x float4 {origin, dir.x}, n x float4 {dir.y, dir.z, camera (int bits), 0} -- single precision for the gate's fast path --,
+// n x 4 doubles {dir, 0}
+constexpr int FDET_BYTES = 64;
 constexpr int LINK_MAX_DETS = CLS_MAX_CAMS * TRI_MAX_DETS;  // 240
 
 struct ClsParams {
@@ -50,8 +52,10 @@ struct ClsParams {
 struct ClsCounters {
   u64 leaf_total, fdet_total, nodes, solves, leaves, lm_iters, phase1, phase2, ties;
   int max_frontier, overflow_frontier, overflow_leaves, overflow_final, bad_input;
-  u64 prof[8];  // tuning builds: clock cycles of the linking pass by section (wait, gates, phase 1, phase 2, classifyPaths)
+  u64 prof[12];  // tuning builds: clock cycles of the linking pass by section (wait, gates, phase 1, phase 2, classifyPaths)
 };
+// tuning builds: thread 0 times its own sections with clock64.  (BAR.SYNC defers blocking -- the warp only waits at its next
+// shared-memory access -- so a section that follows a block barrier also holds the wait for it.)
 #ifdef TRI_TUNING
 #define CLS_PROF(k) do { const long long now__ = clock64(); prof_acc[k] += (u64)(now__ - prof_t); prof_t = now__; } while (0)
 #else
