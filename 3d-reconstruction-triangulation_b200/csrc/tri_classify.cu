@@ -45,15 +45,23 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
   __shared__ double s_px[CLS_MAX_CAMS][TRI_MAX_DETS], s_py[CLS_MAX_CAMS][TRI_MAX_DETS];
   __shared__ int s_warp[CLS_THREADS / 32];
   __shared__ long long s_off;
+  extern __shared__ __align__(16) unsigned char enum_dyn[];  // the sort keys of a frame's leaves
+  u64* s_ka = reinterpret_cast<u64*>(enum_dyn);                   // error bits
+  unsigned* s_kb = reinterpret_cast<unsigned*>(s_ka + ENUM_SORT_CAP);  // (unused cameras, DFS index)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int C = p.n_cams;
+  __shared__ double s_P[CLS_MAX_CAMS][12];  // the projection matrices: every thread solves a different camera subset
+  for (int i = tid; i < C * 12; i += CLS_THREADS) s_P[i / 12][i % 12] = dlt.P[i / 12][i % 12];
   u64* buf0 = front + (size_t)blockIdx.x * 2 * p.cap;
   u64* buf1 = buf0 + p.cap;
   double* t_xyz = tmp_xyz + (size_t)blockIdx.x * 3 * p.cap;
   double* t_err = tmp_err + (size_t)blockIdx.x * p.cap;
   u64 st_nodes = 0, st_solves = 0, st_iters = 0;
 
-  for (int f = p.f0 + blockIdx.x; f < p.f1; f += gridDim.x) {
+  // Frames are handed out one at a time (their cost varies by orders of magnitude with the number of detections): the
+  // first round by block index, then from a shared counter.
+  __shared__ int s_frame;
+  for (int f = p.f0 + blockIdx.x; f < p.f1;) {
     __syncthreads();
     for (int i = tid; i < C * TRI_MAX_DETS; i += CLS_THREADS) {
       const int c = i / TRI_MAX_DETS, d = i % TRI_MAX_DETS;
@@ -115,7 +123,7 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
           if (cnt >= 2) st_solves++;  // the reference re-solves the "none" children too (:166-181)
           if (cnt >= 2 && (k > 0 || last)) {  // a "none" child repeats its parent's subset: same error
             int it;
-            err = solve_combination(dlt, ray, p.solver, comb, c + 1, s_px, s_py, X, it);
+            err = solve_combination(s_P, ray, p.solver, comb, c + 1, s_px, s_py, X, it);
             st_iters += it;
             if (err > p.error_) keep = false;  // :185-187
           }
@@ -157,28 +165,15 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
         __syncthreads();
         const long long off = s_off;
         if (off >= 0) {
-          // ... in PRIORITY order: rank of leaf i = number of leaves the reference's priority_queue pops
-          // before it = those with fewer unused cameras, then smaller error (Combination::operator<,
-          // :12-20), ties by DFS order.  Rank by counting (m is ~1e3; frames are independent, so this is
-          // parallel work) and scatter; the sequential linking kernel then only walks prefixes.
+          // ... in PRIORITY order: the order in which the reference's priority_queue pops them = fewer unused cameras first,
+          // then smaller error (Combination::operator<, :12-20), ties by DFS order.  The errors are >= +0, so their bit
+          // patterns order like the values: the leaves are sorted by (unused cameras, error bits, DFS index) with a bitonic
+          // network in shared memory (round 1 ranked by counting, O(m^2): three quarters of this kernel's time); only a
+          // frame with more than ENUM_SORT_CAP leaves still ranks by counting.
           const u64 cam_bits = C == 16 ? ~0ull : ((1ull << (4 * C)) - 1);
           const int RW = rec_words(p.W);
           u64 n_tie = 0;
-          for (int i = tid; i < m; i += CLS_THREADS) {
-            const u64 ci = fin[i];
-            const double ei = t_err[i];
-            const int zi = C - __popcll(nonzero_nibbles(ci & cam_bits));
-            int rank = 0;
-            bool tie = false;
-            for (int j = 0; j < m; j++) {
-              const int zj = C - __popcll(nonzero_nibbles(fin[j] & cam_bits));
-              const double ej = t_err[j];
-              const bool eq = zj == zi && ej == ei;
-              rank += (zj < zi) || (zj == zi && ej < ei) || (eq && j < i);
-              tie = tie || (eq && j != i);
-            }
-            n_tie += tie;
-            atomicAdd(&s_hist[zi + 1], 1);
+          auto publish = [&](int i, int rank, u64 ci, double ei) {  // leaf i is the rank-th to be popped
             // the frame's block: m masks of W words, then m x (point, combination)
             u64* mrow = leaf_rec + (size_t)off * RW + (size_t)rank * p.W;
             u64* prow = leaf_rec + (size_t)off * RW + (size_t)m * p.W + (size_t)rank * 4;
@@ -193,6 +188,59 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
             prow[1] = (u64)__double_as_longlong(t_xyz[3 * i + 1]);
             prow[2] = (u64)__double_as_longlong(t_xyz[3 * i + 2]);
             prow[3] = ci;
+          };
+          if (m <= ENUM_SORT_CAP) {
+            int n = 2;
+            while (n < m) n <<= 1;
+            for (int i = tid; i < n; i += CLS_THREADS) {
+              if (i < m) {
+                const int zi = C - __popcll(nonzero_nibbles(fin[i] & cam_bits));
+                s_ka[i] = (u64)__double_as_longlong(t_err[i]);
+                s_kb[i] = ((unsigned)zi << ENUM_IDX_BITS) | (unsigned)i;
+                atomicAdd(&s_hist[zi + 1], 1);
+              } else {
+                s_ka[i] = ~0ull; s_kb[i] = ~0u;  // padding sorts last
+              }
+            }
+            __syncthreads();
+            for (int k = 2; k <= n; k <<= 1)
+              for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int t = tid; t < (n >> 1); t += CLS_THREADS) {
+                  const int lo = 2 * t - (t & (j - 1)), hi = lo + j;  // the t-th pair of this step
+                  const u64 a = s_ka[lo], b = s_ka[hi];
+                  const unsigned ab = s_kb[lo], bb = s_kb[hi];
+                  const unsigned za = ab >> ENUM_IDX_BITS, zb = bb >> ENUM_IDX_BITS;
+                  const bool a_after_b = za != zb ? za > zb : (a != b ? a > b : ab > bb);
+                  if (a_after_b == ((lo & k) == 0)) { s_ka[lo] = b; s_ka[hi] = a; s_kb[lo] = bb; s_kb[hi] = ab; }
+                }
+                __syncthreads();
+              }
+            for (int r = tid; r < m; r += CLS_THREADS) {
+              const u64 a = s_ka[r];
+              const unsigned ab = s_kb[r], z = ab >> ENUM_IDX_BITS;
+              const int i = (int)(ab & ((1u << ENUM_IDX_BITS) - 1));
+              n_tie += (r > 0 && s_ka[r - 1] == a && (s_kb[r - 1] >> ENUM_IDX_BITS) == z) ||
+                       (r + 1 < m && s_ka[r + 1] == a && (s_kb[r + 1] >> ENUM_IDX_BITS) == z);
+              publish(i, r, fin[i], __longlong_as_double((long long)a));
+            }
+          } else {
+            for (int i = tid; i < m; i += CLS_THREADS) {
+              const u64 ci = fin[i];
+              const double ei = t_err[i];
+              const int zi = C - __popcll(nonzero_nibbles(ci & cam_bits));
+              int rank = 0;
+              bool tie = false;
+              for (int j = 0; j < m; j++) {
+                const int zj = C - __popcll(nonzero_nibbles(fin[j] & cam_bits));
+                const double ej = t_err[j];
+                const bool eq = zj == zi && ej == ei;
+                rank += (zj < zi) || (zj == zi && ej < ei) || (eq && j < i);
+                tie = tie || (eq && j != i);
+              }
+              n_tie += tie;
+              atomicAdd(&s_hist[zi + 1], 1);
+              publish(i, rank, ci, ei);
+            }
           }
           if (n_tie) atomicAdd(&ctr->ties, n_tie);
           __syncthreads();
@@ -215,6 +263,9 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
       for (int z = 0; z <= C + 1; z++) hdr[(size_t)(f - p.f0) * HDR_INTS + z] = 0;
       for (int c = 0; c <= C; c++) hdr[(size_t)(f - p.f0) * HDR_INTS + HDR_PREF + c] = s_pref[c];
     }
+    if (tid == 0) s_frame = p.f0 + (int)gridDim.x + (int)atomicAdd(&ctr->next_frame, 1ull);
+    __syncthreads();
+    f = s_frame;
   }
   // block totals of the per-thread statistics
   for (int o = 16; o > 0; o >>= 1) {
@@ -911,7 +962,8 @@ int cls_grid(const tri_engine* e, int frames) {
   // lanes on narrow levels), so occupancy is what hides it -- 4 CTAs per SM instead of 2: S09_D6 with the
   // exact LM 3.88 -> 2.82 s (profiles/r1_cls_grid_sweep.log)
   int per_sm = 2;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, enumerate_kernel, CLS_THREADS, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
+  if (cudaFuncSetAttribute(enumerate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ENUM_SMEM_BYTES) != cudaSuccess ||
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, enumerate_kernel, CLS_THREADS, ENUM_SMEM_BYTES) != cudaSuccess || per_sm < 1) per_sm = 2;
 #ifdef TRI_TUNING
   if (const char* v = getenv("TRI_CLS_CTAS_PER_SM")) per_sm = std::max(1, atoi(v));
 #endif
@@ -937,9 +989,9 @@ int cls_enumerate(tri_engine* e, ClsWork& W, int k, ClsParams& p, int cap, long 
   TRI_CUDA(I.fdcnt.alloc(sizeof(int) * frames));
   p.cap = cap; p.leaf_cap = leaf_cap;
   ClsCounters* ctr = W.ctr.as<ClsCounters>();
-  TRI_CUDA(cudaMemsetAsync(&ctr->leaf_total, 0, 2 * sizeof(u64), s));  // leaf_total, fdet_total: offsets within this batch
+  TRI_CUDA(cudaMemsetAsync(&ctr->leaf_total, 0, 3 * sizeof(u64), s));  // leaf_total, fdet_total, next_frame: within this batch
   TRI_CUDA(cudaEventRecord(W.ev[0], s));
-  enumerate_kernel<<<grid, CLS_THREADS, 0, s>>>(e->rig64, e->ray, p, W.offs.as<int32_t>(), W.dets.as<double>(), W.front.as<u64>(),
+  enumerate_kernel<<<grid, CLS_THREADS, ENUM_SMEM_BYTES, s>>>(e->rig64, e->ray, p, W.offs.as<int32_t>(), W.dets.as<double>(), W.front.as<u64>(),
                                                  W.txyz.as<double>(), W.terr.as<double>(), I.lrec.as<u64>(), I.loff.as<long long>(),
                                                  I.lcnt.as<int>(), I.hdr.as<int>(), I.fdet.as<unsigned char>(), I.fdoff.as<long long>(),
                                                  I.fdcnt.as<int>(), ctr);

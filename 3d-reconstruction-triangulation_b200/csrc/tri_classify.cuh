@@ -10,6 +10,9 @@ namespace tri {
 
 constexpr int CLS_MAX_CAMS = 16;   // 4 bits per camera in a 64-bit combination
 constexpr int CLS_THREADS = 128;
+constexpr int ENUM_SORT_CAP = 4096;   // leaves of one frame sorted in shared memory (12 bytes each); longer lists are ranked by counting
+constexpr int ENUM_IDX_BITS = 12;
+constexpr int ENUM_SMEM_BYTES = ENUM_SORT_CAP * 12;
 constexpr int LINK_MAX_FINAL = 128;  // combinations pickBestCombinations can keep in one frame: <= 15 * C / 2 = 120 disjoint ones
 typedef unsigned long long u64;
 
@@ -50,7 +53,7 @@ struct ClsParams {
 };
 
 struct ClsCounters {
-  u64 leaf_total, fdet_total, nodes, solves, leaves, lm_iters, phase1, phase2, ties;
+  u64 leaf_total, fdet_total, next_frame, nodes, solves, leaves, lm_iters, phase1, phase2, ties;
   int max_frontier, overflow_frontier, overflow_leaves, overflow_final, bad_input;
   u64 prof[12];  // tuning builds: clock cycles of the linking pass by section (wait, gates, phase 1, phase 2, classifyPaths)
 };
@@ -98,7 +101,8 @@ __device__ inline double solve_rays(const RayRig& ray, int solver, const ref::Ra
   return e;
 }
 
-__device__ inline double solve_combination(const DltRig<double>& dlt, const RayRig& ray, int solver, u64 comb, int n_cams,
+template <typename Rows>
+__device__ inline double solve_combination(const Rows& dlt_P, const RayRig& ray, int solver, u64 comb, int n_cams,
                                            const double (*px)[TRI_MAX_DETS], const double (*py)[TRI_MAX_DETS], double X[3],
                                            int& iters) {
   iters = 0;
@@ -109,7 +113,7 @@ __device__ inline double solve_combination(const DltRig<double>& dlt, const RayR
       const int k = (int)((comb >> (4 * i)) & 15);
       if (k) { cam[n] = i; x[n] = px[i][k - 1]; y[n] = py[i][k - 1]; n++; }
     }
-    return ref::dlt_point(dlt, n, cam, x, y, X);
+    return ref::dlt_point_rows(dlt_P, n, cam, x, y, X);
   }
   ref::RaySet rs;
   rs.n = 0;

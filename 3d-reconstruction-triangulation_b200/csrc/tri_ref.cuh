@@ -288,11 +288,13 @@ __device__ inline double lm_point(const RayRig& rig, const RaySet& rs, double X[
 
 // MatrixTriangulator::triangulatePoint (MatrixTriangulator.cpp:3-62) for an arbitrary camera subset:
 // normal equations + adjugate, error from the residual rows themselves.
-__device__ inline double dlt_point(const DltRig<double>& rig, int n, const int* cam, const double* px, const double* py,
-                                   double X[3]) {
+// (Pm[c] = camera c's 3x4 matrix, row-major: the rig's own copy in the constant bank, or a shared-memory copy where every
+// thread indexes a different camera -- divergent constant-bank reads are serialised)
+template <typename Rows>
+__device__ inline double dlt_point_rows(const Rows& Pm, int n, const int* cam, const double* px, const double* py, double X[3]) {
   double M[6] = {0, 0, 0, 0, 0, 0}, v[3] = {0, 0, 0};
   for (int i = 0; i < n; i++) {
-    const double* P = rig.P[cam[i]];
+    const double* P = Pm[cam[i]];
     const double x = px[i], y = py[i];
     double a0 = P[0] - x * P[8], a1 = P[1] - x * P[9], a2 = P[2] - x * P[10], b = x * P[11] - P[3];
     M[0] += a0 * a0; M[1] += a0 * a1; M[2] += a0 * a2; M[3] += a1 * a1; M[4] += a1 * a2; M[5] += a2 * a2;
@@ -304,7 +306,7 @@ __device__ inline double dlt_point(const DltRig<double>& rig, int n, const int* 
   solve_sym3<double>(M, v, X);
   double ss = 0;
   for (int i = 0; i < n; i++) {
-    const double* P = rig.P[cam[i]];
+    const double* P = Pm[cam[i]];
     const double x = px[i], y = py[i];
     const double e0 = ((P[0] - x * P[8]) * X[0] + (P[1] - x * P[9]) * X[1] + (P[2] - x * P[10]) * X[2]) - (x * P[11] - P[3]);
     const double e1 = ((P[4] - y * P[8]) * X[0] + (P[5] - y * P[9]) * X[1] + (P[6] - y * P[10]) * X[2]) - (y * P[11] - P[7]);
@@ -312,6 +314,9 @@ __device__ inline double dlt_point(const DltRig<double>& rig, int n, const int* 
     ss += e1 * e1;
   }
   return sqrt(ss / (2 * n));
+}
+__device__ inline double dlt_point(const DltRig<double>& rig, int n, const int* cam, const double* px, const double* py, double X[3]) {
+  return dlt_point_rows(rig.P, n, cam, px, py, X);
 }
 
 }  // namespace ref

@@ -1,0 +1,5 @@
+#!/bin/bash
+set -x
+cd "$GRAFT_REPO_ROOT"
+timeout 900 python -m pytest tests/test_gpu_classify.py -m gpu -x -q 2>&1 | tail -3
+timeout 600 python tools/link_iter.py --frames 100000 2>&1 | awk '!seen[substr($0,1,30)]++'
