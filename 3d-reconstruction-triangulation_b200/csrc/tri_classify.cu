@@ -277,12 +277,12 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
 }
 
 // ---- (B) linking -------------------------------------------------------------------------------
-// One CTA of sixteen warps per sequence; two block barriers per frame, a third when the frame has a phase 2.  Everything
-// that does not depend on the tracking state was prepared by (A): the leaves in priority order -- their detection masks
-// as one dense array, points + combination words as another --, the number of leaves per count of unused cameras, the
-// frame's detections with their pixel rays.  A frame's leaves, detections and header arrive in shared memory as three
-// bulk async copies (cp.async.bulk -> UBLKCP) that complete on an mbarrier, issued one frame ahead into the other buffer
-// by the last warp (which also reads the frame table two frames ahead, off every other warp's path).  Per frame:
+// One CTA of sixteen warps per sequence; two block barriers per frame, plus one per kept combination when the frame has a
+// phase 2.  Everything that does not depend on the tracking state was prepared by (A): the leaves in priority order -- their
+// detection masks as one dense array, points + combination words as another --, the number of leaves per count of unused
+// cameras, the frame's detections with their pixel rays.  A frame's leaves, detections and header arrive in shared memory
+// as three bulk async copies (cp.async.bulk -> UBLKCP) that complete on an mbarrier, issued one frame ahead into the other
+// buffer by the last warp (which also reads the frame table two frames ahead, off every other warp's path).  Per frame:
 //   speculative phase 1, all tracked paths at once, LINK_WARPS / paths warps per path:
 //     gate    the MAX_STEP ray gate (:228-236) with lane <-> detection: the ballot of one 32-detection test IS a slice
 //             of the path's gate mask.  The distance runs in single precision first and in the reference's
@@ -292,17 +292,21 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
 //             path's last point (:241-246), ignoring earlier paths' picks; it starts at the first leaf with at least
 //             as many unused cameras as the gate leaves empty; a warp tests 128 leaves per step, the warps of a path
 //             take the 128-leaf blocks in turn and keep the smallest hit with a shared-memory atomicMin.
-//   confirmation, every warp for itself (lane <-> path): if the picks' masks are pairwise disjoint -- one OR-reduction
-//     against one sum of popcounts -- every pick is also the first of the list filtered by the earlier paths' picks
-//     (:119-135).  Otherwise (404 of 14 738 picks on S09_D6) warp 0 walks the paths in order, scans the colliding ones
-//     again with the used mask and publishes the result.
-//   phase 2, pickBestCombinations (:200-217): every warp filters its 128-leaf blocks against the used mask into a
-//     survivor bitmap; warp 0 compacts the survivors (usually a few dozen of ~750 leaves) and runs the reference's pop
-//     loop over them 32 at a time with a running used mask.
+//   confirmation, every warp for itself (lane <-> path; the same registers in every warp, so nothing is handed over): if
+//     the picks' masks are pairwise disjoint -- one OR-reduction against one sum of popcounts -- every pick is also the
+//     first of the list filtered by the earlier paths' picks (:119-135).  Otherwise (404 of 14 738 picks on S09_D6)
+//     warp 0 walks the paths in order, scans the colliding ones again with the used mask and publishes the result.
+//   phase 2, pickBestCombinations (:200-217), the reference's pop loop in parallel: every warp keeps the masks of its
+//     128-leaf blocks in registers; a round finds the first leaf of the whole list that misses the used mask (REDUX.MIN
+//     in the warp, atomicMin across the warps, one block barrier), adds its mask to the used mask and strikes the leaves
+//     it collides with.
 //   classifyPaths (:262-332) on warp 0, lane <-> kept combination: tail distances, nearest open path, then the ordered
 //     assignment by warp-wide minimum extraction (three REDUX operations per step).
-// Round 1 ran this with ~15 block barriers per frame, the pixel rays and the whole phase-2 filter inside the sequential
-// kernel (29 ms for S09_D6's 3000 frames, profiles/r1_link_kernel_lines.txt); the history since is in profiles/r2_link_kernel.log.
+// The kernel is one latency-bound CTA per sequence: what a frame costs is the length of its chain of dependent
+// instructions (a lone warp issues one every 6-10 cycles here: LDS 30, VOTE 28, SHFL 33, REDUX 50 cycles, tools/micro/redux.cu;
+// instruction fetch is not the limit, tools/micro/ifetch.cu).  Round 1 ran it with ~15 block barriers per frame, the pixel rays
+// and the whole phase-2 filter inside (29 ms for S09_D6's 3000 frames); the steps since, and the variants that lost, are in
+// profiles/r2_link_kernel.log.
 __device__ __forceinline__ uint32_t cls_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cls_mbar_init(u64* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cls_smem_u32(bar)), "r"(count));
