@@ -34,7 +34,7 @@
 namespace tri {
 
 // ---- (A) candidate generation ------------------------------------------------------------------
-__global__ void __launch_bounds__(CLS_THREADS)
+__global__ void __launch_bounds__(CLS_THREADS, TRI_ENUM_MIN_CTAS)
 enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_constant__ RayRig ray, ClsParams p,
                  const int32_t* __restrict__ offs, const double* __restrict__ dets, u64* __restrict__ front,
                  double* __restrict__ tmp_xyz, double* __restrict__ tmp_err, u64* __restrict__ leaf_rec,

@@ -10,7 +10,13 @@ namespace tri {
 
 constexpr int CLS_MAX_CAMS = 16;   // 4 bits per camera in a 64-bit combination
 constexpr int CLS_THREADS = 128;
-constexpr int ENUM_SORT_CAP = 4096;   // leaves of one frame sorted in shared memory (12 bytes each); longer lists are ranked by counting
+#ifndef TRI_ENUM_SORT_CAP
+#define TRI_ENUM_SORT_CAP 4096
+#endif
+#ifndef TRI_ENUM_MIN_CTAS
+#define TRI_ENUM_MIN_CTAS 4
+#endif
+constexpr int ENUM_SORT_CAP = TRI_ENUM_SORT_CAP;   // leaves of one frame sorted in shared memory (12 bytes each); longer lists are ranked by counting
 constexpr int ENUM_IDX_BITS = 12;
 constexpr int ENUM_SMEM_BYTES = ENUM_SORT_CAP * 12;
 constexpr int LINK_MAX_FINAL = 128;  // combinations pickBestCombinations can keep in one frame: <= 15 * C / 2 = 120 disjoint ones
@@ -107,13 +113,36 @@ __device__ inline double solve_combination(const Rows& dlt_P, const RayRig& ray,
                                            int& iters) {
   iters = 0;
   if (solver == 0) {
-    int cam[CLS_MAX_CAMS], n = 0;
-    double x[CLS_MAX_CAMS], y[CLS_MAX_CAMS];
+    // ref::dlt_point_rows on the combination's detections, camera by camera: the same operations in the same order, without
+    // the compacted (camera, x, y) arrays -- indexed at run time they would live in local memory
+    double M[6] = {0, 0, 0, 0, 0, 0}, v[3] = {0, 0, 0};
+    int n = 0;
     for (int i = 0; i < n_cams; i++) {
       const int k = (int)((comb >> (4 * i)) & 15);
-      if (k) { cam[n] = i; x[n] = px[i][k - 1]; y[n] = py[i][k - 1]; n++; }
+      if (!k) continue;
+      n++;
+      const double* P = dlt_P[i];
+      const double x = px[i][k - 1], y = py[i][k - 1];
+      double a0 = P[0] - x * P[8], a1 = P[1] - x * P[9], a2 = P[2] - x * P[10], b = x * P[11] - P[3];
+      M[0] += a0 * a0; M[1] += a0 * a1; M[2] += a0 * a2; M[3] += a1 * a1; M[4] += a1 * a2; M[5] += a2 * a2;
+      v[0] += a0 * b; v[1] += a1 * b; v[2] += a2 * b;
+      a0 = P[4] - y * P[8]; a1 = P[5] - y * P[9]; a2 = P[6] - y * P[10]; b = y * P[11] - P[7];
+      M[0] += a0 * a0; M[1] += a0 * a1; M[2] += a0 * a2; M[3] += a1 * a1; M[4] += a1 * a2; M[5] += a2 * a2;
+      v[0] += a0 * b; v[1] += a1 * b; v[2] += a2 * b;
     }
-    return ref::dlt_point_rows(dlt_P, n, cam, x, y, X);
+    solve_sym3<double>(M, v, X);
+    double ss = 0;
+    for (int i = 0; i < n_cams; i++) {
+      const int k = (int)((comb >> (4 * i)) & 15);
+      if (!k) continue;
+      const double* P = dlt_P[i];
+      const double x = px[i][k - 1], y = py[i][k - 1];
+      const double e0 = ((P[0] - x * P[8]) * X[0] + (P[1] - x * P[9]) * X[1] + (P[2] - x * P[10]) * X[2]) - (x * P[11] - P[3]);
+      const double e1 = ((P[4] - y * P[8]) * X[0] + (P[5] - y * P[9]) * X[1] + (P[6] - y * P[10]) * X[2]) - (y * P[11] - P[7]);
+      ss += e0 * e0;
+      ss += e1 * e1;
+    }
+    return sqrt(ss / (2 * n));
   }
   ref::RaySet rs;
   rs.n = 0;

@@ -430,7 +430,9 @@ def main():
             cdt = time.perf_counter() - t0
             res["config3_classifier"] = {"dataset": "S09_D6", "mode": "matrix", "n_drones": 6, "frames": c_nf, "seconds": cdt,
                                          "frames_per_s": c_nf / cdt, "candidate_solves": cr["stats"]["solves"],
-                                         "points": int(cr["stats"]["phase1"] + cr["stats"]["phase2"])}
+                                         "points": int(cr["stats"]["phase1"] + cr["stats"]["phase2"]),
+                                         "enumerate_ms": cr["stats"]["enumerate_us"] / 1e3, "link_ms": cr["stats"]["link_us"] / 1e3,
+                                         "link_us_per_frame": cr["stats"]["link_us"] / c_nf}
         except Exception as exc:  # noqa: BLE001
             res["config3_classifier"] = {"error": repr(exc)}
 
