@@ -356,9 +356,12 @@ struct LinkLayout {
   static constexpr int BYTES = 2 * BUF_BYTES + 16;  // + the two mbarriers
 };
 
-constexpr int LINK_WARPS = 16;
+#ifndef TRI_LINK_WARPS
+#define TRI_LINK_WARPS 16
+#endif
+constexpr int LINK_WARPS = TRI_LINK_WARPS;  // >= TRI_MAX_DRONES
 constexpr int LINK_THREADS = 32 * LINK_WARPS;
-constexpr int LINK_BLOCKS = 32;  // phase 2 holds the first 32 x 128 leaves of a frame in registers, two blocks per warp (the rest is walked in place)
+constexpr int LINK_BLOCKS = 2 * LINK_WARPS;  // phase 2 holds the first LINK_BLOCKS x 128 leaves of a frame in registers, two blocks per warp (the rest is walked in place)
 constexpr int LINK_NONE = 0x7fffffff;
 
 // ALL_STAGED: no frame of the batch has more than MAX_LEAVES leaves (the host knows the longest list), so the body that reads

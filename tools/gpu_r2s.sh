@@ -1,0 +1,10 @@
+#!/bin/bash
+# round 2, GPU call S (2 GPUs): the GPU tests that need two devices, the bench under torchrun at N = 2
+set -x
+cd "$GRAFT_REPO_ROOT"
+nvidia-smi -L
+timeout 600 python -c "import __graft_entry__ as g; g.smoke(); print(\"smoke ok\")" 2>&1 | tail -3
+timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/r2s_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2s_pytest.log
+tail -4 gpurun_out/r2s_pytest.log
+timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r2s_bench_n2.json 2> gpurun_out/r2s_bench_n2.err; echo "bench rc=$?"
+tail -c 3000 gpurun_out/r2s_bench_n2.json; tail -3 gpurun_out/r2s_bench_n2.err
