@@ -18,8 +18,11 @@
 // The search is exact; what is bounded is its budget: a search that visits more than LAZY_NODE_BUDGET nodes
 // latches TRI_ERR_CAPACITY instead of returning something else than the reference's answer.
 //
-// One warp per sequence.  Warp-uniform control flow; the lanes evaluate the children of a node in parallel
-// (lane k <-> detection k of the node's camera), each from the parent's accumulated normal equations.
+// One CTA of LZ_WARPS warps per sequence.  Phase 1 is speculative as in tri_classify.cu: every tracked path's search runs on
+// its own warp inside the path's own ray gate, ignoring the other paths' picks; warp 0 then confirms the picks in path order
+// and searches a colliding path again with the used detections taken out.  Inside a search the control flow is warp-uniform
+// and the lanes evaluate the children of a node in parallel (lane k <-> detection k of the node's camera), each from the
+// parent's accumulated normal equations.
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -35,17 +38,19 @@ constexpr int LZ_CAMS = TRI_MAX_CAMS;          // 32
 constexpr int LZ_SLOTS = TRI_MAX_DETS + 1;     // children of a node: "none" + up to 15 detections
 constexpr long long LAZY_NODE_BUDGET = 1 << 20;  // nodes one best-leaf search may visit
 
-struct LzShared {
-  // the frame
+constexpr int LZ_WARPS = 6;  // paths searched at once in phase 1
+
+// the frame: detections and their pixel rays (read by every warp)
+struct LzFrame {
   int n[LZ_CAMS];
   double px[LZ_CAMS][TRI_MAX_DETS], py[LZ_CAMS][TRI_MAX_DETS];
   double dir[LZ_CAMS][TRI_MAX_DETS][3];
-  unsigned short all[LZ_CAMS];      // bit d: detection d exists
-  unsigned short used[LZ_CAMS];     // detections of the combinations accepted so far in this frame
-  unsigned short allowed[LZ_CAMS];  // detections the running search may take
-  unsigned short gate[TRI_MAX_DRONES][LZ_CAMS];
+};
+// one best-leaf search (one per warp)
+struct LzSearch {
+  unsigned short allowed[LZ_CAMS];  // detections the search may take
   int potential[LZ_CAMS + 1];       // cameras >= l with an allowed detection
-  // the search: state of the node at level l (cameras 0 .. l-1 decided)
+  // state of the node at level l (cameras 0 .. l-1 decided)
   double M[LZ_CAMS + 1][6], v[LZ_CAMS + 1][3], X[LZ_CAMS + 1][3], err[LZ_CAMS + 1];
   int count[LZ_CAMS + 1];
   double row[LZ_CAMS][8];           // the two rows (a0 a1 a2 b) of the k-th selected detection, selection order
@@ -57,8 +62,21 @@ struct LzShared {
   int best_count;
   double best_err, best_X[3];
   unsigned char best_choice[LZ_CAMS];
+};
+// the linking state of the frame (warp 0, and the hand-over from the speculative searches)
+struct LzLink {
+  unsigned short all[LZ_CAMS];      // bit d: detection d exists
+  unsigned short used[LZ_CAMS];     // detections of the combinations accepted so far in this frame
+  unsigned short gate[TRI_MAX_DRONES][LZ_CAMS];
+  // phase 1, speculative: each tracked path's best leaf inside its gate, the other paths' picks ignored
+  int spec_count[TRI_MAX_DRONES];
+  double spec_X[TRI_MAX_DRONES][3];
+  unsigned char spec_choice[TRI_MAX_DRONES][LZ_CAMS];
+  int abort;                        // a search ran out of its node budget
+  unsigned processed;               // phase 1's confirmed paths
+  int incumbent;                    // phase 2: the best count any warp of the shared search has found
+  int more;                         // phase 2: another combination was kept
   // classifyPaths
-  int fin_n;
   double fin_X[LINK_MAX_FINAL][3];
   unsigned char fin_choice[LINK_MAX_FINAL][LZ_CAMS];
   double pdist[LINK_MAX_FINAL][TRI_MAX_DRONES];
@@ -66,12 +84,14 @@ struct LzShared {
   double cp_err[LINK_MAX_FINAL];
   LinkState S;
 };
+constexpr size_t LZ_SMEM_BYTES = sizeof(LzFrame) + sizeof(LzLink) + LZ_WARPS * sizeof(LzSearch);
 
 // The best leaf (fewest unused cameras, then smallest error, then DFS order) whose detections lie in sh.allowed, whose error
 // is < error_ and -- if `near` -- whose point is within MAX_STEP of near[0..2].  Result in sh.best_* (best_count = 0: none).
 // Returns false if the node budget ran out.
-__device__ bool lazy_best_leaf(const DltRig<double>& dlt, const RayRig& ray, const ClsParams& p, LzShared& sh, const double* near,
-                               unsigned long long& nodes, unsigned long long& solves, unsigned long long& lm_iters) {
+__device__ bool lazy_best_leaf(const DltRig<double>& dlt, const RayRig& ray, const ClsParams& p, const LzFrame& fr, LzSearch& sh, const double* near,
+                               unsigned long long& nodes, unsigned long long& solves, unsigned long long& lm_iters, int part = 0, int nparts = 1,
+                               int* incumbent = nullptr) {
   const int lane = threadIdx.x & 31, C = p.n_cams;
   if (lane == 0) {
     int run = 0;
@@ -94,8 +114,8 @@ __device__ bool lazy_best_leaf(const DltRig<double>& dlt, const RayRig& ray, con
       if (++visited > LAZY_NODE_BUDGET) return false;
       const int cnt = sh.count[l];
       unsigned ok_bit = 0;
-      if (lane >= 1 && lane <= sh.n[l] && (sh.allowed[l] >> (lane - 1) & 1)) {
-        const double x = sh.px[l][lane - 1], y = sh.py[l][lane - 1];
+      if (lane >= 1 && lane <= fr.n[l] && (sh.allowed[l] >> (lane - 1) & 1)) {
+        const double x = fr.px[l][lane - 1], y = fr.py[l][lane - 1];
         double X[3] = {0, 0, 0}, e = 0;
         bool keep = true;
         if (p.solver == 0) {
@@ -135,10 +155,10 @@ __device__ bool lazy_best_leaf(const DltRig<double>& dlt, const RayRig& ray, con
           rs.n = cnt + 1;
           for (int i = 0; i < cnt; i++) {
             rs.cam[i] = sh.sel_cam[i];
-            for (int j = 0; j < 3; j++) rs.d[i][j] = sh.dir[sh.sel_cam[i]][sh.sel_det[i]][j];
+            for (int j = 0; j < 3; j++) rs.d[i][j] = fr.dir[sh.sel_cam[i]][sh.sel_det[i]][j];
           }
           rs.cam[cnt] = l;
-          for (int j = 0; j < 3; j++) rs.d[cnt][j] = sh.dir[l][lane - 1][j];
+          for (int j = 0; j < 3; j++) rs.d[cnt][j] = fr.dir[l][lane - 1][j];
           int it = 0;
           e = solve_rays(ray, p.solver, rs, X, it);
           lm_iters += it;
@@ -152,6 +172,18 @@ __device__ bool lazy_best_leaf(const DltRig<double>& dlt, const RayRig& ray, con
       unsigned children = 0;
       for (int o = 16; o > 0; o >>= 1) ok_bit |= __shfl_xor_sync(0xffffffffu, ok_bit, o);
       children = ok_bit | 1u;  // "none" repeats the parent's subset: same error, already known to pass
+      if (l == 0 && nparts > 1) {
+        // a search shared by several warps: this one takes every nparts-th subtree of the root (dealing out the subtrees of the
+        // second level instead balances better but shares the bound later: measured slower, profiles/r2_link_kernel.log)
+        unsigned mine = 0;
+        int r = 0;
+        for (unsigned m = children; m; r++) {
+          const int k = 31 - __clz(m);
+          m &= ~(1u << k);
+          if (r % nparts == part) mine |= 1u << k;
+        }
+        children = mine;
+      }
       if (lane == 0) sh.todo[l] = children;
       nodes += __popc(children);
       __syncwarp();
@@ -165,7 +197,8 @@ __device__ bool lazy_best_leaf(const DltRig<double>& dlt, const RayRig& ray, con
     if (lane == 0) sh.todo[l] = todo & ~(1u << k);
     const int cnt = sh.count[l] + (k ? 1 : 0);
     // bound: taking a detection on every remaining camera that has an allowed one
-    if (cnt + sh.potential[l + 1] < max(sh.best_count, MIN_CAMERAS)) { __syncwarp(); continue; }
+    // (the other warps' best count prunes too: a branch is only dropped when it cannot even tie, so what is found does not depend on timing)
+    if (cnt + sh.potential[l + 1] < max(max(sh.best_count, incumbent ? *reinterpret_cast<volatile int*>(incumbent) : 0), MIN_CAMERAS)) { __syncwarp(); continue; }
     if (lane == 0) {
       sh.choice[l] = (unsigned char)k;
       sh.count[l + 1] = cnt;
@@ -176,7 +209,7 @@ __device__ bool lazy_best_leaf(const DltRig<double>& dlt, const RayRig& ray, con
         for (int j = 0; j < 3; j++) sh.X[l + 1][j] = sh.c_X[l][k][j];
         if (p.solver == 0) {
           const double* P = dlt.P[l];
-          const double x = sh.px[l][k - 1], y = sh.py[l][k - 1];
+          const double x = fr.px[l][k - 1], y = fr.py[l][k - 1];
           double* r = sh.row[i];
           r[0] = P[0] - x * P[8]; r[1] = P[1] - x * P[9]; r[2] = P[2] - x * P[10]; r[3] = x * P[11] - P[3];
           r[4] = P[4] - y * P[8]; r[5] = P[5] - y * P[9]; r[6] = P[6] - y * P[10]; r[7] = y * P[11] - P[7];
@@ -220,7 +253,7 @@ __device__ bool lazy_best_leaf(const DltRig<double>& dlt, const RayRig& ray, con
         }
         if (better) {
           __syncwarp();
-          if (lane == 0) { sh.best_count = cnt; sh.best_err = sh.err[C]; for (int j = 0; j < 3; j++) sh.best_X[j] = sh.X[C][j]; }
+          if (lane == 0) { sh.best_count = cnt; sh.best_err = sh.err[C]; for (int j = 0; j < 3; j++) sh.best_X[j] = sh.X[C][j]; if (incumbent) atomicMax(incumbent, cnt); }
           for (int c = lane; c < C; c += 32) sh.best_choice[c] = sh.choice[c];
         }
       }
@@ -231,182 +264,275 @@ __device__ bool lazy_best_leaf(const DltRig<double>& dlt, const RayRig& ray, con
   return true;
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32 * LZ_WARPS)
 lazy_link_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_constant__ RayRig ray, ClsParams p, const int2* __restrict__ seq_bounds,
                  const int32_t* __restrict__ offs, const double* __restrict__ dets, LinkState* state, double* __restrict__ out_paths,
                  int8_t* __restrict__ out_assign, uint8_t* __restrict__ out_phase, ClsCounters* ctr) {
   extern __shared__ __align__(16) unsigned char lazy_dyn[];
-  LzShared& sh = *reinterpret_cast<LzShared*>(lazy_dyn);
-  const int lane = threadIdx.x, C = p.n_cams, D = p.n_drones;
+  LzFrame& fr = *reinterpret_cast<LzFrame*>(lazy_dyn);
+  LzLink& lk = *reinterpret_cast<LzLink*>(lazy_dyn + sizeof(LzFrame));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, C = p.n_cams, D = p.n_drones;
+  LzSearch& sh = reinterpret_cast<LzSearch*>(lazy_dyn + sizeof(LzFrame) + sizeof(LzLink))[warp];
   const int fa = seq_bounds ? seq_bounds[blockIdx.x].x : p.f0, fb = seq_bounds ? seq_bounds[blockIdx.x].y : p.f1;
   LinkState* st = state + blockIdx.x;
-  for (int i = lane; i < (int)(sizeof(LinkState) / sizeof(int)); i += 32) ((int*)&sh.S)[i] = ((const int*)st)[i];
-  __syncwarp();
+  for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += 32 * LZ_WARPS) ((int*)&lk.S)[i] = ((const int*)st)[i];
+  if (tid == 0) lk.abort = 0;
+  __syncthreads();
   unsigned long long nodes = 0, solves = 0, lm_iters = 0, n_phase1 = 0, n_phase2 = 0, leaves = 0;
-  bool out_of_budget = false, overflow_final = false, bad_input = false;
+  bool overflow_final = false, bad_input = false;
 
-  auto emit = [&](int path, int f, const double* X, const unsigned char* choice, int phase) {  // lane 0
-    const int n = sh.S.n[path];
-    double(*t)[3] = sh.S.tail[path];
+  auto emit = [&](int path, int f, const double* X, const unsigned char* choice, int phase) {  // warp 0, lane 0
+    const int n = lk.S.n[path];
+    double(*t)[3] = lk.S.tail[path];
     if (n >= PATH_TAIL) {
       for (int k = 0; k < PATH_TAIL - 1; k++) for (int j = 0; j < 3; j++) t[k][j] = t[k + 1][j];
       for (int j = 0; j < 3; j++) t[PATH_TAIL - 1][j] = X[j];
     } else {
       for (int j = 0; j < 3; j++) t[n][j] = X[j];
     }
-    if (n < 0x3fffffff) sh.S.n[path] = n + 1;
+    if (n < 0x3fffffff) lk.S.n[path] = n + 1;
     double* o = out_paths + ((size_t)path * p.n_frames + f) * 3;
     o[0] = X[0]; o[1] = X[1]; o[2] = X[2];
     if (out_assign) for (int c = 0; c < C; c++) out_assign[((size_t)path * p.n_frames + f) * C + c] = (int8_t)choice[c];
     if (out_phase) out_phase[(size_t)path * p.n_frames + f] = (uint8_t)phase;
   };
+  // the MAX_STEP ray gate of a path (:228-236), lane <-> camera, into lk.gate[np]; allowed = gate & ~(used if filtered); returns
+  // the number of cameras with an allowed detection
+  auto gate_path = [&](int np, const double* last, bool filtered, bool compute) {
+    int cams = 0;
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      const int c = c0 + lane;
+      unsigned g = 0;
+      if (c < C) {
+        if (compute) {
+          for (int d = 0; d < fr.n[c]; d++)
+            if (ref::dist_to_ray(ray.pos[c], fr.dir[c][d], last[0], last[1], last[2]) < MAX_STEP) g |= 1u << d;
+          lk.gate[np][c] = (unsigned short)g;
+        } else {
+          g = lk.gate[np][c];
+        }
+        if (filtered) g &= ~(unsigned)lk.used[c];
+        sh.allowed[c] = (unsigned short)g;
+      }
+      cams += __popc(__ballot_sync(0xffffffffu, c < C && g != 0));
+    }
+    __syncwarp();
+    return cams;
+  };
 
-  for (int f = fa; f < fb && !out_of_budget; f++) {
-    // ---- the frame's detections and their pixel rays ----
-    for (int c = lane; c < C; c += 32) {
+  for (int f = fa; f < fb; f++) {
+    // ---- the frame's detections and their pixel rays (all warps) ----
+    for (int c = tid; c < C; c += 32 * LZ_WARPS) {
       const int a = offs[(size_t)c * (p.n_frames + 1) + f], b = offs[(size_t)c * (p.n_frames + 1) + f + 1];
       if (b < a || b - a > TRI_MAX_DETS) bad_input = true;
       const int n = min(max(b - a, 0), TRI_MAX_DETS);
-      sh.n[c] = n;
-      sh.all[c] = (unsigned short)((1u << n) - 1u);
-      sh.used[c] = 0;
+      fr.n[c] = n;
+      lk.all[c] = (unsigned short)((1u << n) - 1u);
+      lk.used[c] = 0;
     }
-    __syncwarp();
-    for (int i = lane; i < C * TRI_MAX_DETS; i += 32) {
+    __syncthreads();
+    for (int i = tid; i < C * TRI_MAX_DETS; i += 32 * LZ_WARPS) {
       const int c = i / TRI_MAX_DETS, d = i - c * TRI_MAX_DETS;
-      if (d < sh.n[c]) {
+      if (d < fr.n[c]) {
         const int a = offs[(size_t)c * (p.n_frames + 1) + f];
         const double x = dets[2 * (size_t)(a + d)], y = dets[2 * (size_t)(a + d) + 1];
-        sh.px[c][d] = x; sh.py[c][d] = y;
-        ref::make_dir(ray, c, x, y, sh.dir[c][d]);
+        fr.px[c][d] = x; fr.py[c][d] = y;
+        ref::make_dir(ray, c, x, y, fr.dir[c][d]);
       }
     }
-    __syncwarp();
+    __syncthreads();
 
-    // ---- phase 1: tracking (:119-135), paths in order ----
-    unsigned processed = 0;
-    for (int np = 0; np < D && !out_of_budget; np++) {
-      const int n = sh.S.n[np];
+    // ---- phase 1, speculative: every tracked path's best leaf inside its own gate, the other paths' picks ignored;
+    // LZ_WARPS paths at a time, one warp each (:121-123 decides which paths track) ----
+    unsigned act_mask = 0;
+    for (int np = 0; np < D; np++) {
+      const int n = lk.S.n[np];
       if (n == 0) continue;
-      const double* last = sh.S.tail[np][min(n, PATH_TAIL) - 1];
-      if (last[0] == 0 && last[1] == 0 && last[2] == 0) continue;  // :121-123
-      // the MAX_STEP ray gate (:228-236): lane <-> camera
-      int cams_in_gate = 0;
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        const int c = c0 + lane;
-        unsigned g = 0;
-        if (c < C)
-          for (int d = 0; d < sh.n[c]; d++)
-            if (ref::dist_to_ray(ray.pos[c], sh.dir[c][d], last[0], last[1], last[2]) < MAX_STEP) g |= 1u << d;
-        if (c < C) { sh.gate[np][c] = (unsigned short)g; sh.allowed[c] = (unsigned short)(g & ~sh.used[c]); }
-        cams_in_gate += __popc(__ballot_sync(0xffffffffu, c < C && (g & ~(c < C ? sh.used[c] : 0u)) != 0));
+      const double* last = lk.S.tail[np][min(n, PATH_TAIL) - 1];
+      if (last[0] == 0 && last[1] == 0 && last[2] == 0) continue;
+      act_mask |= 1u << np;
+    }
+    {
+      int ai = 0;
+      for (unsigned rem = act_mask; rem; rem &= rem - 1, ai++) {
+        if (ai % LZ_WARPS != warp) continue;
+        const int np = __ffs(rem) - 1;
+        const double* last = lk.S.tail[np][min(lk.S.n[np], PATH_TAIL) - 1];
+        const int cams_in_gate = gate_path(np, last, false, true);
+        int found = 0;
+        if (cams_in_gate >= MIN_CAMERAS) {
+          if (!lazy_best_leaf(dlt, ray, p, fr, sh, last, nodes, solves, lm_iters)) { if (lane == 0) lk.abort = 1; }
+          else found = sh.best_count;
+        }
+        if (lane == 0) { lk.spec_count[np] = found; for (int j = 0; j < 3; j++) lk.spec_X[np][j] = sh.best_X[j]; }
+        if (found >= MIN_CAMERAS) for (int c = lane; c < C; c += 32) lk.spec_choice[np][c] = sh.best_choice[c];
       }
-      __syncwarp();
-      if (cams_in_gate < MIN_CAMERAS) continue;
-      if (!lazy_best_leaf(dlt, ray, p, sh, last, nodes, solves, lm_iters)) { out_of_budget = true; break; }
-      if (sh.best_count >= MIN_CAMERAS) {
+    }
+    __syncthreads();
+    if (lk.abort) break;
+
+    if (warp == 0) {
+      // ---- confirm in path order (:119-135): a pick that shares no detection with the ones accepted before it is also the
+      // best leaf of the filtered search; a colliding one is searched again with the used detections taken out ----
+      unsigned processed = 0;
+      for (unsigned rem = act_mask; rem; rem &= rem - 1) {
+        const int np = __ffs(rem) - 1;
+        if (lk.spec_count[np] < MIN_CAMERAS) continue;  // nothing inside the gate even with every detection free
+        bool clash = false;
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          const int c = c0 + lane;
+          const int k = c < C ? lk.spec_choice[np][c] : 0;
+          clash = clash || __any_sync(0xffffffffu, k && (lk.used[c < C ? c : 0] >> (k - 1) & 1));
+        }
+        const double* X = lk.spec_X[np];
+        const unsigned char* choice = lk.spec_choice[np];
+        if (clash) {
+          const double* last = lk.S.tail[np][min(lk.S.n[np], PATH_TAIL) - 1];
+          if (gate_path(np, last, true, false) < MIN_CAMERAS) continue;
+          if (!lazy_best_leaf(dlt, ray, p, fr, sh, last, nodes, solves, lm_iters)) { if (lane == 0) lk.abort = 1; break; }
+          if (sh.best_count < MIN_CAMERAS) continue;
+          X = sh.best_X; choice = sh.best_choice;
+        }
         leaves++;
         processed |= 1u << np;
-        if (lane == 0) { emit(np, f, sh.best_X, sh.best_choice, 1); n_phase1++; }
         for (int c = lane; c < C; c += 32)
-          if (sh.best_choice[c]) sh.used[c] |= (unsigned short)(1u << (sh.best_choice[c] - 1));
+          if (choice[c]) lk.used[c] |= (unsigned short)(1u << (choice[c] - 1));
+        __syncwarp();
+        if (lane == 0) { emit(np, f, X, choice, 1); n_phase1++; }
+        __syncwarp();
+      }
+      if (lane == 0) lk.processed = processed;
+    }
+    __syncthreads();
+    if (lk.abort) break;
+    const unsigned processed = lk.processed;
+
+    if (__popc(processed) != D) {  // :137
+      // ---- phase 2: pickBestCombinations (:200-217): the best leaf among the unused detections, again and again.  One search,
+      // all warps: each takes every LZ_WARPS-th subtree of the root, the best count found so far is shared ----
+      int n_fin = 0;
+      for (;;) {
+        int live = 0;
+        for (int c0 = 0; c0 < C; c0 += 32) {
+          const int c = c0 + lane;
+          if (c < C) sh.allowed[c] = (unsigned short)(lk.all[c] & ~lk.used[c]);
+          live += __popc(__ballot_sync(0xffffffffu, c < C && (lk.all[c] & ~lk.used[c]) != 0));
+        }
+        if (tid == 0) { lk.incumbent = 0; if (n_fin == 0) lk.more = 0; }
+        __syncthreads();
+        if (live < MIN_CAMERAS) break;
+        if (!lazy_best_leaf(dlt, ray, p, fr, sh, nullptr, nodes, solves, lm_iters, warp, LZ_WARPS, &lk.incumbent) && lane == 0) lk.abort = 1;
+        __syncthreads();
+        if (lk.abort) break;
+        if (warp == 0) {  // the best of the warps' bests: most cameras, smallest error, then DFS order (lexicographic in the choices)
+          LzSearch* all = reinterpret_cast<LzSearch*>(lazy_dyn + sizeof(LzFrame) + sizeof(LzLink));
+          int wb = -1;
+          for (int w = 0; w < LZ_WARPS; w++) {
+            const LzSearch& q = all[w];
+            if (q.best_count < MIN_CAMERAS) continue;
+            bool better = wb < 0 || q.best_count > all[wb].best_count || (q.best_count == all[wb].best_count && q.best_err < all[wb].best_err);
+            if (!better && q.best_count == all[wb].best_count && q.best_err == all[wb].best_err) {
+              int first = C;
+              for (int c0 = 0; c0 < C; c0 += 32) {
+                const int c = c0 + lane;
+                const unsigned diff = __ballot_sync(0xffffffffu, c < C && q.best_choice[c] != all[wb].best_choice[c]);
+                if (diff) { first = c0 + __ffs(diff) - 1; break; }
+              }
+              better = first < C && q.best_choice[first] < all[wb].best_choice[first];
+            }
+            if (better) wb = w;
+          }
+          if (wb >= 0) {
+            leaves++;
+            if (n_fin >= LINK_MAX_FINAL) overflow_final = true;
+            else {
+              const LzSearch& q = all[wb];
+              if (lane == 0) { for (int j = 0; j < 3; j++) lk.fin_X[n_fin][j] = q.best_X[j]; lk.more = n_fin + 1; }  // (only ever rises within a frame)
+              for (int c = lane; c < C; c += 32) {
+                lk.fin_choice[n_fin][c] = q.best_choice[c];
+                if (q.best_choice[c]) lk.used[c] |= (unsigned short)(1u << (q.best_choice[c] - 1));
+              }
+            }
+          }
+        }
+        __syncthreads();
+        if (lk.more != n_fin + 1) break;
+        n_fin++;
+      }
+      if (!lk.abort && warp == 0) {
+        // ---- classifyPaths (:262-332) ----
+        unsigned open_paths = 0;
+        for (int j = 0; j < D; j++) if (!(processed >> j & 1u) && lk.S.n[j] != 0) open_paths |= 1u << j;
+        const int n_open = __popc(open_paths);
+        for (int q = lane; q < n_fin * n_open; q += 32) {
+          const int ci = q / n_open;
+          int j = 0;
+          { unsigned rem = open_paths; for (int s2 = q - ci * n_open; s2 > 0; s2--) rem &= rem - 1; j = __ffs(rem) - 1; }
+          const int npc = min(lk.S.n[j], PATH_TAIL);
+          double dist = 0;
+          for (int t = 0; t < npc; t++) {
+            const double dx = lk.S.tail[j][t][0] - lk.fin_X[ci][0], dy = lk.S.tail[j][t][1] - lk.fin_X[ci][1], dz = lk.S.tail[j][t][2] - lk.fin_X[ci][2];
+            dist += sqrt(dx * dx + dy * dy + dz * dz);
+          }
+          lk.pdist[ci][j] = dist / (double)npc;
+        }
+        __syncwarp();
+        for (int i = lane; i < n_fin; i += 32) {
+          int bestPath = 0;
+          double bestDist = -1;
+          for (unsigned rem = open_paths; rem; rem &= rem - 1) {
+            const int j = __ffs(rem) - 1;
+            const double dist = lk.pdist[i][j];
+            if (dist < bestDist || bestDist == -1) { bestDist = dist; bestPath = j; }
+          }
+          lk.cp_path[i] = bestPath; lk.cp_err[i] = bestDist;
+        }
+        __syncwarp();
+        if (lane == 0) {  // the stable ascending order of :299-300, walked as :302-321 does
+          unsigned done = processed;
+          unsigned long long taken_lo = 0, taken_hi = 0;
+          for (int step = 0; step < n_fin; step++) {
+            int idx = -1;
+            for (int i = 0; i < n_fin; i++) {
+              if ((i < 64 ? taken_lo >> i : taken_hi >> (i - 64)) & 1ull) continue;
+              if (idx < 0 || lk.cp_err[i] < lk.cp_err[idx]) idx = i;
+            }
+            if (idx < 64) taken_lo |= 1ull << idx; else taken_hi |= 1ull << (idx - 64);
+            int target = -1;
+            if (done >> lk.cp_path[idx] & 1u) {
+              for (int i = 0; i < D; i++) if (lk.S.n[i] == 0) { target = i; break; }
+            } else {
+              target = lk.cp_path[idx];
+            }
+            if (target != -1) { emit(target, f, lk.fin_X[idx], lk.fin_choice[idx], 2); done |= 1u << target; n_phase2++; }
+          }
+        }
         __syncwarp();
       }
     }
-    if (out_of_budget || __popc(processed) == D) continue;  // :137
-
-    // ---- phase 2: pickBestCombinations (:200-217): the best leaf among the unused detections, again and again ----
-    int n_fin = 0;
-    for (;;) {
-      int live = 0;
-      for (int c0 = 0; c0 < C; c0 += 32) {
-        const int c = c0 + lane;
-        if (c < C) sh.allowed[c] = (unsigned short)(sh.all[c] & ~sh.used[c]);
-        live += __popc(__ballot_sync(0xffffffffu, c < C && (sh.all[c] & ~sh.used[c]) != 0));
-      }
-      __syncwarp();
-      if (live < MIN_CAMERAS) break;
-      if (!lazy_best_leaf(dlt, ray, p, sh, nullptr, nodes, solves, lm_iters)) { out_of_budget = true; break; }
-      if (sh.best_count < MIN_CAMERAS) break;
-      leaves++;
-      if (n_fin >= LINK_MAX_FINAL) { overflow_final = true; break; }
-      if (lane == 0) for (int j = 0; j < 3; j++) sh.fin_X[n_fin][j] = sh.best_X[j];
-      for (int c = lane; c < C; c += 32) {
-        sh.fin_choice[n_fin][c] = sh.best_choice[c];
-        if (sh.best_choice[c]) sh.used[c] |= (unsigned short)(1u << (sh.best_choice[c] - 1));
-      }
-      n_fin++;
-      __syncwarp();
-    }
-    if (out_of_budget) break;
-
-    // ---- classifyPaths (:262-332) ----
-    unsigned open_paths = 0;
-    for (int j = 0; j < D; j++) if (!(processed >> j & 1u) && sh.S.n[j] != 0) open_paths |= 1u << j;
-    const int n_open = __popc(open_paths);
-    for (int q = lane; q < n_fin * n_open; q += 32) {
-      const int ci = q / n_open;
-      int j = 0;
-      { unsigned rem = open_paths; for (int s2 = q - ci * n_open; s2 > 0; s2--) rem &= rem - 1; j = __ffs(rem) - 1; }
-      const int npc = min(sh.S.n[j], PATH_TAIL);
-      double dist = 0;
-      for (int t = 0; t < npc; t++) {
-        const double dx = sh.S.tail[j][t][0] - sh.fin_X[ci][0], dy = sh.S.tail[j][t][1] - sh.fin_X[ci][1], dz = sh.S.tail[j][t][2] - sh.fin_X[ci][2];
-        dist += sqrt(dx * dx + dy * dy + dz * dz);
-      }
-      sh.pdist[ci][j] = dist / (double)npc;
-    }
-    __syncwarp();
-    for (int i = lane; i < n_fin; i += 32) {
-      int bestPath = 0;
-      double bestDist = -1;
-      for (unsigned rem = open_paths; rem; rem &= rem - 1) {
-        const int j = __ffs(rem) - 1;
-        const double dist = sh.pdist[i][j];
-        if (dist < bestDist || bestDist == -1) { bestDist = dist; bestPath = j; }
-      }
-      sh.cp_path[i] = bestPath; sh.cp_err[i] = bestDist;
-    }
-    __syncwarp();
-    if (lane == 0) {  // the stable ascending order of :299-300, walked as :302-321 does
-      unsigned done = processed;
-      unsigned long long taken_lo = 0, taken_hi = 0;
-      for (int step = 0; step < n_fin; step++) {
-        int idx = -1;
-        for (int i = 0; i < n_fin; i++) {
-          if ((i < 64 ? taken_lo >> i : taken_hi >> (i - 64)) & 1ull) continue;
-          if (idx < 0 || sh.cp_err[i] < sh.cp_err[idx]) idx = i;
-        }
-        if (idx < 64) taken_lo |= 1ull << idx; else taken_hi |= 1ull << (idx - 64);
-        int target = -1;
-        if (done >> sh.cp_path[idx] & 1u) {
-          for (int i = 0; i < D; i++) if (sh.S.n[i] == 0) { target = i; break; }
-        } else {
-          target = sh.cp_path[idx];
-        }
-        if (target != -1) { emit(target, f, sh.fin_X[idx], sh.fin_choice[idx], 2); done |= 1u << target; n_phase2++; }
-      }
-    }
-    __syncwarp();
+    __syncthreads();  // the frame is linked: its data may be overwritten, the state is current
+    if (lk.abort) break;
   }
-  __syncwarp();
-  for (int i = lane; i < (int)(sizeof(LinkState) / sizeof(int)); i += 32) ((int*)st)[i] = ((const int*)&sh.S)[i];
-  for (int o = 16; o > 0; o >>= 1) { solves += __shfl_down_sync(0xffffffffu, solves, o); lm_iters += __shfl_down_sync(0xffffffffu, lm_iters, o); }
+  __syncthreads();
+  for (int i = tid; i < (int)(sizeof(LinkState) / sizeof(int)); i += 32 * LZ_WARPS) ((int*)st)[i] = ((const int*)&lk.S)[i];
+  for (int o = 16; o > 0; o >>= 1) {
+    solves += __shfl_down_sync(0xffffffffu, solves, o); lm_iters += __shfl_down_sync(0xffffffffu, lm_iters, o);
+  }
   if (lane == 0) {
     atomicAdd(&ctr->nodes, nodes); atomicAdd(&ctr->solves, solves); atomicAdd(&ctr->lm_iters, lm_iters);
     atomicAdd(&ctr->leaves, leaves); atomicAdd(&ctr->phase1, n_phase1); atomicAdd(&ctr->phase2, n_phase2);
-    if (out_of_budget) atomicExch(&ctr->overflow_frontier, 1);
     if (overflow_final) atomicExch(&ctr->overflow_final, 1);
   }
+  if (tid == 0 && lk.abort) atomicExch(&ctr->overflow_frontier, 1);
   if (__any_sync(0xffffffffu, bad_input) && lane == 0) atomicExch(&ctr->bad_input, 1);
 }
 
 cudaError_t launch_lazy_link(cudaStream_t s, const DltRig<double>& dlt, const RayRig& ray, const ClsParams& p, int n_seq, const int2* d_seq,
                              const int32_t* d_offs, const double* d_dets, LinkState* d_state, double* d_paths, int8_t* d_assign,
                              uint8_t* d_phase, ClsCounters* d_ctr) {
-  cudaError_t err = cudaFuncSetAttribute(lazy_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LzShared));
+  cudaError_t err = cudaFuncSetAttribute(lazy_link_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LZ_SMEM_BYTES);
   if (err != cudaSuccess) return err;
-  lazy_link_kernel<<<n_seq, 32, sizeof(LzShared), s>>>(dlt, ray, p, d_seq, d_offs, d_dets, d_state, d_paths, d_assign, d_phase, d_ctr);
+  lazy_link_kernel<<<n_seq, 32 * LZ_WARPS, LZ_SMEM_BYTES, s>>>(dlt, ray, p, d_seq, d_offs, d_dets, d_state, d_paths, d_assign, d_phase, d_ctr);
   return cudaGetLastError();
 }
 
