@@ -1,7 +1,7 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-for lib in W18 W20 W24; do
+for lib in M N; do
   [ -f 3d-reconstruction-triangulation_b200/libtri_b200_$lib.so ] || continue
-  echo "== $lib"; TRI_B200_LIB=$PWD/3d-reconstruction-triangulation_b200/libtri_b200_$lib.so timeout 600 python tools/link_iter.py --frames 20000 2>&1 | awk '!seen[substr($0,1,30)]++' | grep -v golden
+  echo "== $lib"; TRI_B200_LIB=$PWD/3d-reconstruction-triangulation_b200/libtri_b200_$lib.so timeout 600 python tools/link_iter.py --frames 20000 2>&1 | awk '!seen[substr($0,1,30)]++' 
 done
 echo "== current"; timeout 600 python tools/link_iter.py --frames 20000 2>&1 | awk '!seen[substr($0,1,30)]++' | grep -v golden
