@@ -1,7 +1,4 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-for lib in M N; do
-  [ -f 3d-reconstruction-triangulation_b200/libtri_b200_$lib.so ] || continue
-  echo "== $lib"; TRI_B200_LIB=$PWD/3d-reconstruction-triangulation_b200/libtri_b200_$lib.so timeout 600 python tools/link_iter.py --frames 20000 2>&1 | awk '!seen[substr($0,1,30)]++' 
-done
-echo "== current"; timeout 600 python tools/link_iter.py --frames 20000 2>&1 | awk '!seen[substr($0,1,30)]++' | grep -v golden
+timeout 600 python tools/link_iter.py --frames 20000 2>&1 | awk '!seen[substr($0,1,30)]++'
+timeout 900 python -m pytest tests/test_gpu_classify.py -m gpu -x -q 2>&1 | tail -3
