@@ -385,3 +385,38 @@ def test_lazy_search_on_12_and_32_camera_rigs():
             for c in range(32):
                 ks = [int(k) for k in r["assign"][:, f, c] if k > 0]
                 assert len(ks) == len(set(ks))
+
+def test_twelve_drones_more_paths_than_half_the_warps():
+    """Twelve drones on a 4-camera rig: more tracked paths than the linking kernel has warps per path to spare (one warp each, no
+    second one to share a scan), twelve detections per camera and frame; enumeration + linking and the lazy search against the
+    oracle, bit for bit, and a run with every other frame empty (paths re-initialise, tails restart)."""
+    from tri_b200 import synthetic as S
+    cams = S.ring_rig(4)
+    nf = 40
+    offs, xy, truth = S.generate_multi_drone(cams, nf, 12)
+    eng = T.Engine(cams, 0)
+    ref = O.classify(ocams(cams), O.MATRIX, 12, offs, xy, 4, nf)
+    for flags in (0, T.CLS_LAZY):
+        r = eng.classify(T.MATRIX, 12, offs, xy, nf, flags)
+        assert np.array_equal(ref["assign"], r["assign"]) and np.array_equal(ref["phase"], r["phase"])
+        np.testing.assert_allclose(r["paths"], ref["paths"], rtol=1e-9, atol=1e-6)
+    assert int((ref["phase"] == 1).sum()) > 6 * nf  # most of the twelve are tracked most of the time
+    # every other frame without a single detection
+    o2 = np.asarray(offs, np.int64).reshape(4, nf + 1).copy()
+    keep = np.ones(len(xy), bool)
+    for c in range(4):
+        cnt = np.diff(o2[c])
+        for f in range(1, nf, 2):
+            keep[o2[c, f]:o2[c, f + 1]] = False
+            cnt[f] = 0
+        o2[c, 1:] = o2[c, 0] + np.cumsum(cnt)
+    base = 0
+    for c in range(4):  # cameras back to back again
+        n_c = o2[c, -1] - o2[c, 0]
+        o2[c] = o2[c] - o2[c, 0] + base
+        base += n_c
+    xy2 = np.asarray(xy)[keep]
+    o2 = o2.astype(np.int32).reshape(-1)
+    ref2 = O.classify(ocams(cams), O.MATRIX, 12, o2, xy2, 4, nf)
+    r2 = eng.classify(T.MATRIX, 12, o2, xy2, nf)
+    assert np.array_equal(ref2["assign"], r2["assign"]) and np.array_equal(ref2["phase"], r2["phase"])
