@@ -39,7 +39,8 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
                  const int32_t* __restrict__ offs, const double* __restrict__ dets, u64* __restrict__ front,
                  double* __restrict__ tmp_xyz, double* __restrict__ tmp_err, u64* __restrict__ leaf_rec,
                  long long* __restrict__ leaf_off, int* __restrict__ leaf_cnt, int* __restrict__ hdr,
-                 unsigned char* __restrict__ fdet, long long* __restrict__ fdet_off, int* __restrict__ fdet_cnt, ClsCounters* ctr) {
+                 unsigned char* __restrict__ fdet, long long* __restrict__ fdet_off, int* __restrict__ fdet_cnt, unsigned* __restrict__ sort_kb,
+                 ClsCounters* ctr) {
   __shared__ int s_n[CLS_MAX_CAMS], s_pref[CLS_MAX_CAMS + 1], s_hist[CLS_MAX_CAMS + 2];
   __shared__ long long s_doff;
   __shared__ double s_px[CLS_MAX_CAMS][TRI_MAX_DETS], s_py[CLS_MAX_CAMS][TRI_MAX_DETS];
@@ -168,8 +169,7 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
           // ... in PRIORITY order: the order in which the reference's priority_queue pops them = fewer unused cameras first,
           // then smaller error (Combination::operator<, :12-20), ties by DFS order.  The errors are >= +0, so their bit
           // patterns order like the values: the leaves are sorted by (unused cameras, error bits, DFS index) with a bitonic
-          // network in shared memory (round 1 ranked by counting, O(m^2): three quarters of this kernel's time); only a
-          // frame with more than ENUM_SORT_CAP leaves still ranks by counting.
+          // network (round 1 ranked by counting, O(m^2): three quarters of this kernel's time).
           const u64 cam_bits = C == 16 ? ~0ull : ((1ull << (4 * C)) - 1);
           const int RW = rec_words(p.W);
           u64 n_tie = 0;
@@ -189,17 +189,19 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
             prow[2] = (u64)__double_as_longlong(t_xyz[3 * i + 2]);
             prow[3] = ci;
           };
-          if (m <= ENUM_SORT_CAP) {
+          // keys in shared memory, or -- a frame with more than ENUM_SORT_CAP leaves -- in this CTA's scratch in global memory
+          // (the frontier buffer that is free after the last level; __syncthreads orders the CTA's global accesses as well)
+          auto sort_and_publish = [&](u64* ka, unsigned* kb) {
             int n = 2;
             while (n < m) n <<= 1;
             for (int i = tid; i < n; i += CLS_THREADS) {
               if (i < m) {
                 const int zi = C - __popcll(nonzero_nibbles(fin[i] & cam_bits));
-                s_ka[i] = (u64)__double_as_longlong(t_err[i]);
-                s_kb[i] = ((unsigned)zi << ENUM_IDX_BITS) | (unsigned)i;
+                ka[i] = (u64)__double_as_longlong(t_err[i]);
+                kb[i] = ((unsigned)zi << ENUM_IDX_BITS) | (unsigned)i;
                 atomicAdd(&s_hist[zi + 1], 1);
               } else {
-                s_ka[i] = ~0ull; s_kb[i] = ~0u;  // padding sorts last
+                ka[i] = ~0ull; kb[i] = ~0u;  // padding sorts last
               }
             }
             __syncthreads();
@@ -207,41 +209,25 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
               for (int j = k >> 1; j > 0; j >>= 1) {
                 for (int t = tid; t < (n >> 1); t += CLS_THREADS) {
                   const int lo = 2 * t - (t & (j - 1)), hi = lo + j;  // the t-th pair of this step
-                  const u64 a = s_ka[lo], b = s_ka[hi];
-                  const unsigned ab = s_kb[lo], bb = s_kb[hi];
+                  const u64 a = ka[lo], b = ka[hi];
+                  const unsigned ab = kb[lo], bb = kb[hi];
                   const unsigned za = ab >> ENUM_IDX_BITS, zb = bb >> ENUM_IDX_BITS;
                   const bool a_after_b = za != zb ? za > zb : (a != b ? a > b : ab > bb);
-                  if (a_after_b == ((lo & k) == 0)) { s_ka[lo] = b; s_ka[hi] = a; s_kb[lo] = bb; s_kb[hi] = ab; }
+                  if (a_after_b == ((lo & k) == 0)) { ka[lo] = b; ka[hi] = a; kb[lo] = bb; kb[hi] = ab; }
                 }
                 __syncthreads();
               }
             for (int r = tid; r < m; r += CLS_THREADS) {
-              const u64 a = s_ka[r];
-              const unsigned ab = s_kb[r], z = ab >> ENUM_IDX_BITS;
+              const u64 a = ka[r];
+              const unsigned ab = kb[r], z = ab >> ENUM_IDX_BITS;
               const int i = (int)(ab & ((1u << ENUM_IDX_BITS) - 1));
-              n_tie += (r > 0 && s_ka[r - 1] == a && (s_kb[r - 1] >> ENUM_IDX_BITS) == z) ||
-                       (r + 1 < m && s_ka[r + 1] == a && (s_kb[r + 1] >> ENUM_IDX_BITS) == z);
+              n_tie += (r > 0 && ka[r - 1] == a && (kb[r - 1] >> ENUM_IDX_BITS) == z) ||
+                       (r + 1 < m && ka[r + 1] == a && (kb[r + 1] >> ENUM_IDX_BITS) == z);
               publish(i, r, fin[i], __longlong_as_double((long long)a));
             }
-          } else {
-            for (int i = tid; i < m; i += CLS_THREADS) {
-              const u64 ci = fin[i];
-              const double ei = t_err[i];
-              const int zi = C - __popcll(nonzero_nibbles(ci & cam_bits));
-              int rank = 0;
-              bool tie = false;
-              for (int j = 0; j < m; j++) {
-                const int zj = C - __popcll(nonzero_nibbles(fin[j] & cam_bits));
-                const double ej = t_err[j];
-                const bool eq = zj == zi && ej == ei;
-                rank += (zj < zi) || (zj == zi && ej < ei) || (eq && j < i);
-                tie = tie || (eq && j != i);
-              }
-              n_tie += tie;
-              atomicAdd(&s_hist[zi + 1], 1);
-              publish(i, rank, ci, ei);
-            }
-          }
+          };
+          if (m <= ENUM_SORT_CAP) sort_and_publish(s_ka, s_kb);
+          else sort_and_publish(fout, sort_kb + (size_t)blockIdx.x * p.cap);
           if (n_tie) atomicAdd(&ctr->ties, n_tie);
           __syncthreads();
           if (tid == 0) {
@@ -902,7 +888,7 @@ struct ClsWork {
     link_ms += ms;
     return cudaSuccess;
   }
-  DevBuf offs, dets, paths, assign, phase, state, ctr, ctr_link, front, txyz, terr, seq;
+  DevBuf offs, dets, paths, assign, phase, state, ctr, ctr_link, front, txyz, terr, sortkb, seq;
   LinkInput in[2];
   // tri_classify_begin / tri_classify_finish: the enumerated shard waiting for its linking pass
   bool pending = false;
@@ -984,6 +970,7 @@ int cls_enumerate(tri_engine* e, ClsWork& W, int k, ClsParams& p, int cap, long 
   TRI_CUDA(W.front.alloc(sizeof(u64) * 2 * (size_t)cap * grid));
   TRI_CUDA(W.txyz.alloc(sizeof(double) * 3 * (size_t)cap * grid));
   TRI_CUDA(W.terr.alloc(sizeof(double) * (size_t)cap * grid));
+  TRI_CUDA(W.sortkb.alloc(sizeof(unsigned) * (size_t)cap * grid));
   TRI_CUDA(W.events());
   TRI_CUDA(W.collect(k));  // the linking pass that read this set before
   LinkInput& I = W.in[k];
@@ -1001,7 +988,7 @@ int cls_enumerate(tri_engine* e, ClsWork& W, int k, ClsParams& p, int cap, long 
   enumerate_kernel<<<grid, CLS_THREADS, ENUM_SMEM_BYTES, s>>>(e->rig64, e->ray, p, W.offs.as<int32_t>(), W.dets.as<double>(), W.front.as<u64>(),
                                                  W.txyz.as<double>(), W.terr.as<double>(), I.lrec.as<u64>(), I.loff.as<long long>(),
                                                  I.lcnt.as<int>(), I.hdr.as<int>(), I.fdet.as<unsigned char>(), I.fdoff.as<long long>(),
-                                                 I.fdcnt.as<int>(), ctr);
+                                                 I.fdcnt.as<int>(), W.sortkb.as<unsigned>(), ctr);
   e->launches++;
   TRI_CUDA(cudaGetLastError());
   TRI_CUDA(cudaEventRecord(W.ev[1], s));

@@ -16,8 +16,8 @@ constexpr int CLS_THREADS = 128;
 #ifndef TRI_ENUM_MIN_CTAS
 #define TRI_ENUM_MIN_CTAS 4
 #endif
-constexpr int ENUM_SORT_CAP = TRI_ENUM_SORT_CAP;   // leaves of one frame sorted in shared memory (12 bytes each); longer lists are ranked by counting
-constexpr int ENUM_IDX_BITS = 12;
+constexpr int ENUM_SORT_CAP = TRI_ENUM_SORT_CAP;   // leaves of one frame sorted in shared memory (12 bytes each); longer lists are sorted in global memory
+constexpr int ENUM_IDX_BITS = 22;                  // a frame's leaves are numbered below the frontier capacity, at most 2^22
 constexpr int ENUM_SMEM_BYTES = ENUM_SORT_CAP * 12;
 constexpr int LINK_MAX_FINAL = 128;  // combinations pickBestCombinations can keep in one frame: <= 15 * C / 2 = 120 disjoint ones
 typedef unsigned long long u64;
