@@ -287,7 +287,8 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
 //     in the warp, atomicMin across the warps, one block barrier), adds its mask to the used mask and strikes the leaves
 //     it collides with.
 //   classifyPaths (:262-332) on warp 0, lane <-> kept combination: tail distances, nearest open path, then the ordered
-//     assignment by warp-wide minimum extraction (three REDUX operations per step).
+//     assignment by warp-wide minimum extraction (three REDUX operations per step).  Phase 1's pushes run on the last warp
+//     meanwhile: phase 2 and classifyPaths only touch the paths phase 1 did not serve.
 // The kernel is one latency-bound CTA per sequence: what a frame costs is the length of its chain of dependent
 // instructions (a lone warp issues one every 6-10 cycles here: LDS 30, VOTE 28, SHFL 33, REDUX 50 cycles, tools/micro/redux.cu;
 // instruction fetch is not the limit, tools/micro/ifetch.cu).  Round 1 ran it with ~15 block barriers per frame, the pixel rays
@@ -618,6 +619,7 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __restr
               c_np = scan(c_np, 0, 1, g, used, last[0], last[1], last[2], nullptr);
               if (lane == np) {
                 cand = c_np;
+                spec[np] = c_np;  // (the warp that pushes reads the picks back)
 #pragma unroll
                 for (int w = 0; w < W; w++) mk[w] = c_np != LINK_NONE ? msk[(size_t)c_np * W + w] : 0ull;
               }
@@ -637,13 +639,14 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __restr
 #pragma unroll
         for (int w = 0; w < W; w++) used[w] = s_used[w];
         processed = s_processed;
+        cand = (lane < D && ((processed >> lane) & 1u)) ? spec[lane] : LINK_NONE;
       }
     }
     CLS_PROF(8);
-    if (warp == 0) {
-      if ((processed >> lane) & 1u) emit(lane, cand, 1);  // all confirmed paths at once, one lane per path
-      if (lane == 0) n_phase1 += __popc(processed);
-    }
+    // phase 1's pushes, all confirmed paths at once (lane <-> path), on the last warp: warp 0 goes straight on to phase 2 and
+    // classifyPaths, which only touch the paths phase 1 did not serve
+    if (warp == LINK_WARPS - 1 && ((processed >> lane) & 1u)) emit(lane, cand, 1);
+    if (tid == 0) n_phase1 += __popc(processed);
     CLS_PROF(5);
     if (__popc(processed) == D) return;  // :137
 
