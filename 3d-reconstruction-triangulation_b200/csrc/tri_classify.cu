@@ -286,9 +286,10 @@ enumerate_kernel(const __grid_constant__ DltRig<double> dlt, const __grid_consta
 //     128-leaf blocks in registers; a round finds the first leaf of the whole list that misses the used mask (REDUX.MIN
 //     in the warp, atomicMin across the warps, one block barrier), adds its mask to the used mask and strikes the leaves
 //     it collides with.
-//   classifyPaths (:262-332) on warp 0, lane <-> kept combination: tail distances, nearest open path, then the ordered
+//   classifyPaths (:262-332) on one warp (LINK_SERIAL_WARP), lane <-> kept combination: tail distances, nearest open path, then the ordered
 //     assignment by warp-wide minimum extraction (three REDUX operations per step).  Phase 1's pushes run on the last warp
-//     meanwhile: phase 2 and classifyPaths only touch the paths phase 1 did not serve.
+//     meanwhile: phase 2 and classifyPaths only touch the paths phase 1 did not serve.  (Both are warps that usually have
+//     no path of their own to gate.)
 // The kernel is one latency-bound CTA per sequence: what a frame costs is the length of its chain of dependent
 // instructions (a lone warp issues one every 6-10 cycles here: LDS 30, VOTE 28, SHFL 33, REDUX 50 cycles, tools/micro/redux.cu;
 // instruction fetch is not the limit, tools/micro/ifetch.cu).  Round 1 ran it with ~15 block barriers per frame, the pixel rays
@@ -350,6 +351,7 @@ constexpr int LINK_WARPS = TRI_LINK_WARPS;  // >= TRI_MAX_DRONES
 constexpr int LINK_THREADS = 32 * LINK_WARPS;
 constexpr int LINK_BLOCKS = 2 * LINK_WARPS;  // phase 2 holds the first LINK_BLOCKS x 128 leaves of a frame in registers, two blocks per warp (the rest is walked in place)
 constexpr int LINK_NONE = 0x7fffffff;
+constexpr int LINK_SERIAL_WARP = LINK_WARPS - 2;  // runs phase 2's bookkeeping and classifyPaths: a warp that usually has no path to gate (S09_D6 4.47 -> 4.43 us per frame against warp 0)
 
 // ALL_STAGED: no frame of the batch has more than MAX_LEAVES leaves (the host knows the longest list), so the body that reads
 // leaves from global memory is not even compiled in -- the kernel is latency-bound on one SM and its instruction footprint counts.
@@ -389,7 +391,7 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __restr
     const double* last = S.tail[tid][min(max(S.n[tid], 1), PATH_TAIL) - 1];
     s_lastf[tid][0] = (float)last[0]; s_lastf[tid][1] = (float)last[1]; s_lastf[tid][2] = (float)last[2];
   }
-  u64 n_phase1 = 0, n_phase2 = 0;  // thread 0
+  u64 n_phase1 = 0, n_phase2 = 0;  // lane 0 of the serial warp
   bool overflow_final = false;
 #ifdef TRI_TUNING
   u64 prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -646,7 +648,7 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __restr
     // phase 1's pushes, all confirmed paths at once (lane <-> path), on the last warp: warp 0 goes straight on to phase 2 and
     // classifyPaths, which only touch the paths phase 1 did not serve
     if (warp == LINK_WARPS - 1 && ((processed >> lane) & 1u)) emit(lane, cand, 1);
-    if (tid == 0) n_phase1 += __popc(processed);
+    if (tid == 32 * LINK_SERIAL_WARP) n_phase1 += __popc(processed);
     CLS_PROF(5);
     if (__popc(processed) == D) return;  // :137
 
@@ -703,11 +705,11 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __restr
             for (int w = 0; w < W; w++) clash = clash || (m[j][u][w] & mj[w]);
             if (clash) ok &= ~(1u << (4 * j + u));  // (the pick collides with itself)
           }
-        if (n_fin < LINK_MAX_FINAL) { if (tid == 0) s_fin_idx[n_fin] = pick; n_fin++; }
+        if (n_fin < LINK_MAX_FINAL) { if (tid == 32 * LINK_SERIAL_WARP) s_fin_idx[n_fin] = pick; n_fin++; }
         else overflow_final = true;
       }
     }
-    if (warp != 0) return;
+    if (warp != LINK_SERIAL_WARP) return;
     // (leaves beyond the blocks held in registers: walked in place, 32 at a time)
     for (int i0 = 128 * LINK_BLOCKS; i0 < L; i0 += 32) {
       const int li = i0 + lane < L ? i0 + lane : -1;
@@ -831,7 +833,7 @@ link_kernel(const __grid_constant__ RayRig ray, ClsParams p, const int2* __restr
 #ifdef TRI_TUNING
   if (tid == 0) for (int q = 0; q < 12; q++) atomicAdd(&ctr->prof[q], prof_acc[q]);
 #endif
-  if (tid == 0) {
+  if (tid == 32 * LINK_SERIAL_WARP) {
     atomicAdd(&ctr->phase1, n_phase1); atomicAdd(&ctr->phase2, n_phase2);
     if (overflow_final) atomicExch(&ctr->overflow_final, 1);
   }
