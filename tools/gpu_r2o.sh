@@ -1,4 +1,6 @@
 #!/bin/bash
 cd "$GRAFT_REPO_ROOT"
-timeout 600 python tools/link_iter.py --frames 100000 2>&1 | awk '!seen[substr($0,1,30)]++'
-timeout 2400 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+for lib in E5 E6 E8; do
+echo "== $lib"; TRI_B200_LIB=$PWD/3d-reconstruction-triangulation_b200/libtri_b200_$lib.so timeout 600 python tools/link_iter.py --frames 100000 2>&1 | awk '!seen[substr($0,1,30)]++' | grep -v golden | tail -3
+done
+echo "== current"; timeout 600 python tools/link_iter.py --frames 100000 2>&1 | awk '!seen[substr($0,1,30)]++' | grep -v golden | tail -3
