@@ -198,7 +198,16 @@ __device__ bool lazy_best_leaf(const DltRig<double>& dlt, const RayRig& ray, con
     const int cnt = sh.count[l] + (k ? 1 : 0);
     // bound: taking a detection on every remaining camera that has an allowed one
     // (the other warps' best count prunes too: a branch is only dropped when it cannot even tie, so what is found does not depend on timing)
-    if (cnt + sh.potential[l + 1] < max(max(sh.best_count, incumbent ? *reinterpret_cast<volatile int*>(incumbent) : 0), MIN_CAMERAS)) { __syncwarp(); continue; }
+    const int inc = incumbent ? *reinterpret_cast<volatile int*>(incumbent) : 0;
+    if (cnt + sh.potential[l + 1] < max(max(sh.best_count, inc), MIN_CAMERAS)) { __syncwarp(); continue; }
+    // second bound (matrix mode): a branch that can only tie the best count K must beat the best error.  The sum of squared
+    // residuals at the least-squares point cannot shrink when rows are added, so every leaf below this child has
+    // error^2 >= (child error)^2 cnt / K.  Only clear cases are dropped -- 1e-6 relative and 1e-10 absolute cover the rounding
+    // of the sums, which are not computed at the exact minimiser --, so what the search returns is unchanged.
+    if (p.solver == 0 && sh.best_count >= MIN_CAMERAS && inc <= sh.best_count && cnt + sh.potential[l + 1] == sh.best_count) {
+      const double ec = k ? sh.c_err[l][k] : sh.err[l];
+      if (ec * ec * (double)cnt > sh.best_err * sh.best_err * (double)sh.best_count * (1.0 + 1e-6) + 1e-10) { __syncwarp(); continue; }
+    }
     if (lane == 0) {
       sh.choice[l] = (unsigned char)k;
       sh.count[l + 1] = cnt;
