@@ -192,7 +192,16 @@ __device__ bool lazy_best_leaf(const DltRig<double>& dlt, const RayRig& ray, con
     // ---- the next child of level l: detections first (they lead to the leaves with the fewest unused cameras), "none" last ----
     const unsigned todo = sh.todo[l];
     if (!todo) { l--; expanded = true; continue; }  // back to the parent, whose todo mask is still in shared memory
-    const int k = 31 - __clz(todo);  // highest bit: detection k - 1 (k = 0: none)
+    // (the order of the visits does not change what the search returns -- ties are settled by the choices themselves -- but
+    // visiting the child with the smallest error first finds a good leaf early, and the error bound below then cuts the rest)
+    int k = 0;  // 0: none
+    if (todo & ~1u) {
+      const bool mine = lane >= 1 && lane < LZ_SLOTS && (todo >> lane & 1u);
+      const u64 key = mine ? (u64)__double_as_longlong(sh.c_err[l][lane]) : ~0ull;  // errors are >= +0: their bits order like the values
+      const unsigned hi = (unsigned)(key >> 32), mh = __reduce_min_sync(0xffffffffu, hi);
+      const unsigned lo = hi == mh ? (unsigned)key : 0xffffffffu, ml = __reduce_min_sync(0xffffffffu, lo);
+      k = 31 - __clz(__ballot_sync(0xffffffffu, mine && hi == mh && lo == ml));  // (equal errors: the highest detection, as before)
+    }
     __syncwarp();
     if (lane == 0) sh.todo[l] = todo & ~(1u << k);
     const int cnt = sh.count[l] + (k ? 1 : 0);
